@@ -1,0 +1,425 @@
+// extern "C" entry points of include/mlt_attn.h: argument validation, workspace carving and
+// dispatch to the SIMT (simt_kernels.cu) or tcgen05 (tc_*.cu) kernels.  No allocation, no
+// retained pointers, no exceptions across the boundary.
+
+#include "../../include/mlt_attn.h"
+
+#include "mlt_common.cuh"
+#include "tc_api.cuh"
+
+namespace {
+
+using namespace mlt;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+inline T4 to_t4(const mlt_tensor4& t) { return T4{t.ptr, t.stride_b, t.stride_l, t.stride_h}; }
+
+inline int elem_size(int dtype) { return dtype == MLT_F32 ? 4 : 2; }
+
+int check_t4(const mlt_tensor4& t, int dtype, int d) {
+  if (t.ptr == nullptr) return MLT_ERR_NULL;
+  // kernels move 4 elements (SIMT) / 16 bytes (tcgen05) per access
+  if (t.stride_b % 4 || t.stride_l % 4 || t.stride_h % 4) return MLT_ERR_STRIDE;
+  if (reinterpret_cast<uintptr_t>(t.ptr) % 16) return MLT_ERR_STRIDE;
+  if (t.stride_h < d && t.stride_h != 0) return MLT_ERR_STRIDE;
+  (void)dtype;
+  return MLT_OK;
+}
+
+#define MLT_TRY(expr)            \
+  do {                           \
+    int _e = (expr);             \
+    if (_e != MLT_OK) return _e; \
+  } while (0)
+#define MLT_CUDA(expr)                  \
+  do {                                  \
+    cudaError_t _e = (expr);            \
+    if (_e != cudaSuccess) return (int)_e; \
+  } while (0)
+
+struct RowWs {  // backward workspace of one row set
+  float* delta;
+  float* allrel;
+  float* dallrel;
+  float* partial;
+  float* partial_bias;
+};
+
+size_t row_ws_bytes(int B, int H, int len, int R, int d) {
+  const int nchunk = simt_table_grad_chunks(len);
+  size_t n = 0;
+  n += align_up(sizeof(float) * (size_t)B * H * len);
+  n += 2 * align_up(sizeof(float) * (size_t)B * H * len * (R > 0 ? R : 1));
+  n += align_up(sizeof(float) * (size_t)B * nchunk * H * (R > 0 ? R : 1) * d);
+  n += align_up(sizeof(float) * (size_t)B * nchunk * H * (R > 0 ? R : 1));
+  return n;
+}
+
+RowWs carve_row_ws(char*& p, int B, int H, int len, int R, int d) {
+  const int nchunk = simt_table_grad_chunks(len);
+  const int r1 = R > 0 ? R : 1;
+  RowWs w;
+  w.delta = reinterpret_cast<float*>(p);
+  p += align_up(sizeof(float) * (size_t)B * H * len);
+  w.allrel = reinterpret_cast<float*>(p);
+  p += align_up(sizeof(float) * (size_t)B * H * len * r1);
+  w.dallrel = reinterpret_cast<float*>(p);
+  p += align_up(sizeof(float) * (size_t)B * H * len * r1);
+  w.partial = reinterpret_cast<float*>(p);
+  p += align_up(sizeof(float) * (size_t)B * nchunk * H * r1 * d);
+  w.partial_bias = reinterpret_cast<float*>(p);
+  p += align_up(sizeof(float) * (size_t)B * nchunk * H * r1);
+  return w;
+}
+
+Side explicit_side(const int32_t* mask, const int32_t* ids, int lq, int width) {
+  Side s{};
+  s.mask_rule = mask ? MR_EXPLICIT : MR_NONE;
+  s.id_rule = ids ? IDR_EXPLICIT : IDR_NONE;
+  s.mask = mask;
+  s.ids = ids;
+  s.sb = (int64_t)lq * width;
+  s.sq = width;
+  return s;
+}
+
+// ---- contract (A) ------------------------------------------------------------------------
+
+int validate_dense(const mlt_dense_params* p) {
+  if (!p) return MLT_ERR_NULL;
+  if (p->abi_version != MLT_ABI_VERSION) return MLT_ERR_UNSUPPORTED;
+  if (p->dtype != MLT_F32 && p->dtype != MLT_BF16) return MLT_ERR_DTYPE;
+  if (p->B <= 0 || p->Lq <= 0 || p->Lk <= 0 || p->H <= 0 || p->d <= 0 || p->R < 0) return MLT_ERR_SHAPE;
+  if (p->R > 64) return MLT_ERR_UNSUPPORTED;
+  if (!simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
+  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  MLT_TRY(check_t4(p->q, p->dtype, p->d));
+  MLT_TRY(check_t4(p->k, p->dtype, p->d));
+  MLT_TRY(check_t4(p->v, p->dtype, p->d));
+  MLT_TRY(check_t4(p->out, p->dtype, p->d));
+  if (!p->stats) return MLT_ERR_NULL;
+  if ((p->tables.emb == nullptr) != (p->tables.bias == nullptr)) return MLT_ERR_NULL;
+  if (p->R > 0 && !p->tables.emb) return MLT_ERR_NULL;
+  if (p->side_mode == MLT_SIDE_COMPACT) {
+    if (!p->q_example_ids || !p->k_example_ids) return MLT_ERR_NULL;
+    if (p->id_layout.max_distance < 0 || p->id_layout.num_patch_per_row < 0) return MLT_ERR_SHAPE;
+    if (p->id_layout.num_patch_per_row > 0 && p->id_layout.num_core_layers <= 0) return MLT_ERR_SHAPE;
+  } else if (p->side_mode != MLT_SIDE_EXPLICIT) {
+    return MLT_ERR_UNSUPPORTED;
+  }
+  return MLT_OK;
+}
+
+Side dense_side(const mlt_dense_params* p) {
+  if (p->side_mode == MLT_SIDE_EXPLICIT) {
+    Side s = explicit_side(p->att_mask, p->R > 0 ? p->relative_att_ids : nullptr, p->Lq, p->Lk);
+    return s;
+  }
+  Side s{};
+  s.mask_rule = MR_EXAMPLE_ID;
+  s.q_eid = p->q_example_ids;
+  s.k_eid = p->k_example_ids;
+  s.q_len = p->Lq;
+  s.k_len = p->Lk;
+  s.max_distance = p->id_layout.max_distance;
+  s.npr = p->id_layout.num_patch_per_row;
+  s.core = p->id_layout.num_core_layers;
+  s.id_rule = p->R == 0 ? IDR_NONE : (s.npr > 0 ? IDR_2D : IDR_1D);
+  return s;
+}
+
+RowSet dense_rows(const mlt_dense_params* p) {
+  return RowSet{to_t4(p->q), p->Lq, p->tables.emb, p->tables.bias, p->R};
+}
+
+// ---- contract (B) ------------------------------------------------------------------------
+
+int validate_gl(const mlt_gl_params* p) {
+  if (!p) return MLT_ERR_NULL;
+  if (p->abi_version != MLT_ABI_VERSION) return MLT_ERR_UNSUPPORTED;
+  if (p->dtype != MLT_F32 && p->dtype != MLT_BF16) return MLT_ERR_DTYPE;
+  if (p->B <= 0 || p->L <= 0 || p->G <= 0 || p->H <= 0 || p->d <= 0 || p->R < 0 ||
+      p->local_radius < 1)
+    return MLT_ERR_SHAPE;
+  if (p->R > 64) return MLT_ERR_UNSUPPORTED;
+  if (!simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
+  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  const mlt_tensor4* ts[] = {&p->long_q, &p->long_k, &p->long_v, &p->global_q, &p->global_k,
+                             &p->global_v, &p->long_out, &p->global_out};
+  for (const mlt_tensor4* t : ts) MLT_TRY(check_t4(*t, p->dtype, p->d));
+  if (!p->long_stats || !p->global_stats) return MLT_ERR_NULL;
+  const mlt_rel_tables* tb[] = {&p->long_tables, &p->global_tables};
+  for (const mlt_rel_tables* t : tb) {
+    if ((t->emb == nullptr) != (t->bias == nullptr)) return MLT_ERR_NULL;
+    if (p->R > 0 && !t->emb) return MLT_ERR_NULL;
+  }
+  if (p->side_mode == MLT_SIDE_COMPACT) {
+    if (!p->long_example_ids || !p->global_example_ids) return MLT_ERR_NULL;
+    if (p->R > 0 && !p->sentence_ids) return MLT_ERR_NULL;
+    if (p->max_distance < 0) return MLT_ERR_SHAPE;
+  } else if (p->side_mode != MLT_SIDE_EXPLICIT) {
+    return MLT_ERR_UNSUPPORTED;
+  }
+  return MLT_OK;
+}
+
+enum GlBlock { L2L, L2G, G2G, G2L };
+
+Side gl_side(const mlt_gl_params* p, GlBlock blk) {
+  const int W = 2 * p->local_radius + 1;
+  if (p->side_mode == MLT_SIDE_EXPLICIT) {
+    const bool rel = p->R > 0;
+    switch (blk) {
+      case L2L: return explicit_side(p->l2l_att_mask, rel ? p->l2l_relative_att_ids : nullptr, p->L, W);
+      case L2G: return explicit_side(p->l2g_att_mask, rel ? p->l2g_relative_att_ids : nullptr, p->L, p->G);
+      case G2G: return explicit_side(p->g2g_att_mask, rel ? p->g2g_relative_att_ids : nullptr, p->G, p->G);
+      default:  return explicit_side(p->g2l_att_mask, rel ? p->g2l_relative_att_ids : nullptr, p->G, p->L);
+    }
+  }
+  Side s{};
+  s.mask_rule = MR_EXAMPLE_ID;
+  s.max_distance = p->max_distance;
+  s.sent = p->sentence_ids;
+  s.sent_len = p->L;
+  const bool q_long = (blk == L2L || blk == L2G);
+  const bool k_long = (blk == L2L || blk == G2L);
+  s.q_eid = q_long ? p->long_example_ids : p->global_example_ids;
+  s.k_eid = k_long ? p->long_example_ids : p->global_example_ids;
+  s.q_len = q_long ? p->L : p->G;
+  s.k_len = k_long ? p->L : p->G;
+  if (p->R == 0) {
+    s.id_rule = IDR_NONE;
+  } else {
+    s.id_rule = (blk == L2L || blk == G2G) ? IDR_1D : (blk == L2G ? IDR_CROSS_QSENT : IDR_CROSS_KSENT);
+  }
+  return s;
+}
+
+KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, int radius,
+                const Side& side) {
+  KeySeg s{};
+  s.k = to_t4(k);
+  s.v = to_t4(v);
+  s.len = len;
+  s.band = band;
+  s.radius = radius;
+  s.side = side;
+  return s;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int mlt_abi_version(void) { return MLT_ABI_VERSION; }
+
+const char* mlt_strerror(int code) {
+  switch (code) {
+    case MLT_OK: return "ok";
+    case MLT_ERR_NULL: return "mlt: required pointer is NULL";
+    case MLT_ERR_SHAPE: return "mlt: non-positive or inconsistent dimension";
+    case MLT_ERR_UNSUPPORTED: return "mlt: unsupported configuration for this build";
+    case MLT_ERR_STRIDE: return "mlt: stride/alignment requirement violated (4 elements, 16 bytes)";
+    case MLT_ERR_WORKSPACE: return "mlt: workspace missing or too small";
+    case MLT_ERR_DTYPE: return "mlt: unknown dtype";
+    case MLT_ERR_DROPOUT: return "mlt: attention-probability dropout is not implemented (dropout_p must be 0)";
+    default:
+      if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+      return "mlt: unknown error";
+  }
+}
+
+int mlt_dense_uses_tensor_cores(const mlt_dense_params* p) {
+  if (!p || p->impl == MLT_IMPL_SIMT) return 0;
+  return mlt::tc_dense_supported(p) ? 1 : 0;
+}
+int mlt_gl_uses_tensor_cores(const mlt_gl_params* p) {
+  if (!p || p->impl == MLT_IMPL_SIMT) return 0;
+  return mlt::tc_gl_supported(p) ? 1 : 0;
+}
+
+size_t mlt_dense_workspace_bytes(const mlt_dense_params* p, int bwd) {
+  if (!p) return 0;
+  size_t n = kAlign;
+  if (bwd) n += row_ws_bytes(p->B, p->H, p->Lq, p->R, p->d);
+  n += mlt::tc_dense_workspace_bytes(p, bwd);
+  return n;
+}
+
+size_t mlt_gl_workspace_bytes(const mlt_gl_params* p, int bwd) {
+  if (!p) return 0;
+  size_t n = kAlign;
+  if (bwd) n += row_ws_bytes(p->B, p->H, p->L, p->R, p->d) + row_ws_bytes(p->B, p->H, p->G, p->R, p->d);
+  n += mlt::tc_gl_workspace_bytes(p, bwd);
+  return n;
+}
+
+int mlt_dense_rel_attn_fwd(const mlt_dense_params* p, void* cuda_stream) {
+  MLT_TRY(validate_dense(p));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (p->impl != MLT_IMPL_SIMT && mlt::tc_dense_supported(p)) return mlt::tc_dense_fwd(p, st);
+  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
+  FwdArgs a{};
+  a.rows = dense_rows(p);
+  a.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, dense_side(p));
+  a.nseg = 1;
+  a.out = to_t4(p->out);
+  a.stats = p->stats;
+  a.B = p->B;
+  a.H = p->H;
+  a.scale = p->scale;
+  a.neg = p->neg;
+  MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
+  return MLT_OK;
+}
+
+int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, void* cuda_stream) {
+  MLT_TRY(validate_dense(p));
+  if (!g) return MLT_ERR_NULL;
+  MLT_TRY(check_t4(g->d_out, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_q, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_k, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_v, p->dtype, p->d));
+  if (p->R > 0 && (!g->d_emb || !g->d_bias)) return MLT_ERR_NULL;
+  if (!p->workspace || p->workspace_bytes < mlt_dense_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (p->impl != MLT_IMPL_SIMT && mlt::tc_dense_supported(p)) return mlt::tc_dense_bwd(p, g, st);
+  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
+  char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
+  RowWs ws = carve_row_ws(wp, p->B, p->H, p->Lq, p->R, p->d);
+  const Side side = dense_side(p);
+
+  BwdQArgs q{};
+  q.rows = dense_rows(p);
+  q.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, side);
+  q.nseg = 1;
+  q.out = to_t4(p->out);
+  q.d_out = to_t4(g->d_out);
+  q.d_q = to_t4(g->d_q);
+  q.stats = p->stats;
+  q.delta = ws.delta;
+  q.allrel = ws.allrel;
+  q.dallrel = ws.dallrel;
+  q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_q(q, p->dtype, p->d, st));
+
+  BwdKVArgs kv{};
+  kv.k = to_t4(p->k); kv.v = to_t4(p->v); kv.d_k = to_t4(g->d_k); kv.d_v = to_t4(g->d_v);
+  kv.len = p->Lk;
+  kv.src[0] = QuerySource{dense_rows(p), to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, side};
+  kv.nsrc = 1;
+  kv.B = p->B; kv.H = p->H; kv.scale = p->scale; kv.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_kv(kv, p->dtype, p->d, st));
+
+  if (p->R > 0) {
+    TableGradArgs t{to_t4(p->q), p->Lq, ws.dallrel, ws.partial, ws.partial_bias, g->d_emb, g->d_bias,
+                    p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->Lq), p->scale};
+    MLT_CUDA(simt_launch_table_grad(t, p->dtype, st));
+  }
+  return MLT_OK;
+}
+
+int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
+  MLT_TRY(validate_gl(p));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (p->impl != MLT_IMPL_SIMT && mlt::tc_gl_supported(p)) return mlt::tc_gl_fwd(p, st);
+  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
+  // long rows: band(l2l) (+) dense(l2g), long tables
+  FwdArgs a{};
+  a.rows = RowSet{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
+  a.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, gl_side(p, L2L));
+  a.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, L2G));
+  a.nseg = 2;
+  a.out = to_t4(p->long_out);
+  a.stats = p->long_stats;
+  a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
+  // global rows: dense(g2g) (+) dense(g2l), global tables
+  FwdArgs g{};
+  g.rows = RowSet{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
+  g.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, G2G));
+  g.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, gl_side(p, G2L));
+  g.nseg = 2;
+  g.out = to_t4(p->global_out);
+  g.stats = p->global_stats;
+  g.B = p->B; g.H = p->H; g.scale = p->scale; g.neg = p->neg;
+  MLT_CUDA(simt_launch_fwd(g, p->dtype, p->d, st));
+  return MLT_OK;
+}
+
+int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_stream) {
+  MLT_TRY(validate_gl(p));
+  if (!g) return MLT_ERR_NULL;
+  const mlt_tensor4* ts[] = {&g->d_long_out, &g->d_global_out, &g->d_long_q, &g->d_long_k,
+                             &g->d_long_v, &g->d_global_q, &g->d_global_k, &g->d_global_v};
+  for (const mlt_tensor4* t : ts) MLT_TRY(check_t4(*t, p->dtype, p->d));
+  if (p->R > 0 && (!g->d_long_emb || !g->d_long_bias || !g->d_global_emb || !g->d_global_bias))
+    return MLT_ERR_NULL;
+  if (!p->workspace || p->workspace_bytes < mlt_gl_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (p->impl != MLT_IMPL_SIMT && mlt::tc_gl_supported(p)) return mlt::tc_gl_bwd(p, g, st);
+  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
+  char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
+  RowWs wl = carve_row_ws(wp, p->B, p->H, p->L, p->R, p->d);
+  RowWs wg = carve_row_ws(wp, p->B, p->H, p->G, p->R, p->d);
+  const RowSet long_rows{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
+  const RowSet glob_rows{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
+  const Side s_l2l = gl_side(p, L2L), s_l2g = gl_side(p, L2G), s_g2g = gl_side(p, G2G),
+             s_g2l = gl_side(p, G2L);
+
+  // 1. long rows: dq + dallrel
+  BwdQArgs ql{};
+  ql.rows = long_rows;
+  ql.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, s_l2l);
+  ql.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_l2g);
+  ql.nseg = 2;
+  ql.out = to_t4(p->long_out); ql.d_out = to_t4(g->d_long_out); ql.d_q = to_t4(g->d_long_q);
+  ql.stats = p->long_stats; ql.delta = wl.delta; ql.allrel = wl.allrel; ql.dallrel = wl.dallrel;
+  ql.B = p->B; ql.H = p->H; ql.scale = p->scale; ql.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_q(ql, p->dtype, p->d, st));
+  // 2. global rows
+  BwdQArgs qg{};
+  qg.rows = glob_rows;
+  qg.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_g2g);
+  qg.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, s_g2l);
+  qg.nseg = 2;
+  qg.out = to_t4(p->global_out); qg.d_out = to_t4(g->d_global_out); qg.d_q = to_t4(g->d_global_q);
+  qg.stats = p->global_stats; qg.delta = wg.delta; qg.allrel = wg.allrel; qg.dallrel = wg.dallrel;
+  qg.B = p->B; qg.H = p->H; qg.scale = p->scale; qg.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_q(qg, p->dtype, p->d, st));
+  // 3. long keys: from long queries (band, l2l) and global queries (dense, g2l)
+  BwdKVArgs kl{};
+  kl.k = to_t4(p->long_k); kl.v = to_t4(p->long_v); kl.d_k = to_t4(g->d_long_k); kl.d_v = to_t4(g->d_long_v);
+  kl.len = p->L;
+  kl.src[0] = QuerySource{long_rows, to_t4(g->d_long_out), p->long_stats, wl.delta, wl.allrel, 1,
+                          p->local_radius, s_l2l};
+  kl.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0,
+                          s_g2l};
+  kl.nsrc = 2;
+  kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_kv(kl, p->dtype, p->d, st));
+  // 4. global keys: from long queries (dense, l2g) and global queries (dense, g2g)
+  BwdKVArgs kg{};
+  kg.k = to_t4(p->global_k); kg.v = to_t4(p->global_v); kg.d_k = to_t4(g->d_global_k); kg.d_v = to_t4(g->d_global_v);
+  kg.len = p->G;
+  kg.src[0] = QuerySource{long_rows, to_t4(g->d_long_out), p->long_stats, wl.delta, wl.allrel, 0, 0, s_l2g};
+  kg.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0, s_g2g};
+  kg.nsrc = 2;
+  kg.B = p->B; kg.H = p->H; kg.scale = p->scale; kg.neg = p->neg;
+  MLT_CUDA(simt_launch_bwd_kv(kg, p->dtype, p->d, st));
+  // 5./6. relative tables
+  if (p->R > 0) {
+    TableGradArgs tl{to_t4(p->long_q), p->L, wl.dallrel, wl.partial, wl.partial_bias, g->d_long_emb,
+                     g->d_long_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};
+    MLT_CUDA(simt_launch_table_grad(tl, p->dtype, st));
+    TableGradArgs tg{to_t4(p->global_q), p->G, wg.dallrel, wg.partial, wg.partial_bias, g->d_global_emb,
+                     g->d_global_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->G), p->scale};
+    MLT_CUDA(simt_launch_table_grad(tg, p->dtype, st));
+  }
+  return MLT_OK;
+}
+
+}  // extern "C"
