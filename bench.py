@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the global-local attention hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of ETC's path
+
+A "step" is one forward + backward pass of one layer's global-local attention core over one
+batch of synthetic input: workload ``c3_4096`` = B 16 x L 4096 long
+tokens + G 256 global tokens, H 12, d 64, local_radius 64, R 32, D 12, bf16, masks / ids built
+in-kernel from compact descriptors.  tokens := B*L per step.  With N > 1 every rank processes
+the same per-GPU batch on its own GPU (batch x head units sharded, no data-path collective):
+weak scaling, value = N * tokens / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'global_local_attn_fwd_bwd_tokens_per_s'
+UNIT = 'tokens/s'
+WORKLOAD = 'c3_4096'
+NAMES = ('long_q', 'long_k', 'long_v', 'global_q', 'global_k', 'global_v', 'long_emb',
+         'long_bias', 'global_emb', 'global_bias')
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    d = json.load(open(path))
+    return dict(hbm_gbs=d['hbm_gbs'], tflops_burst=d['bf16_tflops'],
+                tflops_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                source='measured (MEASURED_PEAKS.json)')
+  return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0,
+              source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  def __init__(self, index):
+    self.index = index
+    self.rows = []
+    self.proc = None
+
+  def start(self):
+    q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits',
+           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if not self.proc:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for r in self.rows:
+      if len(r) < 7:
+        continue
+      try:
+        sm.append(float(r[0]))
+        mx.append(float(r[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, r[3:7]):
+        if v.lower().startswith('active'):
+          reasons.add(n)
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU restatement (the reference's algorithm; oracle/blocked_etc.py)
+
+
+def cpu_blocked_step(shape, x, side):
+  """One fwd+bwd of ETC's blocked global-local attention on the host (fp32, autograd)."""
+  import torch
+  from oracle import blocked_etc as be
+  leaves = [x[n].float().requires_grad_() for n in NAMES]
+  lo, go = be.fused_global_local_blocked(*leaves[:6], side, (leaves[6], leaves[7]),
+                                         (leaves[8], leaves[9]), shape.local_radius)
+  ((lo * x['d_long_out'].float()).sum() + (go * x['d_global_out'].float()).sum()).backward()
+  return lo
+
+
+def cpu_sample_inputs(workload_shape, sample_batch):
+  import dataclasses
+  import torch
+  from mlt_b200 import feature_utils as fu
+  from mlt_b200 import synthetic
+  shape = dataclasses.replace(workload_shape, batch=sample_batch)
+  x = synthetic.make_inputs(shape, seed=1234 + 4)
+  side = fu.make_global_local_transformer_side_inputs_from_example_ids(
+      x['long_example_ids'], x['global_example_ids'], x['sentence_ids'], shape.local_radius,
+      shape.max_distance).to_dict()
+  return shape, x, side
+
+
+def time_cpu(workload_shape, steps, warmup, sample_batch=1):
+  import torch
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  shape, x, side = cpu_sample_inputs(workload_shape, sample_batch)
+  for _ in range(warmup):
+    cpu_blocked_step(shape, x, side)
+  times = []
+  for _ in range(steps):
+    t0 = time.perf_counter()
+    cpu_blocked_step(shape, x, side)
+    times.append(time.perf_counter() - t0)
+  sec = sum(times) / len(times)
+  return dict(tokens_per_s=shape.tokens / sec, sec_per_step=sec, cores=cores,
+              sample=(f'{WORKLOAD} with batch {sample_batch} (= {shape.tokens} long tokens per '
+                      f'fwd+bwd; full workload batch {workload_shape.batch}), fp32, ETC blocked '
+                      f'algorithm restated in PyTorch-CPU (oracle/blocked_etc.py), '
+                      f'{steps} timed + {warmup} warm-up calls'))
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import mlt_b200  # noqa: F401
+  from mlt_b200 import synthetic
+  _, wshape = synthetic.CONFIGS[WORKLOAD]
+  steps = max(1, min(args.steps, 30))
+  warm = max(1, min(args.warmup, 3))
+  r = time_cpu(wshape, steps, warm)
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': r['tokens_per_s'], 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+      'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'note': 'TensorFlow/etcmodel cannot run in this image; '
+                 'this arm times the CPU restatement of the same algorithm (kind=port)'},
+      'cpu_baseline': {'value': r['tokens_per_s'], 'unit': UNIT, 'cores': r['cores'],
+                       'kind': 'port', 'sample': r['sample']},
+      'e2e': {'value': r['tokens_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA path
+
+
+def run_cuda(args):
+  import torch
+  import torch.distributed as dist
+  import mlt_b200  # noqa: F401
+  from mlt_b200 import _lib, ops, synthetic
+  from mlt_b200.feature_utils import CompactSideInputs
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); '
+                     'use --impl reference for the CPU arm')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  _lib.load()
+
+  seed_off, shape = synthetic.CONFIGS[WORKLOAD]
+  dtype = torch.bfloat16
+  host = synthetic.make_inputs(shape, seed=1234 + seed_off + rank, dtype=dtype, pin=True)
+  x = {k: (v.to(dev) if hasattr(v, 'to') else v) for k, v in host.items()}
+  compact = CompactSideInputs(x['long_example_ids'], x['global_example_ids'], x['sentence_ids'],
+                              shape.max_distance)
+  leaves = [x[n].requires_grad_() for n in NAMES]
+
+  def step():
+    for t in leaves:
+      t.grad = None
+    lo, go = ops.global_local_attention(*leaves, local_radius=shape.local_radius, side=compact,
+                                        impl=args.kernel)
+    torch.autograd.backward([lo, go], [x['d_long_out'], x['d_global_out']])
+    return lo
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+
+  # ---- timed region: exactly K steps, device-timed, inputs resident in HBM ----------------
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  launches0 = _lib.launch_count()
+  beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  wall0 = time.perf_counter()
+  beg.record()
+  for _ in range(args.steps):
+    step()
+  end.record()
+  barrier()
+  wall = time.perf_counter() - wall0
+  launches = _lib.launch_count() - launches0
+  clocks = sampler.stop()
+  ms = beg.elapsed_time(end)
+  t = torch.tensor([ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = t.item()
+  ms_per_step = ms_total / args.steps
+  tokens_per_s = world * shape.tokens / (ms_per_step * 1e-3)
+
+  # ---- end-to-end: host (pinned) buffers in, results back to the host, every step ---------
+  h2d_names = NAMES[:6] + ('d_long_out', 'd_global_out', 'long_example_ids',
+                           'global_example_ids', 'sentence_ids')
+  pinned = {n: (host[n] if host[n].is_pinned() else host[n].pin_memory()) for n in h2d_names}
+  tables = [x[n] for n in NAMES[6:]]   # layer weights: resident on the device, as in training
+  out_host = {}
+
+  def e2e_step():
+    d = {n: pinned[n].to(dev, non_blocking=True) for n in h2d_names}
+    lv = [d[n].requires_grad_() for n in NAMES[:6]] + [t_.detach().requires_grad_() for t_ in tables]
+    cs = CompactSideInputs(d['long_example_ids'], d['global_example_ids'], d['sentence_ids'],
+                           shape.max_distance)
+    lo, go = ops.global_local_attention(*lv, local_radius=shape.local_radius, side=cs,
+                                        impl=args.kernel)
+    torch.autograd.backward([lo, go], [d['d_long_out'], d['d_global_out']])
+    res = [lo.detach(), go.detach()] + [t_.grad for t_ in lv]
+    for i, r in enumerate(res):
+      if i not in out_host:
+        out_host[i] = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+      out_host[i].copy_(r, non_blocking=True)
+    return res
+
+  e2e_steps = max(1, min(args.steps, 5))
+  e2e_step()
+  barrier()
+  eb, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  w0 = time.perf_counter()
+  eb.record()
+  for _ in range(e2e_steps):
+    e2e_step()
+  ee.record()
+  barrier()
+  e2e_wall = (time.perf_counter() - w0) / e2e_steps
+  e2e_ms = max(eb.elapsed_time(ee) / e2e_steps, e2e_wall * 1e3)
+  t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_tokens_per_s = world * shape.tokens / (t.item() * 1e-3)
+  h2d_bytes = sum(pinned[n].numel() * pinned[n].element_size() for n in h2d_names)
+  d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+
+  # ---- per-kernel timing (CUDA events on the launching stream, inside the library) --------
+  peaks = load_peaks()
+  roofline = None
+  kernels = {}
+  if rank == 0:
+    _lib.profile_enable(True)
+    for _ in range(3):
+      step()
+    torch.cuda.synchronize()
+    recs = _lib.profile_read()
+    _lib.profile_enable(False)
+    for name, kms, flops, nbytes in recs:
+      k = kernels.setdefault(name, dict(ms=0.0, n=0, flops=flops, bytes=nbytes))
+      k['ms'] += kms
+      k['n'] += 1
+    for k in kernels.values():
+      k['ms'] /= k['n']
+    total = sum(k['ms'] for k in kernels.values())
+    top_name, top = max(kernels.items(), key=lambda kv: kv[1]['ms'])
+    achieved = top['flops'] / (top['ms'] * 1e-3) / 1e12
+    peak = peaks['tflops_sustained']
+    roofline = {
+        'bound': 'tensor', 'kernel': top_name, 'achieved': achieved, 'peak': peak,
+        'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+        'peak_source': peaks['source'] + ', sustained bf16 figure (kernel timed inside the step loop)',
+        'kernel_ms': top['ms'], 'kernel_share_of_step': top['ms'] / total if total else None,
+        'algorithmic_flops_per_launch': top['flops'],
+        'step_achieved_tflops': 3 * shape.flops_fwd() / (ms_per_step * 1e-3) / 1e12,
+        'step_frac_of_peak': 3 * shape.flops_fwd() / (ms_per_step * 1e-3) / 1e12 / peak,
+    }
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    r = time_cpu(shape, steps=2, warmup=1)
+    cpu = {'value': r['tokens_per_s'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+           'sample': r['sample']}
+
+  if rank == 0:
+    uses_tc = any(n.startswith('tc_') for n in kernels)
+    line = {
+        'metric': METRIC, 'value': tokens_per_s, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic',
+        'config': {
+            'workload': WORKLOAD, 'batch_per_gpu': shape.batch, 'long_len': shape.long_len,
+            'global_len': shape.global_len, 'heads': shape.heads, 'head_dim': shape.head_dim,
+            'local_radius': shape.local_radius, 'relative_vocab_size': shape.relative_vocab_size,
+            'max_distance': shape.max_distance, 'side_inputs': 'compact (built in-kernel)',
+            'pass': 'fwd+bwd', 'tokens_per_step_per_gpu': shape.tokens,
+            'kernel_path': 'tcgen05' if uses_tc else 'simt',
+            'l2_policy': 'per-step working set (~1.3 GB of q/k/v/out/grads) exceeds the 126 MB L2; no flush',
+            'parallelism': f'batch x head units sharded over {world} GPU(s), no collective',
+        },
+        'clocks': clocks,
+        'e2e': {'value': e2e_tokens_per_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
+                'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': t.item(), 'steps': e2e_steps},
+        'gpu_launches': launches,
+        'roofline': roofline,
+        'kernels_ms': {k: round(v['ms'], 4) for k, v in kernels.items()},
+        'wall_ms_per_step': wall * 1e3 / args.steps,
+    }
+    if cpu is not None:
+      line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_cuda(args)
+
+
+if __name__ == '__main__':
+  main()

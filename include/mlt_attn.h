@@ -230,6 +230,20 @@ MLT_API int mlt_build_gl_side_inputs(const int32_t* long_example_ids, const int3
                              int32_t local_radius, int32_t max_distance, int32_t* const out[8],
                              void* cuda_stream);
 
+/* ---- profiling facility (bench.py; off by default) ------------------------------------ */
+typedef struct {
+  char name[48];   /* kernel role, e.g. "fwd_long_rows" */
+  float ms;        /* CUDA-event duration on the caller's stream */
+  double flops;    /* algorithmic FLOPs of this launch ("Work accounting") */
+  double bytes;    /* algorithmic HBM bytes of this launch */
+} mlt_kernel_time;
+/* When on, every kernel launch is bracketed by events on the caller's stream. */
+MLT_API int mlt_profile_enable(int on);
+/* Synchronises the recorded events, copies up to max_entries records, clears the list. */
+MLT_API int mlt_profile_read(mlt_kernel_time* out, int max_entries);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+MLT_API long long mlt_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,12 +86,18 @@ class GlGrads(C.Structure):
   ]
 
 
+class KernelTime(C.Structure):
+  _fields_ = [('name', C.c_char * 48), ('ms', C.c_float), ('flops', C.c_double),
+              ('bytes', C.c_double)]
+
+
 # Every symbol include/mlt_attn.h declares (checked by tests/test_abi_symbols.py).
 EXPORTS = (
     'mlt_abi_version', 'mlt_strerror', 'mlt_gl_uses_tensor_cores',
     'mlt_dense_uses_tensor_cores', 'mlt_dense_workspace_bytes', 'mlt_gl_workspace_bytes',
     'mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd', 'mlt_gl_attn_bwd',
     'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs',
+    'mlt_profile_enable', 'mlt_profile_read', 'mlt_launch_count',
 )
 
 _lib = None
@@ -136,6 +142,9 @@ def load() -> C.CDLL:
   for name in ('mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd',
                'mlt_gl_attn_bwd', 'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs'):
     getattr(lib, name).restype = C.c_int
+  lib.mlt_profile_enable.argtypes = [C.c_int]
+  lib.mlt_profile_read.argtypes = [C.POINTER(KernelTime), C.c_int]
+  lib.mlt_launch_count.restype = C.c_longlong
   if lib.mlt_abi_version() != MLT_ABI_VERSION:
     raise MltLibraryError('libmlt_attn.so ABI version mismatch; rebuild it.')
   _lib = lib
@@ -146,3 +155,18 @@ def check(code: int, what: str):
   if code != 0:
     msg = load().mlt_strerror(code).decode()
     raise MltLibraryError(f'{what} failed with code {code}: {msg}')
+
+
+def profile_enable(on: bool):
+  load().mlt_profile_enable(1 if on else 0)
+
+
+def profile_read(max_entries: int = 4096):
+  """Returns [(name, ms, flops, bytes)] for every launch since the last read."""
+  buf = (KernelTime * max_entries)()
+  n = load().mlt_profile_read(buf, max_entries)
+  return [(buf[i].name.decode(), buf[i].ms, buf[i].flops, buf[i].bytes) for i in range(n)]
+
+
+def launch_count() -> int:
+  return int(load().mlt_launch_count())

@@ -5,6 +5,7 @@
 #include "../../include/mlt_attn.h"
 
 #include "mlt_common.cuh"
+#include "profile.cuh"
 #include "tc_api.cuh"
 
 namespace {
@@ -17,6 +18,19 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 inline T4 to_t4(const mlt_tensor4& t) { return T4{t.ptr, t.stride_b, t.stride_l, t.stride_h}; }
 
 inline int elem_size(int dtype) { return dtype == MLT_F32 ? 4 : 2; }
+
+// ---- work accounting (algorithmic, DESIGN.md "Work accounting") --------------------------
+inline double band_pairs(double L, double r) {
+  if (L > r) return L * (2 * r + 1) - r * (r + 1);
+  return L * L;
+}
+// forward of one row set: QK^T + PV over `pairs` attended pairs + q.E^T over R ids
+inline double fwd_flops(double bh, double pairs, double d, double R, double lq) {
+  return bh * (4 * d * pairs + 2 * d * R * lq);
+}
+inline double qkv_bytes(double bh, double rows, double d, int dtype, double ntensors) {
+  return bh * rows * d * elem_size(dtype) * ntensors;
+}
 
 int check_t4(const mlt_tensor4& t, int dtype, int d) {
   if (t.ptr == nullptr) return MLT_ERR_NULL;
@@ -272,6 +286,9 @@ int mlt_dense_rel_attn_fwd(const mlt_dense_params* p, void* cuda_stream) {
   a.H = p->H;
   a.scale = p->scale;
   a.neg = p->neg;
+  const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
+  ProfileScope ps("simt_fwd_dense", fwd_flops(bh, pairs, p->d, p->R, p->Lq),
+                  qkv_bytes(bh, 2.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
   MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
   return MLT_OK;
 }
@@ -304,7 +321,12 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   q.allrel = ws.allrel;
   q.dallrel = ws.dallrel;
   q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_q(q, p->dtype, p->d, st));
+  const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
+  {
+    ProfileScope ps("simt_bwd_q_dense", bh * (4.0 * p->d * pairs + 2.0 * p->d * p->R * p->Lq),
+                    qkv_bytes(bh, 4.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_q(q, p->dtype, p->d, st));
+  }
 
   BwdKVArgs kv{};
   kv.k = to_t4(p->k); kv.v = to_t4(p->v); kv.d_k = to_t4(g->d_k); kv.d_v = to_t4(g->d_v);
@@ -312,11 +334,17 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   kv.src[0] = QuerySource{dense_rows(p), to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, side};
   kv.nsrc = 1;
   kv.B = p->B; kv.H = p->H; kv.scale = p->scale; kv.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_kv(kv, p->dtype, p->d, st));
+  {
+    ProfileScope ps("simt_bwd_kv_dense", bh * 4.0 * p->d * pairs,
+                    qkv_bytes(bh, 2.0 * p->Lq + 4.0 * p->Lk, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_kv(kv, p->dtype, p->d, st));
+  }
 
   if (p->R > 0) {
     TableGradArgs t{to_t4(p->q), p->Lq, ws.dallrel, ws.partial, ws.partial_bias, g->d_emb, g->d_bias,
                     p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->Lq), p->scale};
+    ProfileScope ps("simt_table_grad_dense", bh * 2.0 * p->d * p->R * p->Lq,
+                    qkv_bytes(bh, p->Lq, p->d, p->dtype, 1), st, 2);
     MLT_CUDA(simt_launch_table_grad(t, p->dtype, st));
   }
   return MLT_OK;
@@ -336,7 +364,14 @@ int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
   a.out = to_t4(p->long_out);
   a.stats = p->long_stats;
   a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
-  MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
+  const double bh = (double)p->B * p->H;
+  const double pl = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
+  const double pg = (double)p->G * (p->G + p->L);
+  {
+    ProfileScope ps("simt_fwd_long_rows", fwd_flops(bh, pl, p->d, p->R, p->L),
+                    qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
+  }
   // global rows: dense(g2g) (+) dense(g2l), global tables
   FwdArgs g{};
   g.rows = RowSet{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
@@ -346,7 +381,11 @@ int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
   g.out = to_t4(p->global_out);
   g.stats = p->global_stats;
   g.B = p->B; g.H = p->H; g.scale = p->scale; g.neg = p->neg;
-  MLT_CUDA(simt_launch_fwd(g, p->dtype, p->d, st));
+  {
+    ProfileScope ps("simt_fwd_global_rows", fwd_flops(bh, pg, p->d, p->R, p->G),
+                    qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_fwd(g, p->dtype, p->d, st));
+  }
   return MLT_OK;
 }
 
@@ -379,7 +418,14 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   ql.out = to_t4(p->long_out); ql.d_out = to_t4(g->d_long_out); ql.d_q = to_t4(g->d_long_q);
   ql.stats = p->long_stats; ql.delta = wl.delta; ql.allrel = wl.allrel; ql.dallrel = wl.dallrel;
   ql.B = p->B; ql.H = p->H; ql.scale = p->scale; ql.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_q(ql, p->dtype, p->d, st));
+  const double bh = (double)p->B * p->H, dd = p->d, RR = p->R;
+  const double p_l2l = band_pairs(p->L, p->local_radius), p_lg = (double)p->L * p->G,
+               p_gg = (double)p->G * p->G;
+  {
+    ProfileScope ps("simt_bwd_q_long_rows", bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
+                    qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_q(ql, p->dtype, p->d, st));
+  }
   // 2. global rows
   BwdQArgs qg{};
   qg.rows = glob_rows;
@@ -389,7 +435,11 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   qg.out = to_t4(p->global_out); qg.d_out = to_t4(g->d_global_out); qg.d_q = to_t4(g->d_global_q);
   qg.stats = p->global_stats; qg.delta = wg.delta; qg.allrel = wg.allrel; qg.dallrel = wg.dallrel;
   qg.B = p->B; qg.H = p->H; qg.scale = p->scale; qg.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_q(qg, p->dtype, p->d, st));
+  {
+    ProfileScope ps("simt_bwd_q_global_rows", bh * (4 * dd * (p_gg + p_lg) + 2 * dd * RR * p->G),
+                    qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_q(qg, p->dtype, p->d, st));
+  }
   // 3. long keys: from long queries (band, l2l) and global queries (dense, g2l)
   BwdKVArgs kl{};
   kl.k = to_t4(p->long_k); kl.v = to_t4(p->long_v); kl.d_k = to_t4(g->d_long_k); kl.d_v = to_t4(g->d_long_v);
@@ -400,7 +450,11 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                           s_g2l};
   kl.nsrc = 2;
   kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_kv(kl, p->dtype, p->d, st));
+  {
+    ProfileScope ps("simt_bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
+                    qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_kv(kl, p->dtype, p->d, st));
+  }
   // 4. global keys: from long queries (dense, l2g) and global queries (dense, g2g)
   BwdKVArgs kg{};
   kg.k = to_t4(p->global_k); kg.v = to_t4(p->global_v); kg.d_k = to_t4(g->d_global_k); kg.d_v = to_t4(g->d_global_v);
@@ -409,15 +463,27 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   kg.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0, s_g2g};
   kg.nsrc = 2;
   kg.B = p->B; kg.H = p->H; kg.scale = p->scale; kg.neg = p->neg;
-  MLT_CUDA(simt_launch_bwd_kv(kg, p->dtype, p->d, st));
+  {
+    ProfileScope ps("simt_bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
+                    qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st);
+    MLT_CUDA(simt_launch_bwd_kv(kg, p->dtype, p->d, st));
+  }
   // 5./6. relative tables
   if (p->R > 0) {
     TableGradArgs tl{to_t4(p->long_q), p->L, wl.dallrel, wl.partial, wl.partial_bias, g->d_long_emb,
                      g->d_long_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};
-    MLT_CUDA(simt_launch_table_grad(tl, p->dtype, st));
+    {
+      ProfileScope ps("simt_table_grad_long", bh * 2 * dd * RR * p->L,
+                      qkv_bytes(bh, p->L, p->d, p->dtype, 1), st, 2);
+      MLT_CUDA(simt_launch_table_grad(tl, p->dtype, st));
+    }
     TableGradArgs tg{to_t4(p->global_q), p->G, wg.dallrel, wg.partial, wg.partial_bias, g->d_global_emb,
                      g->d_global_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->G), p->scale};
-    MLT_CUDA(simt_launch_table_grad(tg, p->dtype, st));
+    {
+      ProfileScope ps("simt_table_grad_global", bh * 2 * dd * RR * p->G,
+                      qkv_bytes(bh, p->G, p->d, p->dtype, 1), st, 2);
+      MLT_CUDA(simt_launch_table_grad(tg, p->dtype, st));
+    }
   }
   return MLT_OK;
 }

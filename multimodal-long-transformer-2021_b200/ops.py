@@ -114,7 +114,7 @@ def _fill_gl_params(p: GlParams, lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbia
   p.long_tables = RelTables(_ptr(lemb), _ptr(lbias))
   p.global_tables = RelTables(_ptr(gemb), _ptr(gbias))
   side = cfg.side
-  if isinstance(side, CompactSideInputs):
+  if hasattr(side, 'long_example_ids'):  # CompactSideInputs (duck-typed)
     p.side_mode = _lib.MLT_SIDE_COMPACT
     le = _int32(side.long_example_ids, (b, l), 'long_example_ids')
     ge = _int32(side.global_example_ids, (b, g), 'global_example_ids')
