@@ -8,6 +8,8 @@
 #include "profile.cuh"
 #include "tc_api.cuh"
 
+#include <cstdio>
+
 namespace {
 
 using namespace mlt;
@@ -223,6 +225,66 @@ KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, i
   return s;
 }
 
+FwdArgs dense_fwd_args(const mlt_dense_params* p) {
+  FwdArgs a{};
+  a.rows = dense_rows(p);
+  a.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, dense_side(p));
+  a.nseg = 1;
+  a.out = to_t4(p->out);
+  a.stats = p->stats;
+  a.B = p->B;
+  a.H = p->H;
+  a.scale = p->scale;
+  a.neg = p->neg;
+  return a;
+}
+
+// long rows: band(l2l) (+) dense(l2g), long tables
+FwdArgs gl_long_fwd_args(const mlt_gl_params* p) {
+  FwdArgs a{};
+  a.rows = RowSet{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
+  a.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, gl_side(p, L2L));
+  a.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, L2G));
+  a.nseg = 2;
+  a.out = to_t4(p->long_out);
+  a.stats = p->long_stats;
+  a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  return a;
+}
+
+// global rows: dense(g2g) (+) dense(g2l), global tables
+FwdArgs gl_global_fwd_args(const mlt_gl_params* p) {
+  FwdArgs g{};
+  g.rows = RowSet{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
+  g.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, G2G));
+  g.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, gl_side(p, G2L));
+  g.nseg = 2;
+  g.out = to_t4(p->global_out);
+  g.stats = p->global_stats;
+  g.B = p->B; g.H = p->H; g.scale = p->scale; g.neg = p->neg;
+  return g;
+}
+
+bool gl_fwd_on_tc(const mlt_gl_params* p) {
+  if (p->impl == MLT_IMPL_SIMT) return false;
+  return tc_fwd_args_supported(gl_long_fwd_args(p), p->dtype, p->d) &&
+         tc_fwd_args_supported(gl_global_fwd_args(p), p->dtype, p->d);
+}
+bool dense_fwd_on_tc(const mlt_dense_params* p) {
+  if (p->impl == MLT_IMPL_SIMT) return false;
+  return tc_fwd_args_supported(dense_fwd_args(p), p->dtype, p->d);
+}
+
+int launch_fwd(const FwdArgs& a, bool tc, int dtype, int d, const char* name, double flops,
+               double bytes, cudaStream_t st) {
+  char full[48];
+  snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
+  ProfileScope ps(full, flops, bytes, st);
+  if (tc) return tc_launch_fwd(a, st);
+  MLT_CUDA(simt_launch_fwd(a, dtype, d, st));
+  return MLT_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -247,19 +309,18 @@ const char* mlt_strerror(int code) {
 }
 
 int mlt_dense_uses_tensor_cores(const mlt_dense_params* p) {
-  if (!p || p->impl == MLT_IMPL_SIMT) return 0;
-  return mlt::tc_dense_supported(p) ? 1 : 0;
+  if (validate_dense(p) != MLT_OK) return 0;
+  return dense_fwd_on_tc(p) ? 1 : 0;
 }
 int mlt_gl_uses_tensor_cores(const mlt_gl_params* p) {
-  if (!p || p->impl == MLT_IMPL_SIMT) return 0;
-  return mlt::tc_gl_supported(p) ? 1 : 0;
+  if (validate_gl(p) != MLT_OK) return 0;
+  return gl_fwd_on_tc(p) ? 1 : 0;
 }
 
 size_t mlt_dense_workspace_bytes(const mlt_dense_params* p, int bwd) {
   if (!p) return 0;
   size_t n = kAlign;
   if (bwd) n += row_ws_bytes(p->B, p->H, p->Lq, p->R, p->d);
-  n += mlt::tc_dense_workspace_bytes(p, bwd);
   return n;
 }
 
@@ -267,30 +328,18 @@ size_t mlt_gl_workspace_bytes(const mlt_gl_params* p, int bwd) {
   if (!p) return 0;
   size_t n = kAlign;
   if (bwd) n += row_ws_bytes(p->B, p->H, p->L, p->R, p->d) + row_ws_bytes(p->B, p->H, p->G, p->R, p->d);
-  n += mlt::tc_gl_workspace_bytes(p, bwd);
   return n;
 }
 
 int mlt_dense_rel_attn_fwd(const mlt_dense_params* p, void* cuda_stream) {
   MLT_TRY(validate_dense(p));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (p->impl != MLT_IMPL_SIMT && mlt::tc_dense_supported(p)) return mlt::tc_dense_fwd(p, st);
-  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
-  FwdArgs a{};
-  a.rows = dense_rows(p);
-  a.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, dense_side(p));
-  a.nseg = 1;
-  a.out = to_t4(p->out);
-  a.stats = p->stats;
-  a.B = p->B;
-  a.H = p->H;
-  a.scale = p->scale;
-  a.neg = p->neg;
+  const bool tc = dense_fwd_on_tc(p);
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
-  ProfileScope ps("simt_fwd_dense", fwd_flops(bh, pairs, p->d, p->R, p->Lq),
-                  qkv_bytes(bh, 2.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
-  MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
-  return MLT_OK;
+  return launch_fwd(dense_fwd_args(p), tc, p->dtype, p->d, "fwd_dense",
+                    fwd_flops(bh, pairs, p->d, p->R, p->Lq),
+                    qkv_bytes(bh, 2.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
 }
 
 int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, void* cuda_stream) {
@@ -303,8 +352,8 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   if (p->R > 0 && (!g->d_emb || !g->d_bias)) return MLT_ERR_NULL;
   if (!p->workspace || p->workspace_bytes < mlt_dense_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (p->impl != MLT_IMPL_SIMT && mlt::tc_dense_supported(p)) return mlt::tc_dense_bwd(p, g, st);
-  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
+  // Backward currently always runs on the CUDA-core kernels (statistics are layout-compatible
+  // with the tcgen05 forward).
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
   RowWs ws = carve_row_ws(wp, p->B, p->H, p->Lq, p->R, p->d);
   const Side side = dense_side(p);
@@ -353,39 +402,18 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
 int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
   MLT_TRY(validate_gl(p));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (p->impl != MLT_IMPL_SIMT && mlt::tc_gl_supported(p)) return mlt::tc_gl_fwd(p, st);
-  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
-  // long rows: band(l2l) (+) dense(l2g), long tables
-  FwdArgs a{};
-  a.rows = RowSet{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
-  a.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, gl_side(p, L2L));
-  a.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, L2G));
-  a.nseg = 2;
-  a.out = to_t4(p->long_out);
-  a.stats = p->long_stats;
-  a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  const bool tc = gl_fwd_on_tc(p);
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H;
   const double pl = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
   const double pg = (double)p->G * (p->G + p->L);
-  {
-    ProfileScope ps("simt_fwd_long_rows", fwd_flops(bh, pl, p->d, p->R, p->L),
-                    qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_fwd(a, p->dtype, p->d, st));
-  }
-  // global rows: dense(g2g) (+) dense(g2l), global tables
-  FwdArgs g{};
-  g.rows = RowSet{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
-  g.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, G2G));
-  g.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, gl_side(p, G2L));
-  g.nseg = 2;
-  g.out = to_t4(p->global_out);
-  g.stats = p->global_stats;
-  g.B = p->B; g.H = p->H; g.scale = p->scale; g.neg = p->neg;
-  {
-    ProfileScope ps("simt_fwd_global_rows", fwd_flops(bh, pg, p->d, p->R, p->G),
-                    qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_fwd(g, p->dtype, p->d, st));
-  }
+  // global rows first: few, long-running tiles
+  MLT_TRY(launch_fwd(gl_global_fwd_args(p), tc, p->dtype, p->d, "fwd_global_rows",
+                     fwd_flops(bh, pg, p->d, p->R, p->G),
+                     qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_fwd(gl_long_fwd_args(p), tc, p->dtype, p->d, "fwd_long_rows",
+                     fwd_flops(bh, pl, p->d, p->R, p->L),
+                     qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   return MLT_OK;
 }
 
@@ -399,8 +427,6 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
     return MLT_ERR_NULL;
   if (!p->workspace || p->workspace_bytes < mlt_gl_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (p->impl != MLT_IMPL_SIMT && mlt::tc_gl_supported(p)) return mlt::tc_gl_bwd(p, g, st);
-  if (p->impl == MLT_IMPL_TC) return MLT_ERR_UNSUPPORTED;
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
   RowWs wl = carve_row_ws(wp, p->B, p->H, p->L, p->R, p->d);
   RowWs wg = carve_row_ws(wp, p->B, p->H, p->G, p->R, p->d);

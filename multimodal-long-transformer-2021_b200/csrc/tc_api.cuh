@@ -5,17 +5,14 @@
 #include <stddef.h>
 
 #include "../../include/mlt_attn.h"
+#include "mlt_common.cuh"
 
 namespace mlt {
 
-// True when the tcgen05 path can run these parameters (bf16, d == 64, R <= 64, ...).
-bool tc_gl_supported(const mlt_gl_params* p);
-bool tc_dense_supported(const mlt_dense_params* p);
-size_t tc_gl_workspace_bytes(const mlt_gl_params* p, int bwd);
-size_t tc_dense_workspace_bytes(const mlt_dense_params* p, int bwd);
-int tc_gl_fwd(const mlt_gl_params* p, cudaStream_t st);
-int tc_gl_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, cudaStream_t st);
-int tc_dense_fwd(const mlt_dense_params* p, cudaStream_t st);
-int tc_dense_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, cudaStream_t st);
+// True when the tcgen05 forward kernel can run this problem (bf16, d == 64, R <= 64, 16-byte
+// aligned strides, TMA encode entry point available).
+bool tc_fwd_args_supported(const FwdArgs& a, int dtype, int d);
+// Enqueues the forward kernel; returns 0, an MLT_ERR_* (< 0) or a cudaError_t (> 0).
+int tc_launch_fwd(const FwdArgs& a, cudaStream_t st);
 
 }  // namespace mlt

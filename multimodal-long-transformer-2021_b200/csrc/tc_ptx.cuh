@@ -51,16 +51,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: traps (instead of hanging the GPU) if the barrier never flips.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef MLT_TC_DEBUG_TIMEOUT
-  for (uint64_t spin = 0; spin < (1ull << 26); ++spin)
-    if (mbar_try_wait(bar, parity)) return;
-  printf("mbar_wait timeout block (%d,%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
-         blockIdx.z, threadIdx.x, (void*)bar, parity);
-  __trap();
-#else
+  uint32_t spin = 0;
   while (!mbar_try_wait(bar, parity)) {
-  }
+    if (++spin > (1u << 28)) {
+#ifdef MLT_TC_DEBUG_TIMEOUT
+      printf("mbar_wait timeout block (%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity);
 #endif
+      __trap();
+    }
+  }
 }
 
 // ---- TMA ----------------------------------------------------------------------------------
@@ -215,6 +215,12 @@ __device__ __forceinline__ void tmem_wait_st() {
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

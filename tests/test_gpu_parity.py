@@ -240,3 +240,54 @@ def test_deterministic_bitwise_repeat():
   assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
   for ga, gb in zip(a[2], b[2]):
     assert torch.equal(ga, gb)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 path (bf16, d = 64)
+
+TC_SHAPES = [
+    # (B, L, G, H, r, R, D)
+    (2, 512, 32, 4, 64, 32, 12),
+    (1, 200, 8, 2, 64, 32, 12),      # ragged tile / chunk tails
+    (1, 50, 4, 2, 64, 32, 12),       # L < r
+    (2, 300, 70, 2, 20, 20, 3),      # small radius, R not a multiple of 16, G > 64
+    (1, 1024, 64, 2, 100, 64, 30),   # radius > chunk, R = 64
+]
+
+
+@pytest.mark.parametrize('dims', TC_SHAPES, ids=lambda d: 'x'.join(map(str, d)))
+@pytest.mark.parametrize('mode', ['compact', 'explicit'])
+def test_tc_forward_matches_oracle_and_simt(dims, mode):
+  b, l, g, h, r, rv, dist = dims
+  shape = synthetic.GlobalLocalShape(b, l, g, h, 64, r, rv, dist)
+  x = synthetic.make_inputs(shape, seed=l + r, dtype=torch.bfloat16)
+  for n in ('long_emb', 'long_bias', 'global_emb', 'global_bias'):
+    x[n] = (x[n].float() * 10).bfloat16()
+  side = oracle_side(x, shape)
+  rl, rg, rgrads = run_oracle_gl(x, shape, side)
+  cuda_side = compact_of(x, shape) if mode == 'compact' else {k: v.cuda() for k, v in side.items()}
+  lo, go, grads = run_cuda_gl(x, shape, cuda_side, impl='tc')
+  ls, gs, sgrads = run_cuda_gl(x, shape, cuda_side, impl='simt')
+  assert abs_err(lo, rl) < BF16_ABS and abs_err(go, rg) < BF16_ABS
+  # the two CUDA paths see identical bf16 inputs: they must agree to bf16 output rounding
+  assert abs_err(lo, ls.double().cpu()) < BF16_ABS and abs_err(go, gs.double().cpu()) < BF16_ABS
+  for name, got, want in zip(NAMES, grads, rgrads):
+    scale = max(1.0, want.abs().max().item())
+    assert abs_err(got, want) < BF16_ABS * scale, name
+
+
+def test_tc_dense_2d_ids():
+  b, s, h, d = 2, 230, 2, 64
+  gen = torch.Generator().manual_seed(4)
+  q, k, v = (torch.randn(b, s, h, d, generator=gen).bfloat16() for _ in range(3))
+  emb = (torch.randn(49, h, d, generator=gen) * 0.2).bfloat16()
+  bias = (torch.randn(49, h, generator=gen) * 0.2).bfloat16()
+  e = (torch.arange(s)[None] < torch.tensor([[230], [180]])).int()
+  mask = torch.tensor(fo.make_segmented_att_mask(e.numpy()))
+  ids = torch.tensor(fo.MmtRelativePositionOracle(14, 2, 12).make_relative_att_ids(s))[None].expand(b, s, s).contiguous()
+  ro = ao.qkv_relative_attention(q.double(), k.double(), v.double(), mask, ids, emb.double(), bias.double())
+  for kwargs in (dict(att_mask=mask.cuda(), relative_att_ids=ids.cuda()),
+                 dict(compact=ops.DenseCompactSideInputs(e.cuda(), max_distance=12, num_patch_per_row=14,
+                                                         num_core_layers=2))):
+    out = ops.dense_relative_attention(q.cuda(), k.cuda(), v.cuda(), emb.cuda(), bias.cuda(), impl='tc', **kwargs)
+    assert abs_err(out, ro) < BF16_ABS
