@@ -285,6 +285,35 @@ int launch_fwd(const FwdArgs& a, bool tc, int dtype, int d, const char* name, do
   return MLT_OK;
 }
 
+bool t4_tc_ok(const T4& t) {
+  return t.ptr && t.sb % 8 == 0 && t.sl % 8 == 0 && t.sh % 8 == 0 && reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0;
+}
+bool bwd_kv_on_tc(const BwdKVArgs& kv) {
+  if (!t4_tc_ok(kv.k) || !t4_tc_ok(kv.v) || !t4_tc_ok(kv.d_k) || !t4_tc_ok(kv.d_v)) return false;
+  for (int s = 0; s < kv.nsrc; ++s)
+    if (!t4_tc_ok(kv.src[s].rows.q) || !t4_tc_ok(kv.src[s].d_out)) return false;
+  return true;
+}
+
+int launch_bwd_q(const BwdQArgs& a, bool tc, void* tc_ws, int dtype, int d, const char* name, double flops,
+                 double bytes, cudaStream_t st) {
+  char full[48];
+  snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
+  ProfileScope ps(full, flops, bytes, st);
+  if (tc) return tc_launch_bwd_q(a, tc_ws, st);
+  MLT_CUDA(simt_launch_bwd_q(a, dtype, d, st));
+  return MLT_OK;
+}
+int launch_bwd_kv(const BwdKVArgs& a, bool tc, void* const tc_ws[2], int dtype, int d, const char* name,
+                  double flops, double bytes, cudaStream_t st) {
+  char full[48];
+  snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
+  ProfileScope ps(full, flops, bytes, st);
+  if (tc) return tc_launch_bwd_kv(a, tc_ws, st);
+  MLT_CUDA(simt_launch_bwd_kv(a, dtype, d, st));
+  return MLT_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -320,14 +349,16 @@ int mlt_gl_uses_tensor_cores(const mlt_gl_params* p) {
 size_t mlt_dense_workspace_bytes(const mlt_dense_params* p, int bwd) {
   if (!p) return 0;
   size_t n = kAlign;
-  if (bwd) n += row_ws_bytes(p->B, p->H, p->Lq, p->R, p->d);
+  if (bwd) n += row_ws_bytes(p->B, p->H, p->Lq, p->R, p->d) + tc_bwd_rows_ws_bytes(p->B, p->H, p->Lq, p->R);
   return n;
 }
 
 size_t mlt_gl_workspace_bytes(const mlt_gl_params* p, int bwd) {
   if (!p) return 0;
   size_t n = kAlign;
-  if (bwd) n += row_ws_bytes(p->B, p->H, p->L, p->R, p->d) + row_ws_bytes(p->B, p->H, p->G, p->R, p->d);
+  if (bwd)
+    n += row_ws_bytes(p->B, p->H, p->L, p->R, p->d) + row_ws_bytes(p->B, p->H, p->G, p->R, p->d) +
+         tc_bwd_rows_ws_bytes(p->B, p->H, p->L, p->R) + tc_bwd_rows_ws_bytes(p->B, p->H, p->G, p->R);
   return n;
 }
 
@@ -352,10 +383,9 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   if (p->R > 0 && (!g->d_emb || !g->d_bias)) return MLT_ERR_NULL;
   if (!p->workspace || p->workspace_bytes < mlt_dense_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  // Backward currently always runs on the CUDA-core kernels (statistics are layout-compatible
-  // with the tcgen05 forward).
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
   RowWs ws = carve_row_ws(wp, p->B, p->H, p->Lq, p->R, p->d);
+  void* tcw[2] = {wp, wp};
   const Side side = dense_side(p);
 
   BwdQArgs q{};
@@ -370,25 +400,21 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   q.allrel = ws.allrel;
   q.dallrel = ws.dallrel;
   q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
-  const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
-  {
-    ProfileScope ps("simt_bwd_q_dense", bh * (4.0 * p->d * pairs + 2.0 * p->d * p->R * p->Lq),
-                    qkv_bytes(bh, 4.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_q(q, p->dtype, p->d, st));
-  }
-
   BwdKVArgs kv{};
   kv.k = to_t4(p->k); kv.v = to_t4(p->v); kv.d_k = to_t4(g->d_k); kv.d_v = to_t4(g->d_v);
   kv.len = p->Lk;
   kv.src[0] = QuerySource{dense_rows(p), to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, side};
   kv.nsrc = 1;
   kv.B = p->B; kv.H = p->H; kv.scale = p->scale; kv.neg = p->neg;
-  {
-    ProfileScope ps("simt_bwd_kv_dense", bh * 4.0 * p->d * pairs,
-                    qkv_bytes(bh, 2.0 * p->Lq + 4.0 * p->Lk, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_kv(kv, p->dtype, p->d, st));
-  }
 
+  const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(q, p->dtype, p->d) && bwd_kv_on_tc(kv);
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
+  MLT_TRY(launch_bwd_q(q, tc, tcw[0], p->dtype, p->d, "bwd_q_dense",
+                       bh * (4.0 * p->d * pairs + 2.0 * p->d * p->R * p->Lq),
+                       qkv_bytes(bh, 4.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_bwd_kv(kv, tc, tcw, p->dtype, p->d, "bwd_kv_dense", bh * 4.0 * p->d * pairs,
+                        qkv_bytes(bh, 2.0 * p->Lq + 4.0 * p->Lk, p->d, p->dtype, 1), st));
   if (p->R > 0) {
     TableGradArgs t{to_t4(p->q), p->Lq, ws.dallrel, ws.partial, ws.partial_bias, g->d_emb, g->d_bias,
                     p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->Lq), p->scale};
@@ -430,12 +456,14 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
   RowWs wl = carve_row_ws(wp, p->B, p->H, p->L, p->R, p->d);
   RowWs wg = carve_row_ws(wp, p->B, p->H, p->G, p->R, p->d);
+  void* tc_wl = wp;
+  wp += tc_bwd_rows_ws_bytes(p->B, p->H, p->L, p->R);
+  void* tc_wg = wp;
   const RowSet long_rows{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
   const RowSet glob_rows{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
   const Side s_l2l = gl_side(p, L2L), s_l2g = gl_side(p, L2G), s_g2g = gl_side(p, G2G),
              s_g2l = gl_side(p, G2L);
 
-  // 1. long rows: dq + dallrel
   BwdQArgs ql{};
   ql.rows = long_rows;
   ql.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, s_l2l);
@@ -444,15 +472,6 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   ql.out = to_t4(p->long_out); ql.d_out = to_t4(g->d_long_out); ql.d_q = to_t4(g->d_long_q);
   ql.stats = p->long_stats; ql.delta = wl.delta; ql.allrel = wl.allrel; ql.dallrel = wl.dallrel;
   ql.B = p->B; ql.H = p->H; ql.scale = p->scale; ql.neg = p->neg;
-  const double bh = (double)p->B * p->H, dd = p->d, RR = p->R;
-  const double p_l2l = band_pairs(p->L, p->local_radius), p_lg = (double)p->L * p->G,
-               p_gg = (double)p->G * p->G;
-  {
-    ProfileScope ps("simt_bwd_q_long_rows", bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
-                    qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_q(ql, p->dtype, p->d, st));
-  }
-  // 2. global rows
   BwdQArgs qg{};
   qg.rows = glob_rows;
   qg.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_g2g);
@@ -461,12 +480,7 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   qg.out = to_t4(p->global_out); qg.d_out = to_t4(g->d_global_out); qg.d_q = to_t4(g->d_global_q);
   qg.stats = p->global_stats; qg.delta = wg.delta; qg.allrel = wg.allrel; qg.dallrel = wg.dallrel;
   qg.B = p->B; qg.H = p->H; qg.scale = p->scale; qg.neg = p->neg;
-  {
-    ProfileScope ps("simt_bwd_q_global_rows", bh * (4 * dd * (p_gg + p_lg) + 2 * dd * RR * p->G),
-                    qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_q(qg, p->dtype, p->d, st));
-  }
-  // 3. long keys: from long queries (band, l2l) and global queries (dense, g2l)
+  // long keys: from long queries (band, l2l) and global queries (dense, g2l)
   BwdKVArgs kl{};
   kl.k = to_t4(p->long_k); kl.v = to_t4(p->long_v); kl.d_k = to_t4(g->d_long_k); kl.d_v = to_t4(g->d_long_v);
   kl.len = p->L;
@@ -476,12 +490,7 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                           s_g2l};
   kl.nsrc = 2;
   kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
-  {
-    ProfileScope ps("simt_bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
-                    qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_kv(kl, p->dtype, p->d, st));
-  }
-  // 4. global keys: from long queries (dense, l2g) and global queries (dense, g2g)
+  // global keys: from long queries (dense, l2g) and global queries (dense, g2g)
   BwdKVArgs kg{};
   kg.k = to_t4(p->global_k); kg.v = to_t4(p->global_v); kg.d_k = to_t4(g->d_global_k); kg.d_v = to_t4(g->d_global_v);
   kg.len = p->G;
@@ -489,12 +498,25 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   kg.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0, s_g2g};
   kg.nsrc = 2;
   kg.B = p->B; kg.H = p->H; kg.scale = p->scale; kg.neg = p->neg;
-  {
-    ProfileScope ps("simt_bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
-                    qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st);
-    MLT_CUDA(simt_launch_bwd_kv(kg, p->dtype, p->d, st));
-  }
-  // 5./6. relative tables
+
+  const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(ql, p->dtype, p->d) &&
+                  tc_bwd_q_supported(qg, p->dtype, p->d) && bwd_kv_on_tc(kl) && bwd_kv_on_tc(kg);
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  void* ws_lg[2] = {tc_wl, tc_wg};
+
+  const double bh = (double)p->B * p->H, dd = p->d, RR = p->R;
+  const double p_l2l = band_pairs(p->L, p->local_radius), p_lg = (double)p->L * p->G,
+               p_gg = (double)p->G * p->G;
+  MLT_TRY(launch_bwd_q(qg, tc, tc_wg, p->dtype, p->d, "bwd_q_global_rows",
+                       bh * (4 * dd * (p_gg + p_lg) + 2 * dd * RR * p->G),
+                       qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_bwd_q(ql, tc, tc_wl, p->dtype, p->d, "bwd_q_long_rows",
+                       bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
+                       qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
+                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_bwd_kv(kl, tc, ws_lg, p->dtype, p->d, "bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
+                        qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   if (p->R > 0) {
     TableGradArgs tl{to_t4(p->long_q), p->L, wl.dallrel, wl.partial, wl.partial_bias, g->d_long_emb,
                      g->d_long_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};

@@ -15,4 +15,14 @@ bool tc_fwd_args_supported(const FwdArgs& a, int dtype, int d);
 // Enqueues the forward kernel; returns 0, an MLT_ERR_* (< 0) or a cudaError_t (> 0).
 int tc_launch_fwd(const FwdArgs& a, cudaStream_t st);
 
+
+// ---- backward (tc_bwd.cu) -------------------------------------------------------------------
+// Extra workspace (bytes) of one row set: rowstat [B,H,Lpad] float4 + allrel [B,H,Lpad,R4] f32.
+size_t tc_bwd_rows_ws_bytes(int B, int H, int len, int R);
+bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d);
+// Query-centric pass: dq, dallrel (a.dallrel, [B,H,Lq,R]); publishes rowstat / allrel into `ws`.
+int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st);
+// Key-centric pass: dk, dv.  ws[s] is the workspace tc_launch_bwd_q filled for query source s.
+int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st);
+
 }  // namespace mlt

@@ -291,3 +291,26 @@ def test_tc_dense_2d_ids():
                                                          num_core_layers=2))):
     out = ops.dense_relative_attention(q.cuda(), k.cuda(), v.cuda(), emb.cuda(), bias.cuda(), impl='tc', **kwargs)
     assert abs_err(out, ro) < BF16_ABS
+
+
+def test_tc_dense_backward_matches_oracle():
+  b, s, h, d = 2, 200, 2, 64
+  gen = torch.Generator().manual_seed(8)
+  q, k, v, do = (torch.randn(b, s, h, d, generator=gen).bfloat16() for _ in range(4))
+  emb = (torch.randn(32, h, d, generator=gen) * 0.2).bfloat16()
+  bias = (torch.randn(32, h, generator=gen) * 0.2).bfloat16()
+  e = (torch.arange(s)[None] < torch.tensor([[200], [150]])).int()
+  mask = torch.tensor(fo.make_segmented_att_mask(e.numpy()))
+  ids = torch.tensor(fo.make_relative_att_ids_1d(s, 12))[None].expand(b, s, s).contiguous()
+  ref = [t.double().requires_grad_() for t in (q, k, v, emb, bias)]
+  ro = ao.qkv_relative_attention(ref[0], ref[1], ref[2], mask, ids, ref[3], ref[4])
+  (ro * do.double()).sum().backward()
+  for kwargs in (dict(att_mask=mask.cuda(), relative_att_ids=ids.cuda()),
+                 dict(compact=ops.DenseCompactSideInputs(e.cuda(), max_distance=12))):
+    dev = [t.cuda().requires_grad_() for t in (q, k, v, emb, bias)]
+    out = ops.dense_relative_attention(*dev, impl='tc', **kwargs)
+    (out.float() * do.cuda().float()).sum().backward()
+    assert abs_err(out, ro.detach()) < BF16_ABS
+    for name, got, want in zip('q k v emb bias'.split(), dev, ref):
+      scale = max(1.0, want.grad.abs().max().item())
+      assert abs_err(got.grad, want.grad) < BF16_ABS * scale, name
