@@ -289,7 +289,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (hh == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
     }
     if (rpad) {
-      mbar_wait(&bars->rel_full, 0);
+      mbar_wait_warp(&bars->rel_full, 0);
       tc_fence_after_sync();
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
       for (int c0 = 0; c0 < rpad; c0 += 16) {
@@ -316,7 +316,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const KeySeg& sg = first ? a.seg[0] : a.seg[1];
       const int key0 = (first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN) + hh * 32;
       const int ke = first ? r0.ke : r1.ke;
-      mbar_wait(&bars->sdp_full[c & 1], (c >> 1) & 1);
+      mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
       tc_fence_after_sync();
       uint32_t s_raw[32], dp_raw[32], ds_pk[16];
       tmem_ld32(tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32, s_raw);
@@ -337,7 +337,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     // ---- epilogue: dq = scale * (dS.K + dallrel.E); publish dallrel ----
     named_bar_sync(1, NEW);  // both halves' bins complete
-    mbar_wait(&bars->dq_full, 0);
+    mbar_wait_warp(&bars->dq_full, 0);
     tc_fence_after_sync();
     uint32_t dq_raw[32];
     tmem_ld32(tmem + T_DQ + lane_sel + hh * 32, dq_raw);
@@ -611,8 +611,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       const TcQuerySource& src = first ? p.src[0] : p.src[1];
       const int q0 = (first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN) + hh * 32;
       const int ie = first ? r0.ie : r1.ie;
-      mbar_wait(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
-      mbar_wait(&bars->sdp_full[c & 1], (c >> 1) & 1);
+      mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
+      mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
       tc_fence_after_sync();
       const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + hh * 32;
       const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + hh * 32 * src.rw;
@@ -633,7 +633,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       tc_fence_before_sync();
       mbar_arrive(&bars->pds_full[c & 1]);
     }
-    mbar_wait(&bars->acc_full, 0);
+    mbar_wait_warp(&bars->acc_full, 0);
     tc_fence_after_sync();
     uint32_t dv_raw[32], dk_raw[32];
     tmem_ld32(tmem + T_DV + lane_sel + hh * 32, dv_raw);

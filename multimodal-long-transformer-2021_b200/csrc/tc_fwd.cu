@@ -18,6 +18,7 @@
 #include "mlt_common.cuh"
 #include "profile.cuh"
 #include "tc_ptx.cuh"
+#include "tc_rowscore.cuh"
 
 namespace mlt {
 namespace {
@@ -27,7 +28,7 @@ using namespace ptx;
 constexpr int TM = 128;       // query rows per tile
 constexpr int TN = 64;        // keys per chunk
 constexpr int NST = 3;        // K/V ring stages
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 256;   // warpgroup 0: softmax; warpgroup 1: TMA, MMA, 2 idle warps
 constexpr uint32_t TMEM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -38,6 +39,21 @@ constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64][128] fp32 = 32 KB
 constexpr int SM_BAR = SM_REL + 64 * TM * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;        // slack for 1024-B alignment
+
+#ifdef MLT_TC_TRACE
+__device__ unsigned long long g_trace[3][256];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(role, idx)                                                                  \
+  do {                                                                                    \
+    if (blockIdx.x == 5 && blockIdx.y == 1 && blockIdx.z == 0 && (idx) < 256) g_trace[role][idx] = gtime(); \
+  } while (0)
+#else
+#define TRACE(role, idx) do {} while (0)
+#endif
 
 struct TcFwdParams {
   FwdArgs a;
@@ -68,57 +84,21 @@ __device__ __forceinline__ SegRange seg_range(const KeySeg& sg, int i0) {
   return r;
 }
 
-// Scores of one chunk for one row: t[jj] = (x + rel) * scale (+ neg if masked), -inf if dead.
-template <int MR, int IR>
-__device__ __forceinline__ void score_chunk(float (&t)[TN], const KeySeg& sg, int b, int i, int row,
-                                            bool row_ok, int key0, int ke, int R, const float* rel_s,
-                                            float scale, float neg) {
-  const Side& sd = sg.side;
-  int q_e = 0, q_sent = -1;
-  if (MR == MR_EXAMPLE_ID && row_ok) q_e = __ldg(sd.q_eid + (int64_t)b * sd.q_len + i);
-  if (IR == IDR_CROSS_QSENT && row_ok) q_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + i);
-  const int32_t* mrow = nullptr;
-  const int32_t* irow = nullptr;
-  if (MR == MR_EXPLICIT) mrow = sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq;
-  if (IR == IDR_EXPLICIT) irow = sd.ids + (int64_t)b * sd.sb + (int64_t)i * sd.sq;
-#pragma unroll
-  for (int jj = 0; jj < TN; ++jj) {
-    const int j = key0 + jj;
-    const int off = j - i;
-    const bool live = row_ok && j < ke && (!sg.band || (off <= sg.radius && off >= -sg.radius));
-    const int col = sg.band ? off + sg.radius : j;
-    bool ok = true;
-    int id = -1;
-    if (live) {
-      if (MR == MR_EXPLICIT) ok = __ldg(mrow + col) != 0;
-      if (MR == MR_EXAMPLE_ID) ok = (q_e == __ldg(sd.k_eid + (int64_t)b * sd.k_len + j));
-      if (IR == IDR_EXPLICIT) id = __ldg(irow + col);
-      if (IR == IDR_1D) id = rel_id_1d(off, sd.max_distance);
-      if (IR == IDR_CROSS_QSENT) id = 2 * sd.max_distance + 1 + (q_sent == j ? 1 : 0);
-      if (IR == IDR_CROSS_KSENT)
-        id = 2 * sd.max_distance + 1 + (__ldg(sd.sent + (int64_t)b * sd.sent_len + j) == i ? 1 : 0);
-      if (IR == IDR_2D) id = rel_id_2d(i, j, sd.npr, sd.core, sd.max_distance);
-    }
-    float rel = 0.f;
-    if (IR != IDR_NONE && id >= 0 && id < R) rel = rel_s[id * TM + row];
-    float v = fmaf(t[jj], scale, rel);  // rel_s already holds allrel * scale
-    if (!ok) v += neg;
-    t[jj] = live ? v : -INFINITY;
-  }
-}
-
-template <int MR>
-__device__ __forceinline__ void score_chunk_ir(float (&t)[TN], const KeySeg& sg, int b, int i, int row,
-                                               bool row_ok, int key0, int ke, int R,
-                                               const float* rel_s, float scale, float neg) {
-  switch (sg.side.id_rule) {
-    case IDR_EXPLICIT: score_chunk<MR, IDR_EXPLICIT>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-    case IDR_1D: score_chunk<MR, IDR_1D>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-    case IDR_CROSS_QSENT: score_chunk<MR, IDR_CROSS_QSENT>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-    case IDR_CROSS_KSENT: score_chunk<MR, IDR_CROSS_KSENT>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-    case IDR_2D: score_chunk<MR, IDR_2D>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-    default: score_chunk<MR, IDR_NONE>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, scale, neg); break;
-  }
+__device__ __forceinline__ rowscore::SegCtx make_seg_ctx(const KeySeg& sg, const SegRange& r, int R, int pd,
+                                                        bool perm) {
+  rowscore::SegCtx sc;
+  sc.sg = &sg;
+  sc.kb = r.kb;
+  sc.ke = r.ke;
+  sc.R = R;
+  sc.D = sg.side.max_distance;
+  sc.pd = pd;
+  sc.perm = perm;
+  sc.band = sg.band != 0;
+  sc.radius = sg.radius;
+  sc.mask_rule = sg.side.mask_rule;
+  sc.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  return sc;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2)
@@ -161,9 +141,15 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (a.nseg > 1) r1 = seg_range(a.seg[1], i0);
   const int nchunks = r0.n + r1.n;
 
-  if (warp == 4) {
+  if (warp >= 4) {
+    // warpgroup 1 (TMA, MMA, 2 idle warps that only complete the warpgroup) gives registers away
+    setmaxnreg_dec<40>();
+  }
+  if (warp >= 6) {
+  } else if (warp == 4) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      TRACE(1, 0);
       prefetch_tensormap(&map_q);
       prefetch_tensormap(&map_k0);
       prefetch_tensormap(&map_v0);
@@ -176,6 +162,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const bool first = c < r0.n;
         const int key0 = first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN;
         uint8_t* ks = smem + SM_KV + st * (2 * TN * 128);
+        TRACE(1, 2 + c);
         mbar_arrive_expect_tx(&bars->kv_full[st], 2 * TN * 128);
         tma_load_4d(ks, first ? &map_k0 : &map_k1, &bars->kv_full[st], 0, key0, h, b);
         tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
@@ -187,7 +174,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(TM, 64, 0, 1);
       const uint32_t q_addr = smem_u32(smem + SM_Q);
+      TRACE(2, 0);
       mbar_wait(&bars->q_full, 0);
+      TRACE(2, 1);
       tc_fence_after_sync();
       if (rpad) {
         const uint32_t idesc_r = make_idesc_bf16(TM, rpad, 0, 0);
@@ -202,6 +191,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (c < nchunks) {
           const int st = c % NST;
           mbar_wait(&bars->kv_full[st], (c / NST) & 1);
+          TRACE(2, 2 + 4 * c);
           if (c == 1 && rpad) mbar_wait(&bars->rel_done, 0);  // allrel aliases S1
           tc_fence_after_sync();
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
@@ -210,15 +200,17 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             umma_ss(tmem + (c & 1) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
                     make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
           umma_commit(&bars->s_full[c & 1]);
+          TRACE(2, 3 + 4 * c);
         }
         if (c >= 1) {
           const int pc = c - 1, st = pc % NST;
           mbar_wait(&bars->p_full[pc & 1], (pc >> 1) & 1);
+          TRACE(2, 4 + 4 * pc);
           tc_fence_after_sync();
           const uint32_t v_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128) + TN * 128);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + 128 + (pc & 1) * 64, tmem + (pc & 1) * 64 + kk * 8,
+            umma_ts(tmem + 128 + (pc & 1) * 64, tmem + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
                     make_smem_desc_sw128(v_addr + kk * 2048, 16, 1024), idesc_o, kk > 0);
           umma_commit(&bars->o_full[pc & 1]);
           umma_commit(&bars->kv_empty[st]);
@@ -227,29 +219,61 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else {
     // ===================== softmax / epilogue (warps 0-3) =====================
-    const int row = tid;
+    setmaxnreg_inc<216>();
+    using namespace rowscore;
+    const int row = tid, lane = tid & 31;
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
+    const int wrow0 = i0 + warp * 32;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int pd = a.seg[0].side.max_distance;
+    const bool perm = (2 * pd + 1 <= R);
+    if (tid == 0) TRACE(0, 0);
+    // ---- early global loads: row scalars, bias lanes, first chunk's key lanes ----
+    SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
+    SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    RowCtx rc0, rc1;
+    rc0.i = rc1.i = i;
+    rc0.row = rc1.row = row;
+    rc0.row_ok = rc1.row_ok = row_ok;
+    init_row_loads(rc0, sc0, b);
+    init_row_loads(rc1, sc1, b);
+    auto chunk_key0 = [&](int c) { return c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN; };
+    GroupLanes gl0{0, -1}, gl1{0, -1};
+    if (nchunks > 0) {
+      const SegCtx& s = 0 < r0.n ? sc0 : sc1;
+      gl0 = load_group_lanes(s, b, chunk_key0(0), lane);
+      gl1 = load_group_lanes(s, b, chunk_key0(0) + 32, lane);
+    }
+    float bias_l0 = 0.f, bias_l1 = 0.f;  // lane l holds bias[l], bias[32 + l]
     if (rpad) {
-      mbar_wait(&bars->rel_full, 0);
-      tc_fence_after_sync();
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
+      if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
+      if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
+      mbar_wait_warp(&bars->rel_full, 0);
+      if (tid == 0) TRACE(0, 1);
+      tc_fence_after_sync();
+#pragma unroll 1
       for (int c0 = 0; c0 < rpad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + 64 + lane_sel + c0, v);
-        tmem_wait_ld();
+        {
+          uint32_t v[16];
+          tmem_ld16(tmem + 64 + lane_sel + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          const int pid = c0 + x;
-          if (pid < R)
-            rel_s[pid * TM + row] =
-                (__uint_as_float(v[x]) + __bfloat162float(bias[pid * a.H + h])) * a.scale;
+          for (int x = 0; x < 16; ++x) {
+            const int pid = c0 + x;
+            const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
+            if (pid < R) rel_s[slot_of_id(pid, pd, perm) * TM + row] = (__uint_as_float(v[x]) + bv) * a.scale;
+          }
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&bars->rel_done);
     }
+    if (tid == 0) TRACE(0, 2);
+    init_row(rc0, sc0, b, rel_s);
+    init_row(rc1, sc1, b, rel_s);
+
     float m = -1e30f, l = 0.f, alpha_prev = 0.f;
     float o[64];
 #pragma unroll
@@ -259,61 +283,106 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       float alpha = 0.f;
       if (c < nchunks) {
         const bool first = c < r0.n;
-        const KeySeg& sg = first ? a.seg[0] : a.seg[1];
-        const int key0 = first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN;
-        const int ke = first ? r0.ke : r1.ke;
-        mbar_wait(&bars->s_full[c & 1], (c >> 1) & 1);
+        const SegCtx& sc = first ? sc0 : sc1;
+        const RowCtx& rc = first ? rc0 : rc1;
+        const int key0 = chunk_key0(c);
+        const uint32_t t_s = tmem + (c & 1) * 64 + lane_sel;
+        // prefetch the key-side lane scalars of the next chunk
+        GroupLanes nl0{0, -1}, nl1{0, -1};
+        if (c + 1 < nchunks) {
+          const SegCtx& sn = (c + 1) < r0.n ? sc0 : sc1;
+          nl0 = load_group_lanes(sn, b, chunk_key0(c + 1), lane);
+          nl1 = load_group_lanes(sn, b, chunk_key0(c + 1) + 32, lane);
+        }
+        if (tid == 0) TRACE(0, 4 + 4 * c);
+        mbar_wait_warp(&bars->s_full[c & 1], (c >> 1) & 1);
+        if (tid == 0) TRACE(0, 5 + 4 * c);
         tc_fence_after_sync();
-        float t[TN];
-        {
-          uint32_t v[32];
-          tmem_ld32(tmem + (c & 1) * 64 + lane_sel, v);
-          tmem_wait_ld();
+        // ---- pass 1 (per 32-key group, ONE copy of the code): scores -> TMEM, running max ----
+        float mx = -INFINITY;
+        uint32_t dead_mask = 0;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const GroupLanes& gl = g ? gl1 : gl0;
+          const int g0 = key0 + 32 * g;
+          const GroupPlan gp = classify(sc, rc, gl, wrow0, g0, lane, a.neg);
+          if (gp.mode == GM_DEAD) {
+            dead_mask |= 1u << g;
+            continue;
+          }
+          if (gp.mode == GM_GEN) score_group_generic_tmem(t_s + 32 * g, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
+          float t[32];
+          {
+            uint32_t v[32];
+            tmem_ld32(t_s + 32 * g, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
-          tmem_ld32(tmem + (c & 1) * 64 + lane_sel + 32, v);
-          tmem_wait_ld();
+            for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
+          }
+          score_group<0>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
 #pragma unroll
-          for (int x = 0; x < 32; ++x) t[32 + x] = __uint_as_float(v[x]);
+          for (int x = 0; x < 32; ++x) mx = fmaxf(mx, t[x]);
+          if (gp.mode != GM_GEN) {
+            uint32_t v[32];
+#pragma unroll
+            for (int x = 0; x < 32; ++x) v[x] = __float_as_uint(t[x]);
+            tmem_st32(t_s + 32 * g, v);
+          }
         }
-        switch (sg.side.mask_rule) {
-          case MR_EXPLICIT: score_chunk_ir<MR_EXPLICIT>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, a.scale, a.neg); break;
-          case MR_EXAMPLE_ID: score_chunk_ir<MR_EXAMPLE_ID>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, a.scale, a.neg); break;
-          default: score_chunk_ir<MR_NONE>(t, sg, b, i, row, row_ok, key0, ke, R, rel_s, a.scale, a.neg); break;
-        }
-        float mx = t[0];
-#pragma unroll
-        for (int x = 1; x < TN; ++x) mx = fmaxf(mx, t[x]);
+        tmem_wait_st();
         const float m_new = fmaxf(m, mx);
         alpha = ex2((m - m_new) * LOG2E);
         const float mb = m_new * LOG2E;
+        // ---- pass 2: p = exp2(t * log2e - mb), row sum, P (bf16) back into TMEM ----
         float lsum = 0.f;
-        uint32_t pk[32];
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          uint32_t pk[16];
+          if (dead_mask & (1u << g)) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const float p0 = ex2(fmaf(t[2 * x], LOG2E, -mb));
-          const float p1 = ex2(fmaf(t[2 * x + 1], LOG2E, -mb));
-          lsum += p0 + p1;
-          pk[x] = pack_bf16x2(p0, p1);
+            for (int x = 0; x < 16; ++x) pk[x] = 0u;
+          } else {
+            uint32_t v[32];
+            tmem_ld32(t_s + 32 * g, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), LOG2E, -mb));
+              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), LOG2E, -mb));
+              lsum += p0 + p1;
+              pk[x] = pack_bf16x2(p0, p1);
+            }
+          }
+          // P of keys [32g, 32g+32) -> packed columns [32g, 32g+16): stays inside this group's own
+          // score columns, so the not-yet-read scores of group 1 are never clobbered
+          tmem_st16(t_s + 32 * g, pk);
         }
-        tmem_st32(tmem + (c & 1) * 64 + lane_sel, pk);
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[c & 1]);
+        if (tid == 0) TRACE(0, 6 + 4 * c);
         l = l * alpha + lsum;
         m = m_new;
+        gl0 = nl0;
+        gl1 = nl1;
       }
       if (c >= 1) {
         const int pc = c - 1;
-        mbar_wait(&bars->o_full[pc & 1], (pc >> 1) & 1);
+        mbar_wait_warp(&bars->o_full[pc & 1], (pc >> 1) & 1);
+        if (tid == 0) TRACE(0, 7 + 4 * pc);
         tc_fence_after_sync();
-        uint32_t v[32];
-#pragma unroll
+#pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
           tmem_ld32(tmem + 128 + (pc & 1) * 64 + lane_sel + hh * 32, v);
           tmem_wait_ld();
+          if (hh == 0) {
 #pragma unroll
-          for (int x = 0; x < 32; ++x) o[hh * 32 + x] = fmaf(o[hh * 32 + x], alpha_prev, __uint_as_float(v[x]));
+            for (int x = 0; x < 32; ++x) o[x] = fmaf(o[x], alpha_prev, __uint_as_float(v[x]));
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) o[32 + x] = fmaf(o[32 + x], alpha_prev, __uint_as_float(v[x]));
+          }
         }
       }
       alpha_prev = alpha;
@@ -334,6 +403,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       *st = make_float2(m, l);
     }
   }
+  if (tid == 0) TRACE(0, 3);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem);
@@ -354,6 +424,12 @@ bool tc_fwd_args_supported(const FwdArgs& a, int dtype, int d) {
   if (a.rows.R > 0 && reinterpret_cast<uintptr_t>(a.rows.emb) % 16) return false;
   return get_encode_tiled() != nullptr;
 }
+
+#ifdef MLT_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 3 * 256);
+}
+#endif
 
 int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   static bool attr_set = false;

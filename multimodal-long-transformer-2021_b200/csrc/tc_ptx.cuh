@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace mlt {
 namespace ptx {
@@ -53,14 +54,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spin = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spin > (1u << 28)) {
 #ifdef MLT_TC_DEBUG_TIMEOUT
-      printf("mbar_wait timeout block (%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
-#endif
+    if (++spin > (1u << 20)) {
+      printf("mbar_wait timeout block (%d,%d,%d) thread %d bar+%d parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, (int)(smem_u32(bar) & 1023), parity);
       __trap();
     }
+#else
+    if (++spin > (1u << 28)) __trap();
+#endif
   }
+}
+
+// Whole-warp wait: every lane polls, then the warp is explicitly re-converged.  Required before
+// any `.sync.aligned` tcgen05 instruction or full-mask warp collective (the spin loop may be
+// left by different lanes in different iterations).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---- TMA ----------------------------------------------------------------------------------
@@ -205,11 +216,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[15])
       : "memory");
 }
+// single column (dynamic column address: TMEM doubles as indexable scratch for rare slow paths)
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Register re-balancing between warpgroups (4 consecutive warps each).
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
 // named barrier among a subset of warps
