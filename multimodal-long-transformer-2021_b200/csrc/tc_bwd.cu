@@ -15,6 +15,7 @@
 
 #include "mlt_common.cuh"
 #include "tc_ptx.cuh"
+#include "tc_rowscore.cuh"
 
 namespace mlt {
 namespace {
@@ -96,58 +97,42 @@ struct TcBwdQParams {
   float* allrel_ws;   // ws [B, H, lp, rw] (allrel * scale)
 };
 
-template <int MR, int IR>
-__device__ __forceinline__ void bwd_q_chunk(uint32_t (&s_raw)[32], uint32_t (&dp_raw)[32], uint32_t (&ds_pk)[16],
-                                            const KeySeg& sg, int b, int i, int row, bool row_ok, int key0,
-                                            int ke, int R, const float* rel_s, float* bin, float scale,
-                                            float neg, float m2, float linv, float delta) {
-  const Side& sd = sg.side;
-  int q_e = 0, q_sent = -1;
-  if (MR == MR_EXAMPLE_ID && row_ok) q_e = __ldg(sd.q_eid + (int64_t)b * sd.q_len + i);
-  if (IR == IDR_CROSS_QSENT && row_ok) q_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + i);
-#pragma unroll
-  for (int jj = 0; jj < 32; ++jj) {
-    const int j = key0 + jj;
-    const int off = j - i;
-    const bool live = row_ok && j < ke && (!sg.band || (off <= sg.radius && off >= -sg.radius));
-    float ds = 0.f;
-    if (live) {
-      int k_e = 0, k_sent = -1;
-      if (MR == MR_EXAMPLE_ID) k_e = __ldg(sd.k_eid + (int64_t)b * sd.k_len + j);
-      if (IR == IDR_CROSS_KSENT) k_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + j);
-      bool ok;
-      int id;
-      side_ok_id<MR, IR>(sd, b, i, j, sg.band ? off + sg.radius : j, q_e, k_e, q_sent, k_sent, ok, id);
-      const bool idv = IR != IDR_NONE && id >= 0 && id < R;
-      float t = fmaf(__uint_as_float(s_raw[jj]), scale, idv ? rel_s[id * TM + row] : 0.f);
-      if (!ok) t += neg;
-      const float p = ex2(fmaf(t, LOG2E, -m2)) * linv;
-      ds = p * (__uint_as_float(dp_raw[jj]) - delta);
-      if (idv) bin[id * TM + row] += ds;
-    }
-    if (jj & 1) {
-      ds_pk[jj >> 1] = pack_bf16x2(__uint_as_float(s_raw[jj - 1]), ds);
-    } else {
-      s_raw[jj] = __float_as_uint(ds);  // stash the even element until its odd partner is ready
-    }
-  }
+__device__ __forceinline__ rowscore::SegCtx make_seg_ctx(const KeySeg& sg, const SegRange& r, int R, int pd,
+                                                        bool perm) {
+  rowscore::SegCtx sc;
+  sc.sg = &sg;
+  sc.kb = r.kb;
+  sc.ke = r.ke;
+  sc.R = R;
+  sc.D = sg.side.max_distance;
+  sc.pd = pd;
+  sc.perm = perm;
+  sc.band = sg.band != 0;
+  sc.radius = sg.radius;
+  sc.mask_rule = sg.side.mask_rule;
+  sc.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  return sc;
 }
 
-template <int MR>
-__device__ __forceinline__ void bwd_q_chunk_ir(uint32_t (&s_raw)[32], uint32_t (&dp_raw)[32], uint32_t (&ds_pk)[16],
-                                               const KeySeg& sg, int b, int i, int row, bool row_ok, int key0,
-                                               int ke, int R, const float* rel_s, float* bin, float scale,
-                                               float neg, float m2, float linv, float delta) {
-#define MLT_CALL(IRV) bwd_q_chunk<MR, IRV>(s_raw, dp_raw, ds_pk, sg, b, i, row, row_ok, key0, ke, R, rel_s, bin, scale, neg, m2, linv, delta)
-  switch (sg.side.id_rule) {
-    case IDR_EXPLICIT: MLT_CALL(IDR_EXPLICIT); break;
-    case IDR_1D: MLT_CALL(IDR_1D); break;
-    case IDR_CROSS_QSENT: MLT_CALL(IDR_CROSS_QSENT); break;
-    case IDR_CROSS_KSENT: MLT_CALL(IDR_CROSS_KSENT); break;
-    case IDR_2D: MLT_CALL(IDR_2D); break;
-    default: MLT_CALL(IDR_NONE); break;
+// GM_GEN groups of the query-centric backward: real loop over the 32 columns, TMEM as scratch.
+// Reads S and dP columns, leaves ds (fp32) in the S column, updates the row's bins.
+__device__ __forceinline__ void bwd_q_group_generic_tmem(uint32_t t_s, uint32_t t_dp, const rowscore::SegCtx& sc,
+                                                         const rowscore::RowCtx& rc, const rowscore::GroupLanes& gl,
+                                                         int b, int g0, const float* rel_s, float* bin, float scale,
+                                                         float neg, float m2, float linv, float delta) {
+#pragma unroll 1
+  for (int jj = 0; jj < 32; ++jj) {
+    const uint32_t raw = tmem_ld1(t_s + jj);
+    const uint32_t dpr = tmem_ld1(t_dp + jj);
+    tmem_wait_ld();
+    int slot;
+    const float t = rowscore::score_generic(__uint_as_float(raw), sc, rc, gl, b, g0, jj, rel_s, scale, neg, slot);
+    const float pv = ex2(fmaf(t, LOG2E, -m2)) * linv;
+    const float ds = (t == -INFINITY) ? 0.f : pv * (__uint_as_float(dpr) - delta);
+    if (slot >= 0) bin[slot * TM + rc.row] += ds;
+    tmem_st1(t_s + jj, __float_as_uint(ds));
   }
-#undef MLT_CALL
+  tmem_wait_st();
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -257,13 +242,34 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else {
     // ===================== elementwise warps 0-7 =====================
+    using namespace rowscore;
     const int row = (warp & 3) * 32 + lane;
-    const int hh = warp >> 2;  // column half
+    const int hh = warp >> 2;  // column half == key group of every chunk
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
+    const int wrow0 = i0 + (warp & 3) * 32;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    float* bin = bins + hh * 64 * TM;
-    for (int x = lane + 32 * (warp & 3) + 128 * 0; x < 64 * TM; x += 128) bin[x] = 0.f;  // each half zeroes its bins
+    const int pd = a.seg[0].side.max_distance;
+    const bool perm = (2 * pd + 1 <= R);
+    float* bin = bins + hh * 64 * TM;   // slot-ordered, private to (half, row)
+    for (int x = lane + 32 * (warp & 3); x < 64 * TM; x += 128) bin[x] = 0.f;
+    SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
+    SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    RowCtx rc0, rc1;
+    rc0.i = rc1.i = i;
+    rc0.row = rc1.row = row;
+    rc0.row_ok = rc1.row_ok = row_ok;
+    init_row_loads(rc0, sc0, b);
+    init_row_loads(rc1, sc1, b);
+    auto chunk_key0 = [&](int c) { return (c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN) + hh * 32; };
+    GroupLanes gl{0, -1};
+    if (nchunks > 0) gl = load_group_lanes(0 < r0.n ? sc0 : sc1, b, chunk_key0(0), lane);
+    float bias_l0 = 0.f, bias_l1 = 0.f;
+    if (rpad) {
+      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
+      if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
+      if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
+    }
     // row constants
     float m2 = 0.f, linv = 0.f, delta = 0.f;
     const int64_t srow = (int64_t)(b * a.H + h) * a.rows.len + i;
@@ -291,49 +297,122 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (rpad) {
       mbar_wait_warp(&bars->rel_full, 0);
       tc_fence_after_sync();
-      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
+#pragma unroll 1
       for (int c0 = 0; c0 < rpad; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem + T_REL + lane_sel + c0, v);
         tmem_wait_ld();
-        if (hh == 0) {
 #pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const int pid = c0 + x;
-            if (pid < R) {
-              const float val = (__uint_as_float(v[x]) + __bfloat162float(bias[pid * a.H + h])) * a.scale;
-              rel_s[pid * TM + row] = val;
-              if (row_ok) p.allrel_ws[prow * p.rw + pid] = val;
-            }
+        for (int x = 0; x < 16; ++x) {
+          const int pid = c0 + x;
+          const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
+          if (hh == 0 && pid < R) {
+            const float val = (__uint_as_float(v[x]) + bv) * a.scale;
+            rel_s[slot_of_id(pid, pd, perm) * TM + row] = val;
+            if (row_ok) p.allrel_ws[prow * p.rw + pid] = val;
           }
         }
       }
     }
-    named_bar_sync(1, NEW);  // rel_s / bins visible to both halves
+    named_bar_sync(1, NEW);  // rel_s (written by half 0) visible to both halves; bins zeroed
+    init_row(rc0, sc0, b, rel_s);
+    init_row(rc1, sc1, b, rel_s);
+    // per-row accumulators of the constant relative classes (flushed into the bins at the end)
+    float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
 
     for (int c = 0; c < nchunks; ++c) {
       const bool first = c < r0.n;
-      const KeySeg& sg = first ? a.seg[0] : a.seg[1];
-      const int key0 = (first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN) + hh * 32;
-      const int ke = first ? r0.ke : r1.ke;
+      const SegCtx& sc = first ? sc0 : sc1;
+      const RowCtx& rc = first ? rc0 : rc1;
+      const int g0 = chunk_key0(c);
+      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32;
+      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32;
+      GroupLanes nl{0, -1};
+      if (c + 1 < nchunks) nl = load_group_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_key0(c + 1), lane);
+      const GroupPlan gp = classify(sc, rc, gl, wrow0, g0, lane, a.neg);
       mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
       tc_fence_after_sync();
-      uint32_t s_raw[32], dp_raw[32], ds_pk[16];
-      tmem_ld32(tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32, s_raw);
-      tmem_ld32(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, dp_raw);
-      tmem_wait_ld();
-#define MLT_CALL(MRV) bwd_q_chunk_ir<MRV>(s_raw, dp_raw, ds_pk, sg, b, i, row, row_ok, key0, ke, R, rel_s, bin, a.scale, a.neg, m2, linv, delta)
-      switch (sg.side.mask_rule) {
-        case MR_EXPLICIT: MLT_CALL(MR_EXPLICIT); break;
-        case MR_EXAMPLE_ID: MLT_CALL(MR_EXAMPLE_ID); break;
-        default: MLT_CALL(MR_NONE); break;
+      uint32_t ds_pk[16];
+      if (gp.mode == GM_DEAD) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) ds_pk[x] = 0u;
+      } else {
+        float ds[32];
+        if (gp.mode == GM_GEN) {
+          bwd_q_group_generic_tmem(t_s, t_dp, sc, rc, gl, b, g0, rel_s, bin, a.scale, a.neg, m2, linv, delta);
+          uint32_t v[32];
+          tmem_ld32(t_s, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) ds[x] = __uint_as_float(v[x]);
+        } else {
+          float t[32];
+          uint32_t v[32];
+          tmem_ld32(t_s, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
+          score_group<0>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
+          tmem_ld32(t_dp, v);
+          tmem_wait_ld();
+          float tot = 0.f;
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const float pv = ex2(fmaf(t[x], LOG2E, -m2)) * linv;   // dead: t = -inf -> 0
+            ds[x] = pv * (__uint_as_float(v[x]) - delta);
+            tot += ds[x];
+          }
+          // ---- relative-id bins ----
+          if (gp.mode == GM_FAST || gp.mode == GM_EDGE) {
+            if (gp.ccls == 1) accP += tot;
+            else if (gp.ccls == 2) accN += tot;
+            else if (gp.ccls == 3) accX += tot;
+          } else if (gp.mode == GM_DIAG) {
+            const int d0 = g0 - i + sc.D;
+            float* base = bin + row;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+              const int sl = min(max(d0 + x, 0), 2 * sc.D);
+              base[sl * TM] += ds[x];
+            }
+          } else if (gp.mode == GM_QS) {
+            const int d0 = rc.q_sent - g0;
+            float sp = 0.f;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) sp += (d0 == x) ? ds[x] : 0.f;
+            accX1 += sp;
+            accX += tot - sp;
+          } else {  // GM_KS
+            float sp = 0.f;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+              const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, x);
+              sp += (ks_j == i) ? ds[x] : 0.f;
+            }
+            accX1 += sp;
+            accX += tot - sp;
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
       }
-#undef MLT_CALL
       // each half packs into its OWN column range (the other half may still be reading its inputs)
       tmem_st16(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, ds_pk);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->ds_full[c & 1]);
+      gl = nl;
+    }
+    // flush the constant-class accumulators into this half's bins
+    if (R > 0) {
+      auto flush = [&](int id, float v) {
+        if (id >= 0 && id < R) bin[slot_of_id(id, pd, perm) * TM + row] += v;
+      };
+      const int dd = sc0.D;   // both segments of a row set share max_distance
+      flush(dd, accP);
+      flush(2 * dd, accN);
+      flush(2 * dd + 1, accX);
+      flush(2 * dd + 2, accX1);
     }
     // ---- epilogue: dq = scale * (dS.K + dallrel.E); publish dallrel ----
     named_bar_sync(1, NEW);  // both halves' bins complete
@@ -348,8 +427,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (R > 0) {
       const float* bin0 = bins;
       const float* bin1 = bins + 64 * TM;
+#pragma unroll 1
       for (int pid = 0; pid < R; ++pid) {
-        const float w = bin0[pid * TM + row] + bin1[pid * TM + row];
+        const int sl = slot_of_id(pid, pd, perm);
+        const float w = bin0[sl * TM + row] + bin1[sl * TM + row];
         if (hh == 0 && row_ok) a.dallrel[srow * R + pid] = w;
         // E row pid, columns [32 hh, 32 hh + 32): 4 swizzled 16-byte chunks (warp-broadcast reads)
         const uint8_t* erow = smem + SM_E + pid * 128;
@@ -439,63 +520,240 @@ __device__ __forceinline__ SrcRange src_range(const TcQuerySource& s, int j0) {
   return r;
 }
 
-template <int MR, int IR>
-__device__ __forceinline__ void bwd_kv_chunk(uint32_t (&s_raw)[32], uint32_t (&dp_raw)[32], uint32_t (&p_pk)[16],
-                                             uint32_t (&ds_pk)[16], const TcQuerySource& src, int b, int j,
-                                             bool key_ok, int q0, int ie, const float4* rs, const float* relq,
-                                             int rw, float scale, float neg) {
-  const Side& sd = src.q.side;
-  const int R = src.q.rows.R;
-  int k_e = 0, k_sent = -1;
-  if (MR == MR_EXAMPLE_ID && key_ok) k_e = __ldg(sd.k_eid + (int64_t)b * sd.k_len + j);
-  if (IR == IDR_CROSS_KSENT && key_ok) k_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + j);
-  float p_prev = 0.f, ds_prev = 0.f;
+// ---- column-centric scoring: the thread owns KEY row j, the 32 columns of a group are queries.
+// Same warp-uniform classification idea as tc_rowscore.cuh with the roles swapped: query-side
+// scalars are lane-held, the relative term comes from the staged per-query rows relq[ii][id].
+namespace colscore {
+using rowscore::GMode;
+using rowscore::GM_DEAD; using rowscore::GM_FAST; using rowscore::GM_EDGE; using rowscore::GM_DIAG;
+using rowscore::GM_QS; using rowscore::GM_KS; using rowscore::GM_GEN;
+
+struct SrcCtx {          // warp-uniform, one per query source
+  const TcQuerySource* src;
+  int ib, ie;            // query range of this key tile
+  int R, D, rw;
+  bool band;
+  int radius;
+  int mask_rule, id_rule;
+};
+struct KeyCtx {          // per thread
+  int j, row;
+  bool key_ok;
+  int k_e, k_sent;
+};
+struct QLanes {          // lane l holds the scalars of query (g0 + l)
+  int qe_l, qs_l;
+};
+struct Plan {
+  int mode;
+  int cid;               // id of the constant relative class (-1: none)
+  float mrow;
+  bool mask_pe;
+};
+
+__device__ __forceinline__ QLanes load_q_lanes(const SrcCtx& sc, int b, int g0, int lane) {
+  QLanes ql{0, -1};
+  const Side& sd = sc.src->q.side;
+  const int i = g0 + lane;
+  if (i >= 0 && i < sc.src->q.rows.len) {
+    if (sc.mask_rule == MR_EXAMPLE_ID) ql.qe_l = __ldg(sd.q_eid + (int64_t)b * sd.q_len + i);
+    if (sc.id_rule == IDR_CROSS_QSENT) ql.qs_l = __ldg(sd.sent + (int64_t)b * sd.sent_len + i);
+  }
+  return ql;
+}
+
+__device__ __forceinline__ void init_key(KeyCtx& kc, const SrcCtx& sc, int b) {
+  const Side& sd = sc.src->q.side;
+  kc.k_e = 0;
+  kc.k_sent = -1;
+  if (kc.key_ok && sc.mask_rule == MR_EXAMPLE_ID) kc.k_e = __ldg(sd.k_eid + (int64_t)b * sd.k_len + kc.j);
+  if (kc.key_ok && sc.id_rule == IDR_CROSS_KSENT) kc.k_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + kc.j);
+}
+
+// a = first key row of the warp, g0 = first query of the group.  off = key - query.
+__device__ __forceinline__ Plan classify(const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql, int a, int g0,
+                                         int lane, float neg) {
+  Plan pl;
+  pl.cid = -1;
+  pl.mrow = 0.f;
+  pl.mask_pe = false;
+  const int o_min = a - (g0 + 31), o_max = a + 31 - g0;
+  const bool dead = g0 >= sc.ie || (sc.band && (o_min > sc.radius || o_max < -sc.radius));
+  if (dead) {
+    pl.mode = GM_DEAD;
+    return pl;
+  }
+  const bool all_live = (g0 + 31 < sc.ie) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
+  bool gen = false;
+  if (sc.mask_rule == MR_EXPLICIT) {
+    gen = true;
+  } else if (sc.mask_rule == MR_EXAMPLE_ID) {
+    const int qe0 = __shfl_sync(0xffffffffu, ql.qe_l, 0);
+    const bool lane_oob = (g0 + lane >= sc.ie);
+    const bool uni = __all_sync(0xffffffffu, lane_oob || ql.qe_l == qe0);
+    pl.mask_pe = !uni;
+    pl.mrow = uni ? ((kc.k_e == qe0) ? 0.f : neg) : 0.f;
+  }
+  int rcls = 0;  // 0 const, 1 diag, 2 qs, 3 ks, 4 generic
+  switch (sc.id_rule) {
+    case IDR_NONE:
+      break;
+    case IDR_1D:
+      if (2 * sc.D + 1 > sc.R) rcls = 4;
+      else if (o_min >= sc.D) pl.cid = sc.D;
+      else if (o_max <= -sc.D) pl.cid = 2 * sc.D;
+      else rcls = 1;
+      break;
+    case IDR_CROSS_QSENT:
+      if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
+      pl.cid = 2 * sc.D + 1;
+      if (__any_sync(0xffffffffu, ql.qs_l >= a && ql.qs_l <= a + 31)) rcls = 2;
+      break;
+    case IDR_CROSS_KSENT:
+      if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
+      pl.cid = 2 * sc.D + 1;
+      if (__any_sync(0xffffffffu, kc.k_sent >= g0 && kc.k_sent < g0 + 32)) rcls = 3;
+      break;
+    default:
+      rcls = 4;
+  }
+  if (gen || rcls == 4) {
+    pl.mode = GM_GEN;
+    pl.mask_pe = false;
+  } else if (rcls == 0) {
+    pl.mode = all_live ? GM_FAST : GM_EDGE;
+  } else if (!all_live) {
+    pl.mode = GM_GEN;
+    pl.mask_pe = false;
+  } else {
+    pl.mode = rcls == 1 ? GM_DIAG : (rcls == 2 ? GM_QS : GM_KS);
+  }
+  return pl;
+}
+
+// Generic per-element evaluation; returns the score or -inf when (i, j) is dead.
+__device__ __forceinline__ float score_generic(float x, const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql,
+                                               int b, int g0, int ii, const float* relq, float scale, float neg) {
+  const Side& sd = sc.src->q.side;
+  const int i = g0 + ii;
+  const int off = kc.j - i;
+  const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, ii);
+  const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, ii);
+  const bool live = kc.key_ok && i < sc.ie && (!sc.band || (off <= sc.radius && off >= -sc.radius));
+  if (!live) return -INFINITY;
+  const int col = sc.band ? off + sc.radius : kc.j;
+  bool ok = true;
+  int id = -1;
+  switch (sc.mask_rule) {
+    case MR_EXPLICIT: ok = __ldg(sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) != 0; break;
+    case MR_EXAMPLE_ID: ok = (qe_i == kc.k_e); break;
+    default: break;
+  }
+  switch (sc.id_rule) {
+    case IDR_EXPLICIT: id = __ldg(sd.ids + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col); break;
+    case IDR_1D: id = rel_id_1d(off, sc.D); break;
+    case IDR_CROSS_QSENT: id = 2 * sc.D + 1 + (qs_i == kc.j ? 1 : 0); break;
+    case IDR_CROSS_KSENT: id = 2 * sc.D + 1 + (kc.k_sent == i ? 1 : 0); break;
+    case IDR_2D: id = rel_id_2d(i, kc.j, sd.npr, sd.core, sc.D); break;
+    default: break;
+  }
+  const float rel = (id >= 0 && id < sc.R) ? relq[ii * sc.rw + id] : 0.f;
+  float v = fmaf(x, scale, rel);
+  if (!ok) v += neg;
+  return v;
+}
+
+// Scores of one 32-query group in place.  `mode` is warp-uniform; GM_GEN is handled elsewhere.
+__device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, const SrcCtx& sc, const KeyCtx& kc,
+                                            const QLanes& ql, int g0, const float* relq, float scale, float neg) {
+  const int rw = sc.rw;
+  switch (pl.mode) {
+    case GM_FAST:
+      if (pl.cid >= 0) {
 #pragma unroll
-  for (int ii = 0; ii < 32; ++ii) {
-    const int i = q0 + ii;
-    const int off = j - i;
-    const bool live = key_ok && i < ie && (!src.q.band || (off <= src.q.radius && off >= -src.q.radius));
-    float pv = 0.f, ds = 0.f;
-    if (live) {
-      int q_e = 0, q_sent = -1;
-      if (MR == MR_EXAMPLE_ID) q_e = __ldg(sd.q_eid + (int64_t)b * sd.q_len + i);
-      if (IR == IDR_CROSS_QSENT) q_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + i);
-      bool ok;
-      int id;
-      side_ok_id<MR, IR>(sd, b, i, j, src.q.band ? off + src.q.radius : j, q_e, k_e, q_sent, k_sent, ok, id);
-      const bool idv = IR != IDR_NONE && id >= 0 && id < R;
-      float t = fmaf(__uint_as_float(s_raw[ii]), scale, idv ? relq[ii * rw + id] : 0.f);
-      if (!ok) t += neg;
-      const float4 st = rs[ii];  // (m2, linv, delta, -)
-      pv = ex2(fmaf(t, LOG2E, -st.x)) * st.y;
-      ds = pv * (__uint_as_float(dp_raw[ii]) - st.z);
+        for (int ii = 0; ii < 32; ++ii) t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid] + pl.mrow);
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) t[ii] = fmaf(t[ii], scale, pl.mrow);
+      }
+      break;
+    case GM_EDGE: {
+      const int d0 = kc.j - g0;  // off = d0 - ii
+      int ilo = 0, ihi = min(32, sc.ie - g0);
+      if (sc.band) {
+        ilo = max(ilo, d0 - sc.radius);
+        ihi = min(ihi, d0 + sc.radius + 1);
+      }
+      if (!kc.key_ok) ihi = ilo;
+      const unsigned span = (unsigned)max(ihi - ilo, 0);
+      const int cid = pl.cid >= 0 ? pl.cid : 0;
+      const float use = pl.cid >= 0 ? 1.f : 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 32; ++ii) {
+        const float v = fmaf(t[ii], scale, fmaf(use, relq[ii * rw + cid], pl.mrow));
+        t[ii] = ((unsigned)(ii - ilo) < span) ? v : -INFINITY;
+      }
+      break;
     }
-    if (ii & 1) {
-      p_pk[ii >> 1] = pack_bf16x2(p_prev, pv);
-      ds_pk[ii >> 1] = pack_bf16x2(ds_prev, ds);
-    } else {
-      p_prev = pv;
-      ds_prev = ds;
+    case GM_DIAG: {
+      const int d0 = kc.j - g0;
+#pragma unroll
+      for (int ii = 0; ii < 32; ++ii) {
+        const int o = min(max(d0 - ii, -sc.D), sc.D);
+        const int id = o >= 0 ? o : sc.D - o;
+        t[ii] = fmaf(t[ii], scale, relq[ii * rw + id] + pl.mrow);
+      }
+      break;
+    }
+    case GM_QS: {
+#pragma unroll
+      for (int ii = 0; ii < 32; ++ii) {
+        const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, ii);
+        t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (qs_i == kc.j ? 1 : 0)] + pl.mrow);
+      }
+      break;
+    }
+    case GM_KS: {
+      const int sp = kc.k_sent - g0;
+#pragma unroll
+      for (int ii = 0; ii < 32; ++ii)
+        t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (sp == ii ? 1 : 0)] + pl.mrow);
+      break;
+    }
+    default:
+      return;
+  }
+  if (pl.mask_pe) {
+#pragma unroll
+    for (int ii = 0; ii < 32; ++ii) {
+      const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, ii);
+      t[ii] += (qe_i == kc.k_e) ? 0.f : neg;
     }
   }
 }
 
-template <int MR>
-__device__ __forceinline__ void bwd_kv_chunk_ir(uint32_t (&s_raw)[32], uint32_t (&dp_raw)[32], uint32_t (&p_pk)[16],
-                                                uint32_t (&ds_pk)[16], const TcQuerySource& src, int b, int j,
-                                                bool key_ok, int q0, int ie, const float4* rs, const float* relq,
-                                                int rw, float scale, float neg) {
-#define MLT_CALL(IRV) bwd_kv_chunk<MR, IRV>(s_raw, dp_raw, p_pk, ds_pk, src, b, j, key_ok, q0, ie, rs, relq, rw, scale, neg)
-  switch (src.q.side.id_rule) {
-    case IDR_EXPLICIT: MLT_CALL(IDR_EXPLICIT); break;
-    case IDR_1D: MLT_CALL(IDR_1D); break;
-    case IDR_CROSS_QSENT: MLT_CALL(IDR_CROSS_QSENT); break;
-    case IDR_CROSS_KSENT: MLT_CALL(IDR_CROSS_KSENT); break;
-    case IDR_2D: MLT_CALL(IDR_2D); break;
-    default: MLT_CALL(IDR_NONE); break;
+// GM_GEN: real loop, TMEM as scratch.  Leaves p (fp32) in the S^T column and ds in the dP^T column.
+__device__ __forceinline__ void group_generic_tmem(uint32_t t_s, uint32_t t_dp, const SrcCtx& sc, const KeyCtx& kc,
+                                                   const QLanes& ql, int b, int g0, const float4* rs,
+                                                   const float* relq, float scale, float neg) {
+#pragma unroll 1
+  for (int ii = 0; ii < 32; ++ii) {
+    const uint32_t raw = tmem_ld1(t_s + ii);
+    const uint32_t dpr = tmem_ld1(t_dp + ii);
+    tmem_wait_ld();
+    const float t = score_generic(__uint_as_float(raw), sc, kc, ql, b, g0, ii, relq, scale, neg);
+    float pv = 0.f, ds = 0.f;
+    if (t != -INFINITY) {
+      const float4 st = rs[ii];
+      pv = ex2(fmaf(t, LOG2E, -st.x)) * st.y;
+      ds = pv * (__uint_as_float(dpr) - st.z);
+    }
+    tmem_st1(t_s + ii, __float_as_uint(pv));
+    tmem_st1(t_dp + ii, __float_as_uint(ds));
   }
-#undef MLT_CALL
+  tmem_wait_st();
 }
+}  // namespace colscore
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -600,38 +858,103 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       }
     }
   } else {
+    using namespace colscore;
     const int row = (warp & 3) * 32 + lane;
     const int hh = warp >> 2;
     const int j = j0 + row;
     const bool key_ok = j < p.len;
+    const int wrow0 = j0 + (warp & 3) * 32;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    auto make_src = [&](const TcQuerySource& src, const SrcRange& r) {
+      SrcCtx sc;
+      sc.src = &src;
+      sc.ib = r.ib;
+      sc.ie = r.ie;
+      sc.R = src.q.rows.R;
+      sc.D = src.q.side.max_distance;
+      sc.rw = src.rw;
+      sc.band = src.q.band != 0;
+      sc.radius = src.q.radius;
+      sc.mask_rule = src.q.side.mask_rule;
+      sc.id_rule = sc.R > 0 ? src.q.side.id_rule : IDR_NONE;
+      return sc;
+    };
+    const SrcCtx sc0 = make_src(p.src[0], r0);
+    const SrcCtx sc1 = make_src(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
+    KeyCtx kc0, kc1;
+    kc0.j = kc1.j = j;
+    kc0.row = kc1.row = row;
+    kc0.key_ok = kc1.key_ok = key_ok;
+    init_key(kc0, sc0, b);
+    init_key(kc1, sc1, b);
+    auto chunk_q0 = [&](int c) { return (c < r0.n ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN) + hh * 32; };
+    QLanes ql{0, -1};
+    if (nchunks > 0) ql = load_q_lanes(0 < r0.n ? sc0 : sc1, b, chunk_q0(0), lane);
     for (int c = 0; c < nchunks; ++c) {
       const int st = c % NST;
       const bool first = c < r0.n;
-      const TcQuerySource& src = first ? p.src[0] : p.src[1];
-      const int q0 = (first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN) + hh * 32;
-      const int ie = first ? r0.ie : r1.ie;
+      const SrcCtx& sc = first ? sc0 : sc1;
+      const KeyCtx& kc = first ? kc0 : kc1;
+      const int g0 = chunk_q0(c);
+      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32;
+      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32;
+      QLanes nl{0, -1};
+      if (c + 1 < nchunks) nl = load_q_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_q0(c + 1), lane);
+      const Plan pl = classify(sc, kc, ql, wrow0, g0, lane, p.neg);
       mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
       mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
       tc_fence_after_sync();
       const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + hh * 32;
-      const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + hh * 32 * src.rw;
-      uint32_t s_raw[32], dp_raw[32], p_pk[16], ds_pk[16];
-      tmem_ld32(tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32, s_raw);
-      tmem_ld32(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, dp_raw);
-      tmem_wait_ld();
-#define MLT_CALL(MRV) bwd_kv_chunk_ir<MRV>(s_raw, dp_raw, p_pk, ds_pk, src, b, j, key_ok, q0, ie, rs, relq, src.rw, p.scale, p.neg)
-      switch (src.q.side.mask_rule) {
-        case MR_EXPLICIT: MLT_CALL(MR_EXPLICIT); break;
-        case MR_EXAMPLE_ID: MLT_CALL(MR_EXAMPLE_ID); break;
-        default: MLT_CALL(MR_NONE); break;
+      const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + hh * 32 * sc.rw;
+      uint32_t p_pk[16], ds_pk[16];
+      if (pl.mode == GM_DEAD) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
+      } else if (pl.mode == GM_GEN) {
+        group_generic_tmem(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg);
+        uint32_t v[32];
+        tmem_ld32(t_s, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int x = 0; x < 16; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+        tmem_ld32(t_dp, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int x = 0; x < 16; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+      } else {
+        float t[32];
+        uint32_t v[32];
+        tmem_ld32(t_s, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
+        score_group(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg);
+        tmem_ld32(t_dp, v);
+        tmem_wait_ld();
+        const bool guard = (pl.mode == GM_EDGE);   // dead columns may carry garbage row records
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int y = 0; y < 2; ++y) {
+            const int ii = 2 * x + y;
+            const float4 r4 = rs[ii];   // (m*log2e, 1/l, delta, -): warp-broadcast LDS.128
+            const float e = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
+            const float d = e * (__uint_as_float(v[ii]) - r4.z);
+            const bool dead = guard && (t[ii] == -INFINITY);
+            pv[y] = dead ? 0.f : e;
+            dsv[y] = dead ? 0.f : d;
+          }
+          p_pk[x] = pack_bf16x2(pv[0], pv[1]);
+          ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
+        }
       }
-#undef MLT_CALL
       tmem_st16(tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32, p_pk);
       tmem_st16(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, ds_pk);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->pds_full[c & 1]);
+      ql = nl;
     }
     mbar_wait_warp(&bars->acc_full, 0);
     tc_fence_after_sync();
