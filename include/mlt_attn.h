@@ -189,6 +189,45 @@ typedef struct {
   float* d_global_bias;
 } mlt_gl_grads;
 
+/* ---- long rows only: QkvRelativeLocalAttention ------------------------------------------- */
+typedef struct {
+  int32_t abi_version;
+  int32_t dtype;
+  int32_t impl;
+  int32_t B, L, G, H, d, R;   /* G = number of side keys (0: none) */
+  int32_t local_radius;
+  float scale;
+  float neg;
+  float dropout_p;            /* must be 0 */
+  uint64_t dropout_seed;
+  mlt_tensor4 q, k, v;        /* [B, L, H, d] */
+  mlt_tensor4 side_k, side_v; /* [B, G, H, d]; ignored when G == 0 */
+  mlt_tensor4 out;            /* [B, L, H, d] */
+  float* stats;               /* [B, H, L, 2] */
+  mlt_rel_tables tables;
+  int32_t side_mode;
+  /* MLT_SIDE_EXPLICIT: att_mask / relative_att_ids [B, L, 2r+1]; side_* [B, L, G] */
+  const int32_t* att_mask;
+  const int32_t* relative_att_ids;
+  const int32_t* side_att_mask;
+  const int32_t* side_relative_att_ids;
+  /* MLT_SIDE_COMPACT: as in mlt_gl_params (l2l and l2g blocks) */
+  const int32_t* example_ids;       /* [B, L] */
+  const int32_t* side_example_ids;  /* [B, G] */
+  const int32_t* sentence_ids;      /* [B, L] */
+  int32_t max_distance;
+  void* workspace;
+  size_t workspace_bytes;
+} mlt_local_params;
+
+typedef struct {
+  mlt_tensor4 d_out;                     /* input */
+  mlt_tensor4 d_q, d_k, d_v;             /* outputs */
+  mlt_tensor4 d_side_k, d_side_v;        /* outputs (G > 0) */
+  float* d_emb;                          /* fp32 [R, H, d] */
+  float* d_bias;                         /* fp32 [R, H] */
+} mlt_local_grads;
+
 /* ---- entry points -------------------------------------------------------------------- */
 
 /* Library / ABI identification. */
@@ -213,6 +252,13 @@ MLT_API int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_gr
 /* Contract (B).  Replaces the core of FusedGlobalLocalAttention.call [UPSTREAM-RECALLED]. */
 MLT_API int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream);
 MLT_API int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_stream);
+
+/* Long rows only.  Replaces QkvRelativeLocalAttention.call(queries, keys, values, att_mask,
+ * relative_att_ids, side_keys, side_values, side_att_mask, side_relative_att_ids)
+ * [UPSTREAM-RECALLED]. */
+MLT_API size_t mlt_local_workspace_bytes(const mlt_local_params* p, int bwd);
+MLT_API int mlt_local_rel_attn_fwd(const mlt_local_params* p, void* cuda_stream);
+MLT_API int mlt_local_rel_attn_bwd(const mlt_local_params* p, const mlt_local_grads* g, void* cuda_stream);
 
 /* Device-side side-input constructors (write the explicit int32 tensors the Keras signature
  * carries; bit-exact with the host constructors).

@@ -86,6 +86,28 @@ class GlGrads(C.Structure):
   ]
 
 
+class LocalParams(C.Structure):
+  _fields_ = [
+      ('abi_version', C.c_int32), ('dtype', C.c_int32), ('impl', C.c_int32),
+      ('B', C.c_int32), ('L', C.c_int32), ('G', C.c_int32), ('H', C.c_int32),
+      ('d', C.c_int32), ('R', C.c_int32), ('local_radius', C.c_int32),
+      ('scale', C.c_float), ('neg', C.c_float), ('dropout_p', C.c_float),
+      ('dropout_seed', C.c_uint64),
+      ('q', Tensor4), ('k', Tensor4), ('v', Tensor4), ('side_k', Tensor4), ('side_v', Tensor4),
+      ('out', Tensor4), ('stats', C.c_void_p), ('tables', RelTables), ('side_mode', C.c_int32),
+      ('att_mask', C.c_void_p), ('relative_att_ids', C.c_void_p),
+      ('side_att_mask', C.c_void_p), ('side_relative_att_ids', C.c_void_p),
+      ('example_ids', C.c_void_p), ('side_example_ids', C.c_void_p), ('sentence_ids', C.c_void_p),
+      ('max_distance', C.c_int32), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+  ]
+
+
+class LocalGrads(C.Structure):
+  _fields_ = [('d_out', Tensor4), ('d_q', Tensor4), ('d_k', Tensor4), ('d_v', Tensor4),
+              ('d_side_k', Tensor4), ('d_side_v', Tensor4), ('d_emb', C.c_void_p),
+              ('d_bias', C.c_void_p)]
+
+
 class KernelTime(C.Structure):
   _fields_ = [('name', C.c_char * 48), ('ms', C.c_float), ('flops', C.c_double),
               ('bytes', C.c_double)]
@@ -98,6 +120,7 @@ EXPORTS = (
     'mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd', 'mlt_gl_attn_bwd',
     'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs',
     'mlt_profile_enable', 'mlt_profile_read', 'mlt_launch_count',
+    'mlt_local_workspace_bytes', 'mlt_local_rel_attn_fwd', 'mlt_local_rel_attn_bwd',
 )
 
 _lib = None
@@ -142,6 +165,12 @@ def load() -> C.CDLL:
   for name in ('mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd',
                'mlt_gl_attn_bwd', 'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs'):
     getattr(lib, name).restype = C.c_int
+  lib.mlt_local_workspace_bytes.argtypes = [C.POINTER(LocalParams), C.c_int]
+  lib.mlt_local_workspace_bytes.restype = C.c_size_t
+  lib.mlt_local_rel_attn_fwd.argtypes = [C.POINTER(LocalParams), C.c_void_p]
+  lib.mlt_local_rel_attn_fwd.restype = C.c_int
+  lib.mlt_local_rel_attn_bwd.argtypes = [C.POINTER(LocalParams), C.POINTER(LocalGrads), C.c_void_p]
+  lib.mlt_local_rel_attn_bwd.restype = C.c_int
   lib.mlt_profile_enable.argtypes = [C.c_int]
   lib.mlt_profile_read.argtypes = [C.POINTER(KernelTime), C.c_int]
   lib.mlt_launch_count.restype = C.c_longlong

@@ -9,6 +9,7 @@
 #include "tc_api.cuh"
 
 #include <cstdio>
+#include <mutex>
 
 namespace {
 
@@ -225,6 +226,66 @@ KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, i
   return s;
 }
 
+// ---- fork / join helper: runs independent kernels of one call on a second, library-owned
+// stream so that the few long-running global-row tiles overlap the many long-row tiles.
+// Plain event fork/join (CUDA-graph-capture friendly).  Disabled while per-kernel profiling is
+// on (timings must stay attributable) and when event/stream creation failed.
+struct ForkCtx {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+constexpr int kMaxDevices = 64;
+ForkCtx g_fork[kMaxDevices];
+std::once_flag g_fork_once[kMaxDevices];
+std::mutex g_fork_mu;
+
+ForkCtx* get_fork() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::call_once(g_fork_once[dev], [dev] {
+    ForkCtx& f = g_fork[dev];
+    f.ok = cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) == cudaSuccess;
+  });
+  return g_fork[dev].ok ? &g_fork[dev] : nullptr;
+}
+
+// RAII: between construction and join() the side stream is ordered after everything enqueued on
+// `st` so far; join() orders `st` after the side stream.  Holds a mutex for the enqueue window.
+class ForkScope {
+ public:
+  explicit ForkScope(cudaStream_t st) : st_(st), f_(profile_enabled() ? nullptr : get_fork()) {
+    if (f_) {
+      g_fork_mu.lock();
+      if (cudaEventRecord(f_->fork, st_) != cudaSuccess || cudaStreamWaitEvent(f_->s2, f_->fork, 0) != cudaSuccess) {
+        g_fork_mu.unlock();
+        f_ = nullptr;
+      }
+    }
+  }
+  cudaStream_t side() const { return f_ ? f_->s2 : st_; }
+  void join() {
+    if (f_ && !joined_) {
+      cudaEventRecord(f_->join, f_->s2);
+      cudaStreamWaitEvent(st_, f_->join, 0);
+      joined_ = true;
+    }
+  }
+  ~ForkScope() {
+    if (f_) {
+      join();
+      g_fork_mu.unlock();
+    }
+  }
+
+ private:
+  cudaStream_t st_;
+  ForkCtx* f_;
+  bool joined_ = false;
+};
+
 FwdArgs dense_fwd_args(const mlt_dense_params* p) {
   FwdArgs a{};
   a.rows = dense_rows(p);
@@ -433,10 +494,11 @@ int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
   const double bh = (double)p->B * p->H;
   const double pl = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
   const double pg = (double)p->G * (p->G + p->L);
-  // global rows first: few, long-running tiles
+  // global rows (few, long-running tiles) on the side stream, overlapping the long rows
+  ForkScope fk(st);
   MLT_TRY(launch_fwd(gl_global_fwd_args(p), tc, p->dtype, p->d, "fwd_global_rows",
                      fwd_flops(bh, pg, p->d, p->R, p->G),
-                     qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), st));
+                     qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), fk.side()));
   MLT_TRY(launch_fwd(gl_long_fwd_args(p), tc, p->dtype, p->d, "fwd_long_rows",
                      fwd_flops(bh, pl, p->d, p->R, p->L),
                      qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
@@ -507,14 +569,18 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   const double bh = (double)p->B * p->H, dd = p->d, RR = p->R;
   const double p_l2l = band_pairs(p->L, p->local_radius), p_lg = (double)p->L * p->G,
                p_gg = (double)p->G * p->G;
-  MLT_TRY(launch_bwd_q(qg, tc, tc_wg, p->dtype, p->d, "bwd_q_global_rows",
-                       bh * (4 * dd * (p_gg + p_lg) + 2 * dd * RR * p->G),
-                       qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st));
+  {
+    ForkScope fk(st);
+    MLT_TRY(launch_bwd_q(qg, tc, tc_wg, p->dtype, p->d, "bwd_q_global_rows",
+                         bh * (4 * dd * (p_gg + p_lg) + 2 * dd * RR * p->G),
+                         qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), fk.side()));
   MLT_TRY(launch_bwd_q(ql, tc, tc_wl, p->dtype, p->d, "bwd_q_long_rows",
                        bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
                        qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
+  }
+  ForkScope fk2(st);
   MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
-                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), st));
+                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), fk2.side()));
   MLT_TRY(launch_bwd_kv(kl, tc, ws_lg, p->dtype, p->d, "bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
                         qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   if (p->R > 0) {
@@ -532,6 +598,149 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                       qkv_bytes(bh, p->G, p->d, p->dtype, 1), st, 2);
       MLT_CUDA(simt_launch_table_grad(tg, p->dtype, st));
     }
+  }
+  return MLT_OK;
+}
+
+// ---- long rows only (QkvRelativeLocalAttention) ---------------------------------------------
+namespace {
+int validate_local(const mlt_local_params* p) {
+  if (!p) return MLT_ERR_NULL;
+  if (p->abi_version != MLT_ABI_VERSION) return MLT_ERR_UNSUPPORTED;
+  if (p->dtype != MLT_F32 && p->dtype != MLT_BF16) return MLT_ERR_DTYPE;
+  if (p->B <= 0 || p->L <= 0 || p->G < 0 || p->H <= 0 || p->d <= 0 || p->R < 0 || p->local_radius < 1)
+    return MLT_ERR_SHAPE;
+  if (p->R > 64 || !simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
+  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  MLT_TRY(check_t4(p->q, p->dtype, p->d));
+  MLT_TRY(check_t4(p->k, p->dtype, p->d));
+  MLT_TRY(check_t4(p->v, p->dtype, p->d));
+  MLT_TRY(check_t4(p->out, p->dtype, p->d));
+  if (p->G > 0) {
+    MLT_TRY(check_t4(p->side_k, p->dtype, p->d));
+    MLT_TRY(check_t4(p->side_v, p->dtype, p->d));
+  }
+  if (!p->stats) return MLT_ERR_NULL;
+  if ((p->tables.emb == nullptr) != (p->tables.bias == nullptr)) return MLT_ERR_NULL;
+  if (p->R > 0 && !p->tables.emb) return MLT_ERR_NULL;
+  if (p->side_mode == MLT_SIDE_COMPACT) {
+    if (!p->example_ids || (p->G > 0 && !p->side_example_ids)) return MLT_ERR_NULL;
+    if (p->R > 0 && p->G > 0 && !p->sentence_ids) return MLT_ERR_NULL;
+    if (p->max_distance < 0) return MLT_ERR_SHAPE;
+  } else if (p->side_mode != MLT_SIDE_EXPLICIT) {
+    return MLT_ERR_UNSUPPORTED;
+  }
+  return MLT_OK;
+}
+
+// Reuse the global-local side builder through an equivalent mlt_gl_params view.
+mlt_gl_params local_as_gl(const mlt_local_params* p) {
+  mlt_gl_params g{};
+  g.dtype = p->dtype; g.impl = p->impl;
+  g.B = p->B; g.L = p->L; g.G = p->G > 0 ? p->G : 1; g.H = p->H; g.d = p->d; g.R = p->R;
+  g.local_radius = p->local_radius;
+  g.side_mode = p->side_mode;
+  g.l2l_att_mask = p->att_mask; g.l2l_relative_att_ids = p->relative_att_ids;
+  g.l2g_att_mask = p->side_att_mask; g.l2g_relative_att_ids = p->side_relative_att_ids;
+  g.long_example_ids = p->example_ids; g.global_example_ids = p->side_example_ids;
+  g.sentence_ids = p->sentence_ids; g.max_distance = p->max_distance;
+  return g;
+}
+
+FwdArgs local_fwd_args(const mlt_local_params* p) {
+  const mlt_gl_params g = local_as_gl(p);
+  FwdArgs a{};
+  a.rows = RowSet{to_t4(p->q), p->L, p->tables.emb, p->tables.bias, p->R};
+  a.seg[0] = make_seg(p->k, p->v, p->L, 1, p->local_radius, gl_side(&g, L2L));
+  a.nseg = 1;
+  if (p->G > 0) {
+    a.seg[1] = make_seg(p->side_k, p->side_v, p->G, 0, 0, gl_side(&g, L2G));
+    a.nseg = 2;
+  }
+  a.out = to_t4(p->out);
+  a.stats = p->stats;
+  a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  return a;
+}
+}  // namespace
+
+size_t mlt_local_workspace_bytes(const mlt_local_params* p, int bwd) {
+  if (!p) return 0;
+  size_t n = kAlign;
+  if (bwd) n += row_ws_bytes(p->B, p->H, p->L, p->R, p->d) + tc_bwd_rows_ws_bytes(p->B, p->H, p->L, p->R);
+  return n;
+}
+
+int mlt_local_rel_attn_fwd(const mlt_local_params* p, void* cuda_stream) {
+  MLT_TRY(validate_local(p));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const FwdArgs a = local_fwd_args(p);
+  const bool tc = p->impl != MLT_IMPL_SIMT && tc_fwd_args_supported(a, p->dtype, p->d);
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  const double bh = (double)p->B * p->H;
+  const double pairs = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
+  return launch_fwd(a, tc, p->dtype, p->d, "fwd_local_rows", fwd_flops(bh, pairs, p->d, p->R, p->L),
+                    qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
+}
+
+int mlt_local_rel_attn_bwd(const mlt_local_params* p, const mlt_local_grads* g, void* cuda_stream) {
+  MLT_TRY(validate_local(p));
+  if (!g) return MLT_ERR_NULL;
+  MLT_TRY(check_t4(g->d_out, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_q, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_k, p->dtype, p->d));
+  MLT_TRY(check_t4(g->d_v, p->dtype, p->d));
+  if (p->G > 0) {
+    MLT_TRY(check_t4(g->d_side_k, p->dtype, p->d));
+    MLT_TRY(check_t4(g->d_side_v, p->dtype, p->d));
+  }
+  if (p->R > 0 && (!g->d_emb || !g->d_bias)) return MLT_ERR_NULL;
+  if (!p->workspace || p->workspace_bytes < mlt_local_workspace_bytes(p, 1)) return MLT_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
+  RowWs ws = carve_row_ws(wp, p->B, p->H, p->L, p->R, p->d);
+  void* tcw[2] = {wp, wp};
+  const FwdArgs f = local_fwd_args(p);
+  BwdQArgs q{};
+  q.rows = f.rows;
+  q.seg[0] = f.seg[0];
+  q.seg[1] = f.seg[1];
+  q.nseg = f.nseg;
+  q.out = to_t4(p->out); q.d_out = to_t4(g->d_out); q.d_q = to_t4(g->d_q);
+  q.stats = p->stats; q.delta = ws.delta; q.allrel = ws.allrel; q.dallrel = ws.dallrel;
+  q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
+  BwdKVArgs kl{};
+  kl.k = to_t4(p->k); kl.v = to_t4(p->v); kl.d_k = to_t4(g->d_k); kl.d_v = to_t4(g->d_v);
+  kl.len = p->L;
+  kl.src[0] = QuerySource{f.rows, to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 1, p->local_radius, f.seg[0].side};
+  kl.nsrc = 1;
+  kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
+  BwdKVArgs ks{};
+  if (p->G > 0) {
+    ks.k = to_t4(p->side_k); ks.v = to_t4(p->side_v); ks.d_k = to_t4(g->d_side_k); ks.d_v = to_t4(g->d_side_v);
+    ks.len = p->G;
+    ks.src[0] = QuerySource{f.rows, to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, f.seg[1].side};
+    ks.nsrc = 1;
+    ks.B = p->B; ks.H = p->H; ks.scale = p->scale; ks.neg = p->neg;
+  }
+  const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(q, p->dtype, p->d) && bwd_kv_on_tc(kl) &&
+                  (p->G == 0 || bwd_kv_on_tc(ks));
+  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  const double bh = (double)p->B * p->H, dd = p->d;
+  const double p_l = band_pairs(p->L, p->local_radius), p_s = (double)p->L * p->G;
+  MLT_TRY(launch_bwd_q(q, tc, tcw[0], p->dtype, p->d, "bwd_q_local_rows",
+                       bh * (4 * dd * (p_l + p_s) + 2 * dd * p->R * p->L),
+                       qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
+  MLT_TRY(launch_bwd_kv(kl, tc, tcw, p->dtype, p->d, "bwd_kv_local_keys", bh * 4 * dd * p_l,
+                        qkv_bytes(bh, 6.0 * p->L, p->d, p->dtype, 1), st));
+  if (p->G > 0)
+    MLT_TRY(launch_bwd_kv(ks, tc, tcw, p->dtype, p->d, "bwd_kv_side_keys", bh * 4 * dd * p_s,
+                          qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), st));
+  if (p->R > 0) {
+    TableGradArgs t{to_t4(p->q), p->L, ws.dallrel, ws.partial, ws.partial_bias, g->d_emb, g->d_bias,
+                    p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};
+    ProfileScope ps("simt_table_grad_local", bh * 2.0 * dd * p->R * p->L, qkv_bytes(bh, p->L, p->d, p->dtype, 1), st, 2);
+    MLT_CUDA(simt_launch_table_grad(t, p->dtype, st));
   }
   return MLT_OK;
 }

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(NT) table_grad_partial_kernel(const TableGradA
   const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int R = a.R;
   __shared__ __align__(16) float qs[KC * D];
-  __shared__ float ds[KC * RMAX];
+  __shared__ __align__(16) float ds[KC * RMAX];
   const int c = tid % D;
   const int g = tid / D;
   float acc[NACC][CPT];
@@ -451,12 +451,17 @@ __global__ void __launch_bounds__(NT) table_grad_partial_kernel(const TableGradA
     }
     __syncthreads();
     if (g < GROUPS) {
+      // this thread owns ids [g * NACC, (g + 1) * NACC): contiguous, read as warp-broadcast float4
       for (int rr = 0; rr < n; ++rr) {
+        const float qv = qs[rr * D + c];
+        const float4* w4 = reinterpret_cast<const float4*>(ds + rr * RMAX + g * NACC);
 #pragma unroll
-        for (int x = 0; x < NACC; ++x) {
-          const float w = ds[rr * RMAX + g + x * GROUPS];
-#pragma unroll
-          for (int y = 0; y < CPT; ++y) acc[x][y] = fmaf(w, qs[rr * D + c + y * NT], acc[x][y]);
+        for (int x4 = 0; x4 < NACC / 4; ++x4) {
+          const float4 w = w4[x4];
+          acc[4 * x4 + 0][0] = fmaf(w.x, qv, acc[4 * x4 + 0][0]);
+          acc[4 * x4 + 1][0] = fmaf(w.y, qv, acc[4 * x4 + 1][0]);
+          acc[4 * x4 + 2][0] = fmaf(w.z, qv, acc[4 * x4 + 2][0]);
+          acc[4 * x4 + 3][0] = fmaf(w.w, qv, acc[4 * x4 + 3][0]);
         }
       }
     }
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(NT) table_grad_partial_kernel(const TableGradA
   if (g < GROUPS) {
 #pragma unroll
     for (int x = 0; x < NACC; ++x) {
-      const int p = g + x * GROUPS;
+      const int p = g * NACC + x;
       if (p < R) {
 #pragma unroll
         for (int y = 0; y < CPT; ++y) a.partial[(pidx * R + p) * D + c + y * NT] = acc[x][y];

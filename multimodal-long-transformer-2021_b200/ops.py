@@ -20,8 +20,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (DenseGrads, DenseParams, GlGrads, GlParams, IdLayout, RelTables,
-                   Tensor4)
+from ._lib import (DenseGrads, DenseParams, GlGrads, GlParams, IdLayout, LocalGrads,
+                   LocalParams, RelTables, Tensor4)
 from .feature_utils import CompactSideInputs
 
 NEG = -1e9  # large_compatible_negative [UPSTREAM-RECALLED], SURVEY.md note N2
@@ -340,6 +340,145 @@ def dense_relative_attention(q, k, v, emb=None, bias=None, att_mask=None,
   """
   cfg = _DenseCfg(att_mask, relative_att_ids, compact, impl)
   return _DenseRelAttnFn.apply(q, k, v, emb, bias, cfg)
+
+
+# ---------------------------------------------------------------------------
+# Long rows only (QkvRelativeLocalAttention)
+
+
+class LocalCompactSideInputs:
+  """Compact descriptors for the long rows: example ids of the long / side tokens + sentence ids."""
+
+  def __init__(self, example_ids, side_example_ids=None, sentence_ids=None, max_distance=0):
+    self.example_ids = example_ids
+    self.side_example_ids = side_example_ids
+    self.sentence_ids = sentence_ids
+    self.max_distance = max_distance
+
+
+class _LocalCfg:
+
+  def __init__(self, local_radius, att_mask, relative_att_ids, side_att_mask,
+               side_relative_att_ids, compact, impl):
+    self.local_radius = local_radius
+    self.att_mask = att_mask
+    self.relative_att_ids = relative_att_ids
+    self.side_att_mask = side_att_mask
+    self.side_relative_att_ids = side_relative_att_ids
+    self.compact = compact
+    self.impl = impl
+
+
+def _fill_local_params(p: LocalParams, q, k, v, sk, sv, emb, bias, r_vocab, cfg: _LocalCfg, keep):
+  b, l, h, d = q.shape
+  g = 0 if sk is None else sk.shape[1]
+  p.abi_version = _lib.MLT_ABI_VERSION
+  p.dtype = _dtype_enum(q)
+  p.impl = _lib.IMPL[cfg.impl]
+  p.B, p.L, p.G, p.H, p.d, p.R = b, l, g, h, d, r_vocab
+  p.local_radius = cfg.local_radius
+  p.scale = 1.0 / math.sqrt(d)
+  p.neg = NEG
+  p.dropout_p = 0.0
+  p.q, p.k, p.v = _t4(q), _t4(k), _t4(v)
+  if g:
+    p.side_k, p.side_v = _t4(sk), _t4(sv)
+  p.tables = RelTables(_ptr(emb), _ptr(bias))
+  w = 2 * cfg.local_radius + 1
+  if cfg.compact is not None:
+    c = cfg.compact
+    p.side_mode = _lib.MLT_SIDE_COMPACT
+    e = _int32(c.example_ids, (b, l), 'example_ids')
+    se = _int32(c.side_example_ids, (b, g), 'side_example_ids') if g else None
+    sid = _int32(c.sentence_ids, (b, l), 'sentence_ids') if c.sentence_ids is not None else None
+    keep += [e, se, sid]
+    p.example_ids, p.side_example_ids, p.sentence_ids = _ptr(e), _ptr(se), _ptr(sid)
+    p.max_distance = c.max_distance
+  else:
+    p.side_mode = _lib.MLT_SIDE_EXPLICIT
+    m = _int32(cfg.att_mask, (b, l, w), 'att_mask')
+    ids = _int32(cfg.relative_att_ids, (b, l, w), 'relative_att_ids')
+    sm = _int32(cfg.side_att_mask, (b, l, g), 'side_att_mask') if g else None
+    sids = _int32(cfg.side_relative_att_ids, (b, l, g), 'side_relative_att_ids') if g else None
+    keep += [m, ids, sm, sids]
+    p.att_mask, p.relative_att_ids = _ptr(m), _ptr(ids)
+    p.side_att_mask, p.side_relative_att_ids = _ptr(sm), _ptr(sids)
+
+
+class _LocalRelAttnFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, q, k, v, sk, sv, emb, bias, cfg):
+    lib = _lib.load()
+    q, k, v = map(_prep, (q, k, v))
+    if sk is not None:
+      sk, sv = _prep(sk), _prep(sv)
+    b, l, h, d = q.shape
+    emb, bias, r_vocab = _tables(emb, bias, h, d, q.dtype, 'tables')
+    out = torch.empty((b, l, h, d), dtype=q.dtype, device=q.device)
+    stats = torch.empty((b, h, l, 2), dtype=torch.float32, device=q.device)
+    p = LocalParams()
+    keep = []
+    _fill_local_params(p, q, k, v, sk, sv, emb, bias, r_vocab, cfg, keep)
+    p.out, p.stats = _t4(out), stats.data_ptr()
+    nbytes = lib.mlt_local_workspace_bytes(C.byref(p), 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    _lib.check(lib.mlt_local_rel_attn_fwd(C.byref(p), _stream()), 'mlt_local_rel_attn_fwd')
+    ctx.cfg, ctx.r_vocab = cfg, r_vocab
+    ctx.save_for_backward(q, k, v, sk, sv, emb, bias, out, stats)
+    return out
+
+  @staticmethod
+  def backward(ctx, d_out):
+    lib = _lib.load()
+    q, k, v, sk, sv, emb, bias, out, stats = ctx.saved_tensors
+    b, l, h, d = q.shape
+    r_vocab = ctx.r_vocab
+    d_out = _prep(d_out.to(q.dtype))
+    p = LocalParams()
+    keep = []
+    _fill_local_params(p, q, k, v, sk, sv, emb, bias, r_vocab, ctx.cfg, keep)
+    p.out, p.stats = _t4(out), stats.data_ptr()
+    nbytes = lib.mlt_local_workspace_bytes(C.byref(p), 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    gr = LocalGrads()
+    gr.d_out, gr.d_q, gr.d_k, gr.d_v = _t4(d_out), _t4(dq), _t4(dk), _t4(dv)
+    dsk = dsv = None
+    if sk is not None:
+      dsk, dsv = torch.empty_like(sk), torch.empty_like(sv)
+      gr.d_side_k, gr.d_side_v = _t4(dsk), _t4(dsv)
+    d_emb = d_bias = None
+    if r_vocab > 0:
+      d_emb = torch.empty((r_vocab, h, d), dtype=torch.float32, device=q.device)
+      d_bias = torch.empty((r_vocab, h), dtype=torch.float32, device=q.device)
+      gr.d_emb, gr.d_bias = d_emb.data_ptr(), d_bias.data_ptr()
+    _lib.check(lib.mlt_local_rel_attn_bwd(C.byref(p), C.byref(gr), _stream()),
+               'mlt_local_rel_attn_bwd')
+    if r_vocab > 0:
+      d_emb, d_bias = d_emb.to(q.dtype), d_bias.to(q.dtype)
+    return dq, dk, dv, dsk, dsv, d_emb, d_bias, None
+
+
+def local_relative_attention(q, k, v, emb=None, bias=None, *, local_radius: int, att_mask=None,
+                             relative_att_ids=None, side_keys=None, side_values=None,
+                             side_att_mask=None, side_relative_att_ids=None,
+                             compact: Optional[LocalCompactSideInputs] = None, impl: str = 'auto'):
+  """``QkvRelativeLocalAttention.call`` core [UPSTREAM-RECALLED].
+
+  ``q/k/v [B,L,H,d]``; window masks / ids ``[B,L,2r+1]`` (column k <-> key ``i+k-r``);
+  optional side keys / values ``[B,G,H,d]`` with ``[B,L,G]`` side masks / ids.  One softmax over
+  the window and the side keys.
+  """
+  if local_radius < 1:
+    raise ValueError('`local_radius` must be positive.')
+  if (side_keys is None) != (side_values is None):
+    raise ValueError('`side_keys` and `side_values` go together.')
+  cfg = _LocalCfg(local_radius, att_mask, relative_att_ids, side_att_mask, side_relative_att_ids,
+                  compact, impl)
+  return _LocalRelAttnFn.apply(q, k, v, side_keys, side_values, emb, bias, cfg)
 
 
 # ---------------------------------------------------------------------------
