@@ -13,6 +13,8 @@
 // backward needs no row reductions) + TMA warp + MMA warp, 512 TMEM columns.
 #include "tc_api.cuh"
 
+#include <cstdlib>
+
 #include "mlt_common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_rowscore.cuh"
@@ -24,8 +26,10 @@ using namespace ptx;
 
 constexpr int TM = 128;
 constexpr int TN = 64;
-constexpr int NTHREADS = 320;
-constexpr int NEW = 256;  // elementwise threads
+// NP = threads per row in the elementwise role (each owns 64 / NP columns of a chunk):
+// 4 * NP elementwise warps + TMA warp + MMA warp.
+template <int NP>
+constexpr int nthreads() { return (4 * NP + 2) * 32; }
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -69,7 +73,7 @@ constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_REL = 320;
 struct Bars {
   uint64_t q_full, rel_full;
   uint64_t kv_full[NST], kv_empty[NST];
-  uint64_t sdp_full[2], ds_full[2], dq_full;
+  uint64_t sdp_full[2], ds_full[2], dq_full, dar_full;
   uint32_t tmem_base;
 };
 }  // namespace bq
@@ -116,17 +120,18 @@ __device__ __forceinline__ rowscore::SegCtx make_seg_ctx(const KeySeg& sg, const
 
 // GM_GEN groups of the query-centric backward: real loop over the 32 columns, TMEM as scratch.
 // Reads S and dP columns, leaves ds (fp32) in the S column, updates the row's bins.
+template <int W>
 __device__ __forceinline__ void bwd_q_group_generic_tmem(uint32_t t_s, uint32_t t_dp, const rowscore::SegCtx& sc,
                                                          const rowscore::RowCtx& rc, const rowscore::GroupLanes& gl,
                                                          int b, int g0, const float* rel_s, float* bin, float scale,
-                                                         float neg, float m2, float linv, float delta) {
+                                                         float neg, float m2, float linv, float delta, int sub) {
 #pragma unroll 1
-  for (int jj = 0; jj < 32; ++jj) {
+  for (int jj = 0; jj < W; ++jj) {
     const uint32_t raw = tmem_ld1(t_s + jj);
     const uint32_t dpr = tmem_ld1(t_dp + jj);
     tmem_wait_ld();
     int slot;
-    const float t = rowscore::score_generic(__uint_as_float(raw), sc, rc, gl, b, g0, jj, rel_s, scale, neg, slot);
+    const float t = rowscore::score_generic(__uint_as_float(raw), sc, rc, gl, b, g0, jj, rel_s, scale, neg, slot, sub);
     const float pv = ex2(fmaf(t, LOG2E, -m2)) * linv;
     const float ds = (t == -INFINITY) ? 0.f : pv * (__uint_as_float(dpr) - delta);
     if (slot >= 0) bin[slot * TM + rc.row] += ds;
@@ -135,12 +140,17 @@ __device__ __forceinline__ void bwd_q_group_generic_tmem(uint32_t t_s, uint32_t 
   tmem_wait_st();
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int NP>
+__global__ void __launch_bounds__(nthreads<NP>(), 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
                 const __grid_constant__ CUtensorMap map_e, const TcBwdQParams p) {
   using namespace bq;
+  constexpr int W = 64 / NP;          // columns per elementwise thread and chunk
+  constexpr int NEW = 128 * NP;       // elementwise threads
+  constexpr int WP = 4 * NP, WM = 4 * NP + 1;   // producer / MMA warp
+  constexpr int RB = NP == 4 ? 32 : 64;         // bin slots per part (host picks NP = 4 only if R <= 32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
@@ -163,9 +173,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&bars->ds_full[s], NEW);
     }
     mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dar_full, 128);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -176,7 +187,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (a.nseg > 1) r1 = seg_range(a.seg[1], i0);
   const int nchunks = r0.n + r1.n;
 
-  if (warp == 8) {
+  if (warp == WP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars->q_full, 2 * TM * 128 + rpad * 128);
       tma_load_4d(smem + SM_Q, &map_q, &bars->q_full, 0, i0, h, b);
@@ -193,7 +204,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WM) {
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_dq = make_idesc_bf16(TM, 64, 0, 1);
@@ -233,26 +244,40 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + T_DQ, tmem + T_DP + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+            umma_ts(tmem + T_DQ, tmem + T_DP + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
                     make_smem_desc_sw128(k_addr + kk * 2048, 16, 1024), idesc_dq, (pc > 0 || kk > 0));
           umma_commit(&bars->kv_empty[st]);
-          if (pc == nchunks - 1) umma_commit(&bars->dq_full);
+          if (pc == nchunks - 1) {
+            if (rpad) {
+              // dQ += dallrel . E : A = dallrel (bf16, TMEM columns of the dead allrel region),
+              // B = E tile taken MN-major (K = relative ids)
+              mbar_wait(&bars->dar_full, 0);
+              tc_fence_after_sync();
+              const uint32_t e_addr = smem_u32(smem + SM_E);
+              for (int kk = 0; kk < rpad / 16; ++kk)
+                umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, make_smem_desc_sw128(e_addr + kk * 2048, 16, 1024),
+                        idesc_dq, 1u);
+            }
+            umma_commit(&bars->dq_full);
+          }
         }
       }
     }
   } else {
-    // ===================== elementwise warps 0-7 =====================
+    // ===================== elementwise warps (NP threads per row) =====================
     using namespace rowscore;
     const int row = (warp & 3) * 32 + lane;
-    const int hh = warp >> 2;  // column half == key group of every chunk
+    const int part = warp >> 2;          // which W-column slice of every chunk
+    const int win = (part * W) / 32;     // 32-key lane window holding the slice
+    const int sub = (part * W) % 32;     // offset of the slice inside the window
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
     const int wrow0 = i0 + (warp & 3) * 32;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const int pd = a.seg[0].side.max_distance;
     const bool perm = (2 * pd + 1 <= R);
-    float* bin = bins + hh * 64 * TM;   // slot-ordered, private to (half, row)
-    for (int x = lane + 32 * (warp & 3); x < 64 * TM; x += 128) bin[x] = 0.f;
+    float* bin = bins + part * RB * TM;   // slot-ordered, private to (part, row)
+    for (int x = lane + 32 * (warp & 3); x < RB * TM; x += 128) bin[x] = 0.f;
     SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
     SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
     RowCtx rc0, rc1;
@@ -261,11 +286,11 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     rc0.row_ok = rc1.row_ok = row_ok;
     init_row_loads(rc0, sc0, b);
     init_row_loads(rc1, sc1, b);
-    auto chunk_key0 = [&](int c) { return (c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN) + hh * 32; };
+    auto chunk_key0 = [&](int c) { return c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN; };
     GroupLanes gl{0, -1};
-    if (nchunks > 0) gl = load_group_lanes(0 < r0.n ? sc0 : sc1, b, chunk_key0(0), lane);
+    if (nchunks > 0) gl = load_group_lanes(0 < r0.n ? sc0 : sc1, b, chunk_key0(0) + 32 * win, lane);
     float bias_l0 = 0.f, bias_l1 = 0.f;
-    if (rpad) {
+    if (rpad && part == 0) {
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
       if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
       if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
@@ -292,9 +317,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + srow);
       m2 = st.x * LOG2E;
       linv = 1.f / st.y;
-      if (hh == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
+      if (part == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
     }
-    if (rpad) {
+    if (rpad && part == 0) {   // warp-uniform: the four part-0 warps extract allrel
       mbar_wait_warp(&bars->rel_full, 0);
       tc_fence_after_sync();
 #pragma unroll 1
@@ -306,7 +331,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int x = 0; x < 16; ++x) {
           const int pid = c0 + x;
           const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
-          if (hh == 0 && pid < R) {
+          if (pid < R) {
             const float val = (__uint_as_float(v[x]) + bv) * a.scale;
             rel_s[slot_of_id(pid, pd, perm) * TM + row] = val;
             if (row_ok) p.allrel_ws[prow * p.rw + pid] = val;
@@ -314,96 +339,103 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-    named_bar_sync(1, NEW);  // rel_s (written by half 0) visible to both halves; bins zeroed
+    named_bar_sync(1, NEW);  // rel_s (written by part 0) visible to all parts; bins zeroed
     init_row(rc0, sc0, b, rel_s);
     init_row(rc1, sc1, b, rel_s);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
     float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
 
-    for (int c = 0; c < nchunks; ++c) {
-      const bool first = c < r0.n;
-      const SegCtx& sc = first ? sc0 : sc1;
-      const RowCtx& rc = first ? rc0 : rc1;
-      const int g0 = chunk_key0(c);
-      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32;
-      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32;
-      GroupLanes nl{0, -1};
-      if (c + 1 < nchunks) nl = load_group_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_key0(c + 1), lane);
-      const GroupPlan gp = classify(sc, rc, gl, wrow0, g0, lane, a.neg);
-      mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
-      tc_fence_after_sync();
-      uint32_t ds_pk[16];
-      if (gp.mode == GM_DEAD) {
+    int c = 0;   // chunk counter over both segments
+#pragma unroll 1
+    for (int sgi = 0; sgi < a.nseg; ++sgi) {
+      // segment context copied once: no per-field selects inside the chunk loop
+      const SegCtx sc = sgi ? sc1 : sc0;
+      const RowCtx rc = sgi ? rc1 : rc0;
+      const int seg_n = sgi ? r1.n : r0.n;
+      const int seg_kb = sgi ? r1.kb : r0.kb;
+#pragma unroll 1
+      for (int cc = 0; cc < seg_n; ++cc, ++c) {
+        const int g0 = seg_kb + cc * TN + part * W;
+        const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
+        const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
+        GroupLanes nl{0, -1};
+        if (c + 1 < nchunks) nl = load_group_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_key0(c + 1) + 32 * win, lane);
+        const GroupPlan gp = classify<W>(sc, rc, gl, wrow0, g0, lane, a.neg, sub);
+        mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t ds_pk[W / 2];
+        if (gp.mode == GM_DEAD) {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) ds_pk[x] = 0u;
-      } else {
-        float ds[32];
-        if (gp.mode == GM_GEN) {
-          bwd_q_group_generic_tmem(t_s, t_dp, sc, rc, gl, b, g0, rel_s, bin, a.scale, a.neg, m2, linv, delta);
-          uint32_t v[32];
-          tmem_ld32(t_s, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int x = 0; x < 32; ++x) ds[x] = __uint_as_float(v[x]);
+          for (int x = 0; x < W / 2; ++x) ds_pk[x] = 0u;
         } else {
-          float t[32];
-          uint32_t v[32];
-          tmem_ld32(t_s, v);
-          tmem_wait_ld();
+          float ds[W];
+          if (gp.mode == GM_GEN) {
+            bwd_q_group_generic_tmem<W>(t_s, t_dp, sc, rc, gl, b, g0, rel_s, bin, a.scale, a.neg, m2, linv, delta, sub);
+            uint32_t v[W];
+            tmem_ldN(t_s, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
-          score_group<0>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
-          tmem_ld32(t_dp, v);
-          tmem_wait_ld();
-          float tot = 0.f;
+            for (int x = 0; x < W; ++x) ds[x] = __uint_as_float(v[x]);
+          } else {
+            float t[W];
+            uint32_t v[W];
+            tmem_ldN(t_s, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const float pv = ex2(fmaf(t[x], LOG2E, -m2)) * linv;   // dead: t = -inf -> 0
-            ds[x] = pv * (__uint_as_float(v[x]) - delta);
-            tot += ds[x];
-          }
-          // ---- relative-id bins ----
-          if (gp.mode == GM_FAST || gp.mode == GM_EDGE) {
-            if (gp.ccls == 1) accP += tot;
-            else if (gp.ccls == 2) accN += tot;
-            else if (gp.ccls == 3) accX += tot;
-          } else if (gp.mode == GM_DIAG) {
-            const int d0 = g0 - i + sc.D;
-            float* base = bin + row;
+            for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
+            score_group<0, W, W>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg, sub);
+            tmem_ldN(t_dp, v);
+            tmem_wait_ld();
+            float tot = 0.f;
 #pragma unroll
-            for (int x = 0; x < 32; ++x) {
-              const int sl = min(max(d0 + x, 0), 2 * sc.D);
-              base[sl * TM] += ds[x];
+            for (int x = 0; x < W; ++x) {
+              const float pv = ex2(fmaf(t[x], LOG2E, -m2)) * linv;   // dead: t = -inf -> 0
+              ds[x] = pv * (__uint_as_float(v[x]) - delta);
+              tot += ds[x];
             }
-          } else if (gp.mode == GM_QS) {
-            const int d0 = rc.q_sent - g0;
-            float sp = 0.f;
+            // ---- relative-id bins ----
+            if (gp.mode == GM_FAST || gp.mode == GM_EDGE) {
+              if (gp.ccls == 1) accP += tot;
+              else if (gp.ccls == 2) accN += tot;
+              else if (gp.ccls == 3) accX += tot;
+            } else if (gp.mode == GM_DIAG) {
+              const int d0 = g0 - i + sc.D;
+              float* base = bin + row;
 #pragma unroll
-            for (int x = 0; x < 32; ++x) sp += (d0 == x) ? ds[x] : 0.f;
-            accX1 += sp;
-            accX += tot - sp;
-          } else {  // GM_KS
-            float sp = 0.f;
+              for (int x = 0; x < W; ++x) {
+                const int sl = min(max(d0 + x, 0), 2 * sc.D);
+                base[sl * TM] += ds[x];
+              }
+            } else if (gp.mode == GM_QS) {
+              const int d0 = rc.q_sent - g0;
+              float sp = 0.f;
 #pragma unroll
-            for (int x = 0; x < 32; ++x) {
-              const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, x);
-              sp += (ks_j == i) ? ds[x] : 0.f;
+              for (int x = 0; x < W; ++x) sp += (d0 == x) ? ds[x] : 0.f;
+              accX1 += sp;
+              accX += tot - sp;
+            } else {  // GM_KS
+              float sp = 0.f;
+#pragma unroll
+              for (int x = 0; x < W; ++x) {
+                const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, sub + x);
+                sp += (ks_j == i) ? ds[x] : 0.f;
+              }
+              accX1 += sp;
+              accX += tot - sp;
             }
-            accX1 += sp;
-            accX += tot - sp;
           }
+#pragma unroll
+          for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
         }
-#pragma unroll
-        for (int x = 0; x < 16; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
+        // each part packs into its OWN column range (other parts may still be reading their inputs)
+        tmem_stN(t_dp, ds_pk);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->ds_full[c & 1]);
+        gl = nl;
       }
-      // each half packs into its OWN column range (the other half may still be reading its inputs)
-      tmem_st16(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, ds_pk);
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->ds_full[c & 1]);
-      gl = nl;
     }
-    // flush the constant-class accumulators into this half's bins
+    // flush the constant-class accumulators into this part's bins
     if (R > 0) {
       auto flush = [&](int id, float v) {
         if (id >= 0 && id < R) bin[slot_of_id(id, pd, perm) * TM + row] += v;
@@ -414,43 +446,47 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       flush(2 * dd + 1, accX);
       flush(2 * dd + 2, accX1);
     }
-    // ---- epilogue: dq = scale * (dS.K + dallrel.E); publish dallrel ----
-    named_bar_sync(1, NEW);  // both halves' bins complete
+    // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
+    named_bar_sync(1, NEW);  // all parts' bins complete
+    if (rpad && part == 0) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < rpad; c0 += 16) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          float w2[2];
+#pragma unroll
+          for (int y = 0; y < 2; ++y) {
+            const int pid = c0 + 2 * x + y;
+            float w = 0.f;
+            if (pid < R) {
+              const int sl = slot_of_id(pid, pd, perm);
+#pragma unroll
+              for (int pp = 0; pp < NP; ++pp) w += bins[(pp * RB + sl) * TM + row];
+              if (row_ok) a.dallrel[srow * R + pid] = w;
+            }
+            w2[y] = w;
+          }
+          pk[x] = pack_bf16x2(w2[0], w2[1]);
+        }
+        tmem_st8(tmem + T_REL + lane_sel + c0 / 2, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->dar_full);
+    }
     mbar_wait_warp(&bars->dq_full, 0);
     tc_fence_after_sync();
-    uint32_t dq_raw[32];
-    tmem_ld32(tmem + T_DQ + lane_sel + hh * 32, dq_raw);
+    uint32_t dq_raw[W];
+    tmem_ldN(tmem + T_DQ + lane_sel + part * W, dq_raw);
     tmem_wait_ld();
-    float dq[32];
+    float dq[W];
 #pragma unroll
-    for (int x = 0; x < 32; ++x) dq[x] = __uint_as_float(dq_raw[x]);
-    if (R > 0) {
-      const float* bin0 = bins;
-      const float* bin1 = bins + 64 * TM;
-#pragma unroll 1
-      for (int pid = 0; pid < R; ++pid) {
-        const int sl = slot_of_id(pid, pd, perm);
-        const float w = bin0[sl * TM + row] + bin1[sl * TM + row];
-        if (hh == 0 && row_ok) a.dallrel[srow * R + pid] = w;
-        // E row pid, columns [32 hh, 32 hh + 32): 4 swizzled 16-byte chunks (warp-broadcast reads)
-        const uint8_t* erow = smem + SM_E + pid * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint4 e4 = *reinterpret_cast<const uint4*>(erow + (((hh * 4 + ch) ^ (pid & 7)) << 4));
-          const uint32_t ew[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-          for (int y = 0; y < 4; ++y) {
-            const float2 ef = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ew[y]));
-            dq[ch * 8 + 2 * y] = fmaf(w, ef.x, dq[ch * 8 + 2 * y]);
-            dq[ch * 8 + 2 * y + 1] = fmaf(w, ef.y, dq[ch * 8 + 2 * y + 1]);
-          }
-        }
-      }
-    }
+    for (int x = 0; x < W; ++x) dq[x] = __uint_as_float(dq_raw[x]);
     if (row_ok) {
-      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + hh * 32;
+      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + part * W;
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
+      for (int x = 0; x < W / 8; ++x) {
         uint4 w;
         w.x = pack_bf16x2(dq[8 * x + 0] * a.scale, dq[8 * x + 1] * a.scale);
         w.y = pack_bf16x2(dq[8 * x + 2] * a.scale, dq[8 * x + 3] * a.scale);
@@ -462,7 +498,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == WM) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
 // ============================================================================================
@@ -571,25 +607,26 @@ __device__ __forceinline__ void init_key(KeyCtx& kc, const SrcCtx& sc, int b) {
 }
 
 // a = first key row of the warp, g0 = first query of the group.  off = key - query.
+template <int W>
 __device__ __forceinline__ Plan classify(const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql, int a, int g0,
-                                         int lane, float neg) {
+                                         int lane, float neg, int sub) {
   Plan pl;
   pl.cid = -1;
   pl.mrow = 0.f;
   pl.mask_pe = false;
-  const int o_min = a - (g0 + 31), o_max = a + 31 - g0;
+  const int o_min = a - (g0 + W - 1), o_max = a + 31 - g0;
   const bool dead = g0 >= sc.ie || (sc.band && (o_min > sc.radius || o_max < -sc.radius));
   if (dead) {
     pl.mode = GM_DEAD;
     return pl;
   }
-  const bool all_live = (g0 + 31 < sc.ie) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
+  const bool all_live = (g0 + W - 1 < sc.ie) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
   bool gen = false;
   if (sc.mask_rule == MR_EXPLICIT) {
     gen = true;
   } else if (sc.mask_rule == MR_EXAMPLE_ID) {
-    const int qe0 = __shfl_sync(0xffffffffu, ql.qe_l, 0);
-    const bool lane_oob = (g0 + lane >= sc.ie);
+    const int qe0 = __shfl_sync(0xffffffffu, ql.qe_l, sub);
+    const bool lane_oob = (g0 - sub + lane >= sc.ie) || (W < 32 && (lane < sub || lane >= sub + W));
     const bool uni = __all_sync(0xffffffffu, lane_oob || ql.qe_l == qe0);
     pl.mask_pe = !uni;
     pl.mrow = uni ? ((kc.k_e == qe0) ? 0.f : neg) : 0.f;
@@ -607,12 +644,12 @@ __device__ __forceinline__ Plan classify(const SrcCtx& sc, const KeyCtx& kc, con
     case IDR_CROSS_QSENT:
       if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
       pl.cid = 2 * sc.D + 1;
-      if (__any_sync(0xffffffffu, ql.qs_l >= a && ql.qs_l <= a + 31)) rcls = 2;
+      if (__any_sync(0xffffffffu, ql.qs_l >= a && ql.qs_l <= a + 31 && (W == 32 || (lane >= sub && lane < sub + W)))) rcls = 2;
       break;
     case IDR_CROSS_KSENT:
       if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
       pl.cid = 2 * sc.D + 1;
-      if (__any_sync(0xffffffffu, kc.k_sent >= g0 && kc.k_sent < g0 + 32)) rcls = 3;
+      if (__any_sync(0xffffffffu, kc.k_sent >= g0 && kc.k_sent < g0 + W)) rcls = 3;
       break;
     default:
       rcls = 4;
@@ -633,12 +670,13 @@ __device__ __forceinline__ Plan classify(const SrcCtx& sc, const KeyCtx& kc, con
 
 // Generic per-element evaluation; returns the score or -inf when (i, j) is dead.
 __device__ __forceinline__ float score_generic(float x, const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql,
-                                               int b, int g0, int ii, const float* relq, float scale, float neg) {
+                                               int b, int g0, int ii, const float* relq, float scale, float neg,
+                                               int sub) {
   const Side& sd = sc.src->q.side;
   const int i = g0 + ii;
   const int off = kc.j - i;
-  const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, ii);
-  const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, ii);
+  const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, sub + ii);
+  const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, sub + ii);
   const bool live = kc.key_ok && i < sc.ie && (!sc.band || (off <= sc.radius && off >= -sc.radius));
   if (!live) return -INFINITY;
   const int col = sc.band ? off + sc.radius : kc.j;
@@ -664,22 +702,24 @@ __device__ __forceinline__ float score_generic(float x, const SrcCtx& sc, const 
 }
 
 // Scores of one 32-query group in place.  `mode` is warp-uniform; GM_GEN is handled elsewhere.
-__device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, const SrcCtx& sc, const KeyCtx& kc,
-                                            const QLanes& ql, int g0, const float* relq, float scale, float neg) {
+template <int W>
+__device__ __forceinline__ void score_group(float (&t)[W], const Plan& pl, const SrcCtx& sc, const KeyCtx& kc,
+                                            const QLanes& ql, int g0, const float* relq, float scale, float neg,
+                                            int sub) {
   const int rw = sc.rw;
   switch (pl.mode) {
     case GM_FAST:
       if (pl.cid >= 0) {
 #pragma unroll
-        for (int ii = 0; ii < 32; ++ii) t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid] + pl.mrow);
+        for (int ii = 0; ii < W; ++ii) t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid] + pl.mrow);
       } else {
 #pragma unroll
-        for (int ii = 0; ii < 32; ++ii) t[ii] = fmaf(t[ii], scale, pl.mrow);
+        for (int ii = 0; ii < W; ++ii) t[ii] = fmaf(t[ii], scale, pl.mrow);
       }
       break;
     case GM_EDGE: {
       const int d0 = kc.j - g0;  // off = d0 - ii
-      int ilo = 0, ihi = min(32, sc.ie - g0);
+      int ilo = 0, ihi = min(W, sc.ie - g0);
       if (sc.band) {
         ilo = max(ilo, d0 - sc.radius);
         ihi = min(ihi, d0 + sc.radius + 1);
@@ -689,7 +729,7 @@ __device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, cons
       const int cid = pl.cid >= 0 ? pl.cid : 0;
       const float use = pl.cid >= 0 ? 1.f : 0.f;
 #pragma unroll
-      for (int ii = 0; ii < 32; ++ii) {
+      for (int ii = 0; ii < W; ++ii) {
         const float v = fmaf(t[ii], scale, fmaf(use, relq[ii * rw + cid], pl.mrow));
         t[ii] = ((unsigned)(ii - ilo) < span) ? v : -INFINITY;
       }
@@ -698,7 +738,7 @@ __device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, cons
     case GM_DIAG: {
       const int d0 = kc.j - g0;
 #pragma unroll
-      for (int ii = 0; ii < 32; ++ii) {
+      for (int ii = 0; ii < W; ++ii) {
         const int o = min(max(d0 - ii, -sc.D), sc.D);
         const int id = o >= 0 ? o : sc.D - o;
         t[ii] = fmaf(t[ii], scale, relq[ii * rw + id] + pl.mrow);
@@ -707,8 +747,8 @@ __device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, cons
     }
     case GM_QS: {
 #pragma unroll
-      for (int ii = 0; ii < 32; ++ii) {
-        const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, ii);
+      for (int ii = 0; ii < W; ++ii) {
+        const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, sub + ii);
         t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (qs_i == kc.j ? 1 : 0)] + pl.mrow);
       }
       break;
@@ -716,7 +756,7 @@ __device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, cons
     case GM_KS: {
       const int sp = kc.k_sent - g0;
 #pragma unroll
-      for (int ii = 0; ii < 32; ++ii)
+      for (int ii = 0; ii < W; ++ii)
         t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (sp == ii ? 1 : 0)] + pl.mrow);
       break;
     }
@@ -725,23 +765,24 @@ __device__ __forceinline__ void score_group(float (&t)[32], const Plan& pl, cons
   }
   if (pl.mask_pe) {
 #pragma unroll
-    for (int ii = 0; ii < 32; ++ii) {
-      const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, ii);
+    for (int ii = 0; ii < W; ++ii) {
+      const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, sub + ii);
       t[ii] += (qe_i == kc.k_e) ? 0.f : neg;
     }
   }
 }
 
 // GM_GEN: real loop, TMEM as scratch.  Leaves p (fp32) in the S^T column and ds in the dP^T column.
+template <int W>
 __device__ __forceinline__ void group_generic_tmem(uint32_t t_s, uint32_t t_dp, const SrcCtx& sc, const KeyCtx& kc,
                                                    const QLanes& ql, int b, int g0, const float4* rs,
-                                                   const float* relq, float scale, float neg) {
+                                                   const float* relq, float scale, float neg, int sub) {
 #pragma unroll 1
-  for (int ii = 0; ii < 32; ++ii) {
+  for (int ii = 0; ii < W; ++ii) {
     const uint32_t raw = tmem_ld1(t_s + ii);
     const uint32_t dpr = tmem_ld1(t_dp + ii);
     tmem_wait_ld();
-    const float t = score_generic(__uint_as_float(raw), sc, kc, ql, b, g0, ii, relq, scale, neg);
+    const float t = score_generic(__uint_as_float(raw), sc, kc, ql, b, g0, ii, relq, scale, neg, sub);
     float pv = 0.f, ds = 0.f;
     if (t != -INFINITY) {
       const float4 st = rs[ii];
@@ -755,12 +796,16 @@ __device__ __forceinline__ void group_generic_tmem(uint32_t t_s, uint32_t t_dp, 
 }
 }  // namespace colscore
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int NP>
+__global__ void __launch_bounds__(nthreads<NP>(), 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
                  const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_do1,
                  const TcBwdKVParams p) {
   using namespace bk;
+  constexpr int W = 64 / NP;
+  constexpr int NEW = 128 * NP;
+  constexpr int WP = 4 * NP, WM = 4 * NP + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
@@ -780,7 +825,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -791,7 +836,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   if (p.nsrc > 1) r1 = src_range(p.src[1], j0);
   const int nchunks = r0.n + r1.n;
 
-  if (warp == 8) {
+  if (warp == WP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars->kv_full, 2 * TM * 128);
       tma_load_4d(smem + SM_K, &map_k, &bars->kv_full, 0, j0, h, b);
@@ -814,7 +859,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           bulk_g2s(smem + SM_RELQ + st * TN * 64 * 4, src.allrel_ws + prow * rw, rel_bytes, &bars->qd_full[st]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WM) {
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(TM, 64, 0, 1);
@@ -846,11 +891,11 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           const uint32_t do_addr = q_addr + TN * 128;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dV += P^T . dO_c
-            umma_ts(tmem + T_DV, tmem + T_S + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+            umma_ts(tmem + T_DV, tmem + T_S + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
                     make_smem_desc_sw128(do_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dK += dS^T . Q_c
-            umma_ts(tmem + T_DK, tmem + T_DP + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+            umma_ts(tmem + T_DK, tmem + T_DP + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
                     make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
           umma_commit(&bars->qd_empty[st]);
           if (pc == nchunks - 1) umma_commit(&bars->acc_full);
@@ -860,7 +905,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   } else {
     using namespace colscore;
     const int row = (warp & 3) * 32 + lane;
-    const int hh = warp >> 2;
+    const int part = warp >> 2;
+    const int win = (part * W) / 32, sub = (part * W) % 32;
     const int j = j0 + row;
     const bool key_ok = j < p.len;
     const int wrow0 = j0 + (warp & 3) * 32;
@@ -887,53 +933,53 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     kc0.key_ok = kc1.key_ok = key_ok;
     init_key(kc0, sc0, b);
     init_key(kc1, sc1, b);
-    auto chunk_q0 = [&](int c) { return (c < r0.n ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN) + hh * 32; };
+    auto chunk_q0 = [&](int c) { return c < r0.n ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN; };
     QLanes ql{0, -1};
-    if (nchunks > 0) ql = load_q_lanes(0 < r0.n ? sc0 : sc1, b, chunk_q0(0), lane);
+    if (nchunks > 0) ql = load_q_lanes(0 < r0.n ? sc0 : sc1, b, chunk_q0(0) + 32 * win, lane);
     for (int c = 0; c < nchunks; ++c) {
       const int st = c % NST;
       const bool first = c < r0.n;
       const SrcCtx& sc = first ? sc0 : sc1;
       const KeyCtx& kc = first ? kc0 : kc1;
-      const int g0 = chunk_q0(c);
-      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32;
-      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32;
+      const int g0 = chunk_q0(c) + part * W;
+      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
+      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
       QLanes nl{0, -1};
-      if (c + 1 < nchunks) nl = load_q_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_q0(c + 1), lane);
-      const Plan pl = classify(sc, kc, ql, wrow0, g0, lane, p.neg);
+      if (c + 1 < nchunks) nl = load_q_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_q0(c + 1) + 32 * win, lane);
+      const Plan pl = classify<W>(sc, kc, ql, wrow0, g0, lane, p.neg, sub);
       mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
       mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
       tc_fence_after_sync();
-      const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + hh * 32;
-      const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + hh * 32 * sc.rw;
-      uint32_t p_pk[16], ds_pk[16];
+      const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + part * W;
+      const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + part * W * sc.rw;
+      uint32_t p_pk[W / 2], ds_pk[W / 2];
       if (pl.mode == GM_DEAD) {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
+        for (int x = 0; x < W / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
       } else if (pl.mode == GM_GEN) {
-        group_generic_tmem(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg);
-        uint32_t v[32];
-        tmem_ld32(t_s, v);
+        group_generic_tmem<W>(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg, sub);
+        uint32_t v[W];
+        tmem_ldN(t_s, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < 16; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-        tmem_ld32(t_dp, v);
+        for (int x = 0; x < W / 2; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+        tmem_ldN(t_dp, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < 16; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+        for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
       } else {
-        float t[32];
-        uint32_t v[32];
-        tmem_ld32(t_s, v);
+        float t[W];
+        uint32_t v[W];
+        tmem_ldN(t_s, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
-        score_group(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg);
-        tmem_ld32(t_dp, v);
+        for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
+        score_group<W>(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg, sub);
+        tmem_ldN(t_dp, v);
         tmem_wait_ld();
         const bool guard = (pl.mode == GM_EDGE);   // dead columns may carry garbage row records
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
+        for (int x = 0; x < W / 2; ++x) {
           float pv[2], dsv[2];
 #pragma unroll
           for (int y = 0; y < 2; ++y) {
@@ -949,8 +995,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
         }
       }
-      tmem_st16(tmem + T_S + (c & 1) * 64 + lane_sel + hh * 32, p_pk);
-      tmem_st16(tmem + T_DP + (c & 1) * 64 + lane_sel + hh * 32, ds_pk);
+      tmem_stN(t_s, p_pk);
+      tmem_stN(t_dp, ds_pk);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->pds_full[c & 1]);
@@ -958,15 +1004,15 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     }
     mbar_wait_warp(&bars->acc_full, 0);
     tc_fence_after_sync();
-    uint32_t dv_raw[32], dk_raw[32];
-    tmem_ld32(tmem + T_DV + lane_sel + hh * 32, dv_raw);
-    tmem_ld32(tmem + T_DK + lane_sel + hh * 32, dk_raw);
+    uint32_t dv_raw[W], dk_raw[W];
+    tmem_ldN(tmem + T_DV + lane_sel + part * W, dv_raw);
+    tmem_ldN(tmem + T_DK + lane_sel + part * W, dk_raw);
     tmem_wait_ld();
     if (key_ok) {
-      __nv_bfloat16* dv = row_ptr_mut<__nv_bfloat16>(p.d_v, b, j, h) + hh * 32;
-      __nv_bfloat16* dk = row_ptr_mut<__nv_bfloat16>(p.d_k, b, j, h) + hh * 32;
+      __nv_bfloat16* dv = row_ptr_mut<__nv_bfloat16>(p.d_v, b, j, h) + part * W;
+      __nv_bfloat16* dk = row_ptr_mut<__nv_bfloat16>(p.d_k, b, j, h) + part * W;
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
+      for (int x = 0; x < W / 8; ++x) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 0]), __uint_as_float(dv_raw[8 * x + 1]));
         w.y = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 2]), __uint_as_float(dv_raw[8 * x + 3]));
@@ -984,7 +1030,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == WM) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -1016,7 +1062,9 @@ static bool g_attr_q = false, g_attr_kv = false;
 
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1046,13 +1094,17 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
-  tc_bwd_q_kernel<<<grid, NTHREADS, bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  static const int force_np = getenv("MLT_BWD_NP") ? atoi(getenv("MLT_BWD_NP")) : 0;
+  if (R <= 32 && force_np == 4)   // optional: four threads per row (measured slower than two)
+    tc_bwd_q_kernel<4><<<grid, nthreads<4>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else
+    tc_bwd_q_kernel<2><<<grid, nthreads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   if (!g_attr_kv) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_kv = true;
   }
@@ -1081,7 +1133,7 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.len + TM - 1) / TM, a.H, a.B);
-  tc_bwd_kv_kernel<<<grid, NTHREADS, bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  tc_bwd_kv_kernel<4><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();
 }
 

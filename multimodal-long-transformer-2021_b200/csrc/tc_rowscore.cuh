@@ -100,27 +100,30 @@ struct GroupPlan {
 
 // a = first row of the warp.  All decisions are warp-uniform (computed from uniform values or
 // votes); cadd / mrow are per-thread.
+// W = group width (32, or 16 when four threads share a row); the lane-held scalars always cover
+// the 32-key window starting at g0 - sub.
+template <int W = 32>
 __device__ __forceinline__ GroupPlan classify(const SegCtx& sc, const RowCtx& rc, const GroupLanes& gl,
-                                              int a, int g0, int lane, float neg) {
+                                              int a, int g0, int lane, float neg, int sub = 0) {
   GroupPlan gp;
   gp.cadd = 0.f;
   gp.ccls = 0;
   gp.mrow = 0.f;
   gp.mask_pe = false;
-  const int o_min = g0 - (a + 31), o_max = g0 + 31 - a;
+  const int o_min = g0 - (a + 31), o_max = g0 + (W - 1) - a;
   const bool dead = g0 >= sc.ke || (sc.band && (o_min > sc.radius || o_max < -sc.radius));
   if (dead) {
     gp.mode = GM_DEAD;
     return gp;
   }
-  const bool all_live = (g0 + 31 < sc.ke) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
+  const bool all_live = (g0 + (W - 1) < sc.ke) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
   // ---- mask ----
   bool mask_uniform = true;
   if (sc.mask_rule == MR_EXPLICIT) {
     mask_uniform = false;
   } else if (sc.mask_rule == MR_EXAMPLE_ID) {
-    const int ke0 = __shfl_sync(0xffffffffu, gl.ke_l, 0);
-    const bool lane_oob = (g0 + lane >= sc.ke);
+    const int ke0 = __shfl_sync(0xffffffffu, gl.ke_l, sub);
+    const bool lane_oob = (g0 - sub + lane >= sc.ke) || (W < 32 && (lane < sub || lane >= sub + W));
     const bool uni = __all_sync(0xffffffffu, lane_oob || gl.ke_l == ke0);
     gp.mask_pe = !uni;
     gp.mrow = uni ? ((rc.q_e == ke0) ? 0.f : neg) : 0.f;
@@ -144,15 +147,16 @@ __device__ __forceinline__ GroupPlan classify(const SegCtx& sc, const RowCtx& rc
       }
       break;
     case IDR_CROSS_QSENT: {
-      const bool hit = __any_sync(0xffffffffu, rc.q_sent >= g0 && rc.q_sent < g0 + 32);
+      const bool hit = __any_sync(0xffffffffu, rc.q_sent >= g0 && rc.q_sent < g0 + W);
       rcls = hit ? 2 : 0;
       relc = rc.relX;
       gp.ccls = 3;
       break;
     }
     case IDR_CROSS_KSENT: {
-      const int smin = __reduce_min_sync(0xffffffffu, gl.ks_l < 0 ? 0x7fffffff : gl.ks_l);
-      const int smax = __reduce_max_sync(0xffffffffu, gl.ks_l);
+      const bool in_grp = (W == 32) || (lane >= sub && lane < sub + W);
+      const int smin = __reduce_min_sync(0xffffffffu, (gl.ks_l < 0 || !in_grp) ? 0x7fffffff : gl.ks_l);
+      const int smax = __reduce_max_sync(0xffffffffu, in_grp ? gl.ks_l : -1);
       const bool hit = !(smax < a || smin > a + 31);
       rcls = hit ? 3 : 0;
       relc = rc.relX;
@@ -179,14 +183,15 @@ __device__ __forceinline__ GroupPlan classify(const SegCtx& sc, const RowCtx& rc
 // Generic per-element evaluation (any rule).  Returns the slot (or -1) through `slot`.
 __device__ __forceinline__ float score_generic(float x, const SegCtx& sc, const RowCtx& rc,
                                                const GroupLanes& gl, int b, int g0, int jj,
-                                               const float* rel_s, float scale, float neg, int& slot) {
+                                               const float* rel_s, float scale, float neg, int& slot,
+                                               int sub = 0) {
   const Side& sd = sc.sg->side;
   const int j = g0 + jj;
   const int off = j - rc.i;
   slot = -1;
   // shuffles first: every lane of the warp must take part, live or not
-  const int ke_j = __shfl_sync(0xffffffffu, gl.ke_l, jj);
-  const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, jj);
+  const int ke_j = __shfl_sync(0xffffffffu, gl.ke_l, sub + jj);
+  const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, sub + jj);
   const bool live = j < sc.ke && (!sc.band || (off <= sc.radius && off >= -sc.radius));
   if (!live) return -INFINITY;
   const int col = sc.band ? off + sc.radius : j;
@@ -217,30 +222,30 @@ __device__ __forceinline__ float score_generic(float x, const SegCtx& sc, const 
 
 // Scores of one 32-key group, in place (t[OFF .. OFF+32)).  `mode` is warp-uniform.
 // The shuffles inside GM_GEN / GM_KS require all 32 lanes to execute this function together.
-template <int OFF, int N>
+template <int OFF, int N, int W = 32>
 __device__ __forceinline__ void score_group(float (&t)[N], const GroupPlan& gp, const SegCtx& sc,
                                             const RowCtx& rc, const GroupLanes& gl, int b, int g0,
-                                            const float* rel_s, float scale, float neg) {
+                                            const float* rel_s, float scale, float neg, int sub = 0) {
   switch (gp.mode) {
     case GM_DEAD:
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) t[OFF + jj] = -INFINITY;
+      for (int jj = 0; jj < W; ++jj) t[OFF + jj] = -INFINITY;
       break;
     case GM_FAST:
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) t[OFF + jj] = fmaf(t[OFF + jj], scale, gp.cadd);
+      for (int jj = 0; jj < W; ++jj) t[OFF + jj] = fmaf(t[OFF + jj], scale, gp.cadd);
       break;
     case GM_EDGE: {
       // live columns of this row form one interval [jlo, jhi): branch-free per-element test
       const int d0 = g0 - rc.i;
-      int jlo = 0, jhi = min(32, sc.ke - g0);
+      int jlo = 0, jhi = min(W, sc.ke - g0);
       if (sc.band) {
         jlo = max(jlo, -sc.radius - d0);
         jhi = min(jhi, sc.radius - d0 + 1);
       }
       const unsigned span = (unsigned)max(jhi - jlo, 0);
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
+      for (int jj = 0; jj < W; ++jj) {
         const float v = fmaf(t[OFF + jj], scale, gp.cadd);
         t[OFF + jj] = ((unsigned)(jj - jlo) < span) ? v : -INFINITY;
       }
@@ -250,7 +255,7 @@ __device__ __forceinline__ void score_group(float (&t)[N], const GroupPlan& gp, 
       const int d0 = g0 - rc.i + sc.D;  // slot = clamp(off, -D, D) + D = clamp(d0 + jj, 0, 2D)
       const float* base = rel_s + rc.row;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
+      for (int jj = 0; jj < W; ++jj) {
         const int s = min(max(d0 + jj, 0), 2 * sc.D);
         t[OFF + jj] = fmaf(t[OFF + jj], scale, base[s * TMR] + gp.mrow);
       }
@@ -260,14 +265,14 @@ __device__ __forceinline__ void score_group(float (&t)[N], const GroupPlan& gp, 
       const int d0 = rc.q_sent - g0;  // special column index within the group
       const float c0 = rc.relX + gp.mrow, c1 = rc.relX1 + gp.mrow;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) t[OFF + jj] = fmaf(t[OFF + jj], scale, d0 == jj ? c1 : c0);
+      for (int jj = 0; jj < W; ++jj) t[OFF + jj] = fmaf(t[OFF + jj], scale, d0 == jj ? c1 : c0);
       break;
     }
     case GM_KS: {
       const float c0 = rc.relX + gp.mrow, c1 = rc.relX1 + gp.mrow;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, jj);
+      for (int jj = 0; jj < W; ++jj) {
+        const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, sub + jj);
         t[OFF + jj] = fmaf(t[OFF + jj], scale, ks_j == rc.i ? c1 : c0);
       }
       break;
@@ -277,8 +282,8 @@ __device__ __forceinline__ void score_group(float (&t)[N], const GroupPlan& gp, 
   }
   if (gp.mask_pe && gp.mode != GM_DEAD) {
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const int ke_j = __shfl_sync(0xffffffffu, gl.ke_l, jj);
+    for (int jj = 0; jj < W; ++jj) {
+      const int ke_j = __shfl_sync(0xffffffffu, gl.ke_l, sub + jj);
       t[OFF + jj] += (ke_j == rc.q_e) ? 0.f : neg;
     }
   }
