@@ -578,9 +578,12 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                        bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
                        qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   }
+  // Main stream: the long-key kernel (longest).  Side stream: global-key kernel, then the small
+  // table-gradient kernels, which only need the bins of the query-centric pass and are light
+  // enough (24 KB smem, 128 threads) to co-reside with the key-centric CTAs.
   ForkScope fk2(st);
-  MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
-                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), fk2.side()));
+  cudaStream_t s2 = fk2.side();
+  if (profile_enabled()) s2 = st;
   MLT_TRY(launch_bwd_kv(kl, tc, ws_lg, p->dtype, p->d, "bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
                         qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   if (p->R > 0) {
@@ -588,17 +591,19 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                      g->d_long_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};
     {
       ProfileScope ps("simt_table_grad_long", bh * 2 * dd * RR * p->L,
-                      qkv_bytes(bh, p->L, p->d, p->dtype, 1), st, 2);
-      MLT_CUDA(simt_launch_table_grad(tl, p->dtype, st));
+                      qkv_bytes(bh, p->L, p->d, p->dtype, 1), s2, 2);
+      MLT_CUDA(simt_launch_table_grad(tl, p->dtype, s2));
     }
     TableGradArgs tg{to_t4(p->global_q), p->G, wg.dallrel, wg.partial, wg.partial_bias, g->d_global_emb,
                      g->d_global_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->G), p->scale};
     {
       ProfileScope ps("simt_table_grad_global", bh * 2 * dd * RR * p->G,
-                      qkv_bytes(bh, p->G, p->d, p->dtype, 1), st, 2);
-      MLT_CUDA(simt_launch_table_grad(tg, p->dtype, st));
+                      qkv_bytes(bh, p->G, p->d, p->dtype, 1), s2, 2);
+      MLT_CUDA(simt_launch_table_grad(tg, p->dtype, s2));
     }
   }
+  MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
+                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), s2));
   return MLT_OK;
 }
 

@@ -30,6 +30,21 @@ constexpr int TN = 64;
 // 4 * NP elementwise warps + TMA warp + MMA warp.
 template <int NP>
 constexpr int nthreads() { return (4 * NP + 2) * 32; }
+
+#ifdef MLT_TC_TRACE
+__device__ unsigned long long g_trace_b[3][256];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(role, idx)                                                                  \
+  do {                                                                                    \
+    if (blockIdx.x == 5 && blockIdx.y == 1 && blockIdx.z == 0 && (idx) < 256) g_trace_b[role][idx] = gtime(); \
+  } while (0)
+#else
+#define TRACE(role, idx) do {} while (0)
+#endif
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -796,16 +811,19 @@ __device__ __forceinline__ void group_generic_tmem(uint32_t t_s, uint32_t t_dp, 
 }
 }  // namespace colscore
 
-template <int NP>
-__global__ void __launch_bounds__(nthreads<NP>(), 1)
+// NP threads per row inside a warp set; SETS warp sets take alternate chunks (S^T / dP^T are
+// double-buffered by chunk parity, so set s simply owns buffer s).
+template <int NP, int SETS>
+__global__ void __launch_bounds__(nthreads<NP * SETS>(), 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
                  const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_do1,
                  const TcBwdKVParams p) {
   using namespace bk;
   constexpr int W = 64 / NP;
-  constexpr int NEW = 128 * NP;
-  constexpr int WP = 4 * NP, WM = 4 * NP + 1;
+  constexpr int NEW = 128 * NP;                  // elementwise threads per set
+  constexpr int WP = 4 * NP * SETS, WM = 4 * NP * SETS + 1;
+  static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
@@ -870,6 +888,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         if (c < nchunks) {
           const int st = c % NST;
           mbar_wait(&bars->qd_full[st], (c / NST) & 1);
+          TRACE(2, 4 * c);
           tc_fence_after_sync();
           const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
           const uint32_t do_addr = q_addr + TN * 128;
@@ -882,10 +901,12 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
             umma_ss(tmem + T_DP + (c & 1) * 64, make_smem_desc_sw128(v_addr + kk * 32, 16, 1024),
                     make_smem_desc_sw128(do_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
           umma_commit(&bars->sdp_full[c & 1]);
+          TRACE(2, 4 * c + 1);
         }
         if (c >= 1) {
           const int pc = c - 1, st = pc % NST;
           mbar_wait(&bars->pds_full[pc & 1], (pc >> 1) & 1);
+          TRACE(2, 4 * pc + 2);
           tc_fence_after_sync();
           const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
           const uint32_t do_addr = q_addr + TN * 128;
@@ -898,6 +919,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
             umma_ts(tmem + T_DK, tmem + T_DP + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
                     make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
           umma_commit(&bars->qd_empty[st]);
+          TRACE(2, 4 * pc + 3);
           if (pc == nchunks - 1) umma_commit(&bars->acc_full);
         }
       }
@@ -905,7 +927,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   } else {
     using namespace colscore;
     const int row = (warp & 3) * 32 + lane;
-    const int part = warp >> 2;
+    const int set = warp / (4 * NP);            // which chunk parity this warp serves
+    const int part = (warp >> 2) % NP;
     const int win = (part * W) / 32, sub = (part * W) % 32;
     const int j = j0 + row;
     const bool key_ok = j < p.len;
@@ -925,94 +948,121 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       sc.id_rule = sc.R > 0 ? src.q.side.id_rule : IDR_NONE;
       return sc;
     };
-    const SrcCtx sc0 = make_src(p.src[0], r0);
-    const SrcCtx sc1 = make_src(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
-    KeyCtx kc0, kc1;
-    kc0.j = kc1.j = j;
-    kc0.row = kc1.row = row;
-    kc0.key_ok = kc1.key_ok = key_ok;
-    init_key(kc0, sc0, b);
-    init_key(kc1, sc1, b);
-    auto chunk_q0 = [&](int c) { return c < r0.n ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN; };
-    QLanes ql{0, -1};
-    if (nchunks > 0) ql = load_q_lanes(0 < r0.n ? sc0 : sc1, b, chunk_q0(0) + 32 * win, lane);
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c % NST;
-      const bool first = c < r0.n;
-      const SrcCtx& sc = first ? sc0 : sc1;
-      const KeyCtx& kc = first ? kc0 : kc1;
-      const int g0 = chunk_q0(c) + part * W;
-      const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
-      const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
-      QLanes nl{0, -1};
-      if (c + 1 < nchunks) nl = load_q_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_q0(c + 1) + 32 * win, lane);
-      const Plan pl = classify<W>(sc, kc, ql, wrow0, g0, lane, p.neg, sub);
-      mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
-      mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
-      tc_fence_after_sync();
-      const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + part * W;
-      const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + part * W * sc.rw;
-      uint32_t p_pk[W / 2], ds_pk[W / 2];
-      if (pl.mode == GM_DEAD) {
+    // One call per query source (inlined twice: no per-field selects inside the chunk loop).
+    // Chunks [c_begin, c_end) belong to this source; this warp set handles those with c % SETS == set.
+    auto run_chunks = [&](const SrcCtx sc, const KeyCtx kc, int c_begin, int c_end, int ib) {
+      int c = c_begin + ((set - c_begin) % SETS + SETS) % SETS;
+      if (c >= c_end) return;
+      QLanes ql = load_q_lanes(sc, b, ib + (c - c_begin) * TN + 32 * win, lane);
+#pragma unroll 1
+      for (; c < c_end; c += SETS) {
+        const int st = c % NST;
+        const int g0 = ib + (c - c_begin) * TN + part * W;
+        const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
+        const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
+        QLanes nl{0, -1};
+        if (c + SETS < c_end) nl = load_q_lanes(sc, b, ib + (c + SETS - c_begin) * TN + 32 * win, lane);
+        const Plan pl = classify<W>(sc, kc, ql, wrow0, g0, lane, p.neg, sub);
+        if (tid == 0) TRACE(0, 4 * c);
+        mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
+        mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        if (tid == 0) TRACE(0, 4 * c + 1);
+        tc_fence_after_sync();
+        const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + part * W;
+        const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + part * W * sc.rw;
+        uint32_t p_pk[W / 2], ds_pk[W / 2];
+        if (pl.mode == GM_DEAD) {
 #pragma unroll
-        for (int x = 0; x < W / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
-      } else if (pl.mode == GM_GEN) {
-        group_generic_tmem<W>(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg, sub);
-        uint32_t v[W];
-        tmem_ldN(t_s, v);
-        tmem_wait_ld();
+          for (int x = 0; x < W / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
+        } else if (pl.mode == GM_GEN) {
+          group_generic_tmem<W>(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg, sub);
+          uint32_t v[W];
+          tmem_ldN(t_s, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < W / 2; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-        tmem_ldN(t_dp, v);
-        tmem_wait_ld();
+          for (int x = 0; x < W / 2; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+          tmem_ldN(t_dp, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-      } else {
-        float t[W];
-        uint32_t v[W];
-        tmem_ldN(t_s, v);
-        tmem_wait_ld();
+          for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+        } else {
+          float t[W];
+          uint32_t v[W];
+          tmem_ldN(t_s, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
-        score_group<W>(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg, sub);
-        tmem_ldN(t_dp, v);
-        tmem_wait_ld();
-        const bool guard = (pl.mode == GM_EDGE);   // dead columns may carry garbage row records
+          for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
+          score_group<W>(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg, sub);
+          tmem_ldN(t_dp, v);
+          tmem_wait_ld();
+          if (pl.mode == GM_EDGE) {   // dead columns may carry garbage row records: guarded variant
 #pragma unroll
-        for (int x = 0; x < W / 2; ++x) {
-          float pv[2], dsv[2];
+            for (int x = 0; x < W / 2; ++x) {
+              float pv[2], dsv[2];
 #pragma unroll
-          for (int y = 0; y < 2; ++y) {
-            const int ii = 2 * x + y;
-            const float4 r4 = rs[ii];   // (m*log2e, 1/l, delta, -): warp-broadcast LDS.128
-            const float e = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
-            const float d = e * (__uint_as_float(v[ii]) - r4.z);
-            const bool dead = guard && (t[ii] == -INFINITY);
-            pv[y] = dead ? 0.f : e;
-            dsv[y] = dead ? 0.f : d;
+              for (int y = 0; y < 2; ++y) {
+                const int ii = 2 * x + y;
+                const float4 r4 = rs[ii];
+                const float e = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
+                const float d = e * (__uint_as_float(v[ii]) - r4.z);
+                const bool dead = (t[ii] == -INFINITY);
+                pv[y] = dead ? 0.f : e;
+                dsv[y] = dead ? 0.f : d;
+              }
+              p_pk[x] = pack_bf16x2(pv[0], pv[1]);
+              ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
+            }
+          } else {
+#pragma unroll
+            for (int x = 0; x < W / 2; ++x) {
+              float pv[2], dsv[2];
+#pragma unroll
+              for (int y = 0; y < 2; ++y) {
+                const int ii = 2 * x + y;
+                const float4 r4 = rs[ii];   // (m*log2e, 1/l, delta, -): warp-broadcast LDS.128
+                pv[y] = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
+                dsv[y] = pv[y] * (__uint_as_float(v[ii]) - r4.z);
+              }
+              p_pk[x] = pack_bf16x2(pv[0], pv[1]);
+              ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
+            }
           }
-          p_pk[x] = pack_bf16x2(pv[0], pv[1]);
-          ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
         }
+        if (tid == 0) TRACE(0, 4 * c + 2);
+        tmem_stN(t_s, p_pk);
+        tmem_stN(t_dp, ds_pk);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->pds_full[c & 1]);
+        if (tid == 0) TRACE(0, 4 * c + 3);
+        ql = nl;
       }
-      tmem_stN(t_s, p_pk);
-      tmem_stN(t_dp, ds_pk);
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->pds_full[c & 1]);
-      ql = nl;
+    };
+    {
+      KeyCtx kc;
+      kc.j = j; kc.row = row; kc.key_ok = key_ok;
+      const SrcCtx sc0 = make_src(p.src[0], r0);
+      init_key(kc, sc0, b);
+      run_chunks(sc0, kc, 0, r0.n, r0.ib);
+      if (p.nsrc > 1) {
+        const SrcCtx sc1 = make_src(p.src[1], r1);
+        init_key(kc, sc1, b);
+        run_chunks(sc1, kc, r0.n, nchunks, r1.ib);
+      }
     }
     mbar_wait_warp(&bars->acc_full, 0);
     tc_fence_after_sync();
-    uint32_t dv_raw[W], dk_raw[W];
-    tmem_ldN(tmem + T_DV + lane_sel + part * W, dv_raw);
-    tmem_ldN(tmem + T_DK + lane_sel + part * W, dk_raw);
+    constexpr int WO = 64 / (NP * SETS);         // output columns per thread
+    const int opart = set * NP + part;
+    uint32_t dv_raw[WO], dk_raw[WO];
+    tmem_ldN(tmem + T_DV + lane_sel + opart * WO, dv_raw);
+    tmem_ldN(tmem + T_DK + lane_sel + opart * WO, dk_raw);
     tmem_wait_ld();
     if (key_ok) {
-      __nv_bfloat16* dv = row_ptr_mut<__nv_bfloat16>(p.d_v, b, j, h) + part * W;
-      __nv_bfloat16* dk = row_ptr_mut<__nv_bfloat16>(p.d_k, b, j, h) + part * W;
+      __nv_bfloat16* dv = row_ptr_mut<__nv_bfloat16>(p.d_v, b, j, h) + opart * WO;
+      __nv_bfloat16* dk = row_ptr_mut<__nv_bfloat16>(p.d_k, b, j, h) + opart * WO;
 #pragma unroll
-      for (int x = 0; x < W / 8; ++x) {
+      for (int x = 0; x < WO / 8; ++x) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 0]), __uint_as_float(dv_raw[8 * x + 1]));
         w.y = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 2]), __uint_as_float(dv_raw[8 * x + 3]));
@@ -1060,6 +1110,12 @@ bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d) {
 
 static bool g_attr_q = false, g_attr_kv = false;
 
+#ifdef MLT_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace_b, sizeof(unsigned long long) * 3 * 256);
+}
+#endif
+
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
     cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
@@ -1104,7 +1160,7 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   if (!g_attr_kv) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_kv = true;
   }
@@ -1133,7 +1189,7 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.len + TM - 1) / TM, a.H, a.B);
-  tc_bwd_kv_kernel<4><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  tc_bwd_kv_kernel<2, 2><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();
 }
 

@@ -279,20 +279,44 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
     for (int x = 0; x < 64; ++x) o[x] = 0.f;
 
-    for (int c = 0; c <= nchunks; ++c) {
-      float alpha = 0.f;
-      if (c < nchunks) {
-        const bool first = c < r0.n;
-        const SegCtx& sc = first ? sc0 : sc1;
-        const RowCtx& rc = first ? rc0 : rc1;
-        const int key0 = chunk_key0(c);
+    auto add_o = [&](int pc) {   // o = o * alpha_prev + O_pc
+      mbar_wait_warp(&bars->o_full[pc & 1], (pc >> 1) & 1);
+      if (tid == 0) TRACE(0, 7 + 4 * pc);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(tmem + 128 + (pc & 1) * 64 + lane_sel + hh * 32, v);
+        tmem_wait_ld();
+        if (hh == 0) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) o[x] = fmaf(o[x], alpha_prev, __uint_as_float(v[x]));
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) o[32 + x] = fmaf(o[32 + x], alpha_prev, __uint_as_float(v[x]));
+        }
+      }
+    };
+    int c = 0;   // chunk counter over both segments
+#pragma unroll 1
+    for (int sgi = 0; sgi < a.nseg; ++sgi) {
+      // segment context copied once: no per-field selects inside the chunk loop
+      const SegCtx sc = sgi ? sc1 : sc0;
+      const RowCtx rc = sgi ? rc1 : rc0;
+      const int seg_n = sgi ? r1.n : r0.n;
+      const int seg_kb = sgi ? r1.kb : r0.kb;
+#pragma unroll 1
+      for (int cc = 0; cc < seg_n; ++cc, ++c) {
+        const int key0 = seg_kb + cc * TN;
         const uint32_t t_s = tmem + (c & 1) * 64 + lane_sel;
         // prefetch the key-side lane scalars of the next chunk
         GroupLanes nl0{0, -1}, nl1{0, -1};
-        if (c + 1 < nchunks) {
-          const SegCtx& sn = (c + 1) < r0.n ? sc0 : sc1;
-          nl0 = load_group_lanes(sn, b, chunk_key0(c + 1), lane);
-          nl1 = load_group_lanes(sn, b, chunk_key0(c + 1) + 32, lane);
+        if (cc + 1 < seg_n) {
+          nl0 = load_group_lanes(sc, b, key0 + TN, lane);
+          nl1 = load_group_lanes(sc, b, key0 + TN + 32, lane);
+        } else if (sgi == 0 && a.nseg > 1 && r1.n > 0) {
+          nl0 = load_group_lanes(sc1, b, r1.kb, lane);
+          nl1 = load_group_lanes(sc1, b, r1.kb + 32, lane);
         }
         if (tid == 0) TRACE(0, 4 + 4 * c);
         mbar_wait_warp(&bars->s_full[c & 1], (c >> 1) & 1);
@@ -303,7 +327,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         uint32_t dead_mask = 0;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
-          const GroupLanes& gl = g ? gl1 : gl0;
+          const GroupLanes gl = g ? gl1 : gl0;
           const int g0 = key0 + 32 * g;
           const GroupPlan gp = classify(sc, rc, gl, wrow0, g0, lane, a.neg);
           if (gp.mode == GM_DEAD) {
@@ -331,7 +355,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         tmem_wait_st();
         const float m_new = fmaxf(m, mx);
-        alpha = ex2((m - m_new) * LOG2E);
+        const float alpha = ex2((m - m_new) * LOG2E);
         const float mb = m_new * LOG2E;
         // ---- pass 2: p = exp2(t * log2e - mb), row sum, P (bf16) back into TMEM ----
         float lsum = 0.f;
@@ -365,28 +389,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         m = m_new;
         gl0 = nl0;
         gl1 = nl1;
+        if (c >= 1) add_o(c - 1);   // uses alpha_prev = alpha of chunk c-1
+        alpha_prev = alpha;
       }
-      if (c >= 1) {
-        const int pc = c - 1;
-        mbar_wait_warp(&bars->o_full[pc & 1], (pc >> 1) & 1);
-        if (tid == 0) TRACE(0, 7 + 4 * pc);
-        tc_fence_after_sync();
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld32(tmem + 128 + (pc & 1) * 64 + lane_sel + hh * 32, v);
-          tmem_wait_ld();
-          if (hh == 0) {
-#pragma unroll
-            for (int x = 0; x < 32; ++x) o[x] = fmaf(o[x], alpha_prev, __uint_as_float(v[x]));
-          } else {
-#pragma unroll
-            for (int x = 0; x < 32; ++x) o[32 + x] = fmaf(o[32 + x], alpha_prev, __uint_as_float(v[x]));
-          }
-        }
-      }
-      alpha_prev = alpha;
     }
+    if (nchunks >= 1) add_o(nchunks - 1);
     if (row_ok) {
       const float inv = 1.f / l;
       __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.out, b, i, h);
