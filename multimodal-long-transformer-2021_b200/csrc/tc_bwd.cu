@@ -155,17 +155,22 @@ __device__ __forceinline__ void bwd_q_group_generic_tmem(uint32_t t_s, uint32_t 
   tmem_wait_st();
 }
 
-template <int NP>
-__global__ void __launch_bounds__(nthreads<NP>(), 1)
+// NP threads per row inside a warp set; SETS warp sets take alternate chunks (S / dP are
+// double-buffered by chunk parity, so set s owns buffer s).
+template <int NP, int SETS>
+__global__ void __launch_bounds__(nthreads<NP * SETS>(), 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
                 const __grid_constant__ CUtensorMap map_e, const TcBwdQParams p) {
   using namespace bq;
   constexpr int W = 64 / NP;          // columns per elementwise thread and chunk
-  constexpr int NEW = 128 * NP;       // elementwise threads
-  constexpr int WP = 4 * NP, WM = 4 * NP + 1;   // producer / MMA warp
-  constexpr int RB = NP == 4 ? 32 : 64;         // bin slots per part (host picks NP = 4 only if R <= 32)
+  constexpr int NEW = 128 * NP;       // elementwise threads per set
+  constexpr int NALL = NEW * SETS;    // all elementwise threads
+  constexpr int NB = NP * SETS;       // private bin arrays per row
+  constexpr int WP = 4 * NB, WM = 4 * NB + 1;   // producer / MMA warp
+  constexpr int RB = 128 / NB;        // bin slots per array (host guarantees R <= RB)
+  static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
@@ -282,7 +287,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ===================== elementwise warps (NP threads per row) =====================
     using namespace rowscore;
     const int row = (warp & 3) * 32 + lane;
-    const int part = warp >> 2;          // which W-column slice of every chunk
+    const int set = warp / (4 * NP);     // which chunk parity this warp serves
+    const int part = (warp >> 2) % NP;   // which W-column slice of the chunk
+    const int bidx = set * NP + part;    // private bin array / output column slice
     const int win = (part * W) / 32;     // 32-key lane window holding the slice
     const int sub = (part * W) % 32;     // offset of the slice inside the window
     const int i = i0 + row;
@@ -291,7 +298,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const int pd = a.seg[0].side.max_distance;
     const bool perm = (2 * pd + 1 <= R);
-    float* bin = bins + part * RB * TM;   // slot-ordered, private to (part, row)
+    float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
     for (int x = lane + 32 * (warp & 3); x < RB * TM; x += 128) bin[x] = 0.f;
     SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
     SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
@@ -302,10 +309,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     init_row_loads(rc0, sc0, b);
     init_row_loads(rc1, sc1, b);
     auto chunk_key0 = [&](int c) { return c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN; };
-    GroupLanes gl{0, -1};
-    if (nchunks > 0) gl = load_group_lanes(0 < r0.n ? sc0 : sc1, b, chunk_key0(0) + 32 * win, lane);
     float bias_l0 = 0.f, bias_l1 = 0.f;
-    if (rpad && part == 0) {
+    if (rpad && bidx == 0) {
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
       if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
       if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
@@ -332,9 +337,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + srow);
       m2 = st.x * LOG2E;
       linv = 1.f / st.y;
-      if (part == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
+      if (bidx == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
     }
-    if (rpad && part == 0) {   // warp-uniform: the four part-0 warps extract allrel
+    if (rpad && bidx == 0) {   // warp-uniform: the four (set 0, part 0) warps extract allrel
       mbar_wait_warp(&bars->rel_full, 0);
       tc_fence_after_sync();
 #pragma unroll 1
@@ -354,27 +359,25 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-    named_bar_sync(1, NEW);  // rel_s (written by part 0) visible to all parts; bins zeroed
+    named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
     init_row(rc0, sc0, b, rel_s);
     init_row(rc1, sc1, b, rel_s);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
     float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
 
-    int c = 0;   // chunk counter over both segments
+    // One call per key segment (inlined twice: no per-field selects inside the chunk loop).
+    // Chunks [c_begin, c_end) belong to this segment; this warp set handles c % SETS == set.
+    auto run_chunks = [&](const SegCtx sc, const RowCtx rc, int c_begin, int c_end, int kb) {
+      int c = c_begin + ((set - c_begin) % SETS + SETS) % SETS;
+      if (c >= c_end) return;
+      GroupLanes gl = load_group_lanes(sc, b, kb + (c - c_begin) * TN + 32 * win, lane);
 #pragma unroll 1
-    for (int sgi = 0; sgi < a.nseg; ++sgi) {
-      // segment context copied once: no per-field selects inside the chunk loop
-      const SegCtx sc = sgi ? sc1 : sc0;
-      const RowCtx rc = sgi ? rc1 : rc0;
-      const int seg_n = sgi ? r1.n : r0.n;
-      const int seg_kb = sgi ? r1.kb : r0.kb;
-#pragma unroll 1
-      for (int cc = 0; cc < seg_n; ++cc, ++c) {
-        const int g0 = seg_kb + cc * TN + part * W;
+      for (; c < c_end; c += SETS) {
+        const int g0 = kb + (c - c_begin) * TN + part * W;
         const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
         const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
         GroupLanes nl{0, -1};
-        if (c + 1 < nchunks) nl = load_group_lanes((c + 1) < r0.n ? sc0 : sc1, b, chunk_key0(c + 1) + 32 * win, lane);
+        if (c + SETS < c_end) nl = load_group_lanes(sc, b, kb + (c + SETS - c_begin) * TN + 32 * win, lane);
         const GroupPlan gp = classify<W>(sc, rc, gl, wrow0, g0, lane, a.neg, sub);
         mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
         tc_fence_after_sync();
@@ -449,7 +452,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_arrive(&bars->ds_full[c & 1]);
         gl = nl;
       }
-    }
+    };
+    run_chunks(sc0, rc0, 0, r0.n, r0.kb);
+    if (a.nseg > 1) run_chunks(sc1, rc1, r0.n, nchunks, r1.kb);
     // flush the constant-class accumulators into this part's bins
     if (R > 0) {
       auto flush = [&](int id, float v) {
@@ -462,8 +467,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       flush(2 * dd + 2, accX1);
     }
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
-    named_bar_sync(1, NEW);  // all parts' bins complete
-    if (rpad && part == 0) {
+    named_bar_sync(1, NALL);  // all bin arrays complete
+    if (rpad && bidx == 0) {
 #pragma unroll 1
       for (int c0 = 0; c0 < rpad; c0 += 16) {
         uint32_t pk[8];
@@ -477,7 +482,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (pid < R) {
               const int sl = slot_of_id(pid, pd, perm);
 #pragma unroll
-              for (int pp = 0; pp < NP; ++pp) w += bins[(pp * RB + sl) * TM + row];
+              for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
               if (row_ok) a.dallrel[srow * R + pid] = w;
             }
             w2[y] = w;
@@ -492,16 +497,17 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     mbar_wait_warp(&bars->dq_full, 0);
     tc_fence_after_sync();
-    uint32_t dq_raw[W];
-    tmem_ldN(tmem + T_DQ + lane_sel + part * W, dq_raw);
+    constexpr int WO = 64 / NB;   // output columns per thread
+    uint32_t dq_raw[WO];
+    tmem_ldN(tmem + T_DQ + lane_sel + bidx * WO, dq_raw);
     tmem_wait_ld();
-    float dq[W];
+    float dq[WO];
 #pragma unroll
-    for (int x = 0; x < W; ++x) dq[x] = __uint_as_float(dq_raw[x]);
+    for (int x = 0; x < WO; ++x) dq[x] = __uint_as_float(dq_raw[x]);
     if (row_ok) {
-      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + part * W;
+      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + bidx * WO;
 #pragma unroll
-      for (int x = 0; x < W / 8; ++x) {
+      for (int x = 0; x < WO / 8; ++x) {
         uint4 w;
         w.x = pack_bf16x2(dq[8 * x + 0] * a.scale, dq[8 * x + 1] * a.scale);
         w.y = pack_bf16x2(dq[8 * x + 2] * a.scale, dq[8 * x + 3] * a.scale);
@@ -1118,9 +1124,9 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(uns
 
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1150,17 +1156,24 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
-  static const int force_np = getenv("MLT_BWD_NP") ? atoi(getenv("MLT_BWD_NP")) : 0;
-  if (R <= 32 && force_np == 4)   // optional: four threads per row (measured slower than two)
-    tc_bwd_q_kernel<4><<<grid, nthreads<4>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  // chunks per tile: with many chunks (dense global rows) two warp sets on alternate chunks win;
+  // with few (long rows: band + G/64) the extra per-tile prologue work does not pay off.
+  auto seg_chunks = [](const KeySeg& sg) { return sg.band ? (TM + 2 * sg.radius + TN - 1) / TN : (sg.len + TN - 1) / TN; };
+  const int est_chunks = seg_chunks(a.seg[0]) + (a.nseg > 1 ? seg_chunks(a.seg[1]) : 0);
+  static const int force_sets = getenv("MLT_BWD_SETS") ? atoi(getenv("MLT_BWD_SETS")) : 0;
+  const bool two_sets = force_sets ? force_sets == 2 : est_chunks >= 16;
+  if (R <= 32 && two_sets)   // 4 private bin arrays of 32 slots
+    tc_bwd_q_kernel<2, 2><<<grid, nthreads<4>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else
-    tc_bwd_q_kernel<2><<<grid, nthreads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<2, 1><<<grid, nthreads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   if (!g_attr_kv) {
     cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_kv = true;
   }
@@ -1189,7 +1202,12 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.len + TM - 1) / TM, a.H, a.B);
-  tc_bwd_kv_kernel<2, 2><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  auto src_chunks = [](const QuerySource& q) { return q.band ? (TM + 2 * q.radius + TN - 1) / TN : (q.rows.len + TN - 1) / TN; };
+  const int est_chunks = src_chunks(a.src[0]) + (a.nsrc > 1 ? src_chunks(a.src[1]) : 0);
+  if (est_chunks >= 16)
+    tc_bwd_kv_kernel<2, 2><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  else
+    tc_bwd_kv_kernel<4, 1><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();
 }
 
