@@ -360,7 +360,7 @@ int launch_bwd_q(const BwdQArgs& a, bool tc, void* tc_ws, int dtype, int d, cons
                  double bytes, cudaStream_t st) {
   char full[48];
   snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
-  ProfileScope ps(full, flops, bytes, st);
+  ProfileScope ps(full, flops, bytes, st, tc ? 2 : 1);   // tcgen05 path = row-record preprocess + main kernel
   if (tc) return tc_launch_bwd_q(a, tc_ws, st);
   MLT_CUDA(simt_launch_bwd_q(a, dtype, d, st));
   return MLT_OK;

@@ -70,6 +70,43 @@ __device__ __forceinline__ void side_ok_id(const Side& sd, int b, int i, int j, 
 }
 
 // ============================================================================================
+// Preprocess: rowstat[b,h,i] = (max * log2e, 1 / sum, delta = sum_c dO * O, 0).  HBM-bound,
+// coalesced: 8 lanes x 16 B cover one 128-byte row of dO and of O.
+// ============================================================================================
+__global__ void __launch_bounds__(256) tc_bwd_prep_kernel(const T4 out, const T4 d_out, const float* stats,
+                                                          float4* rowstat, int B, int H, int len, int lp) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r = t >> 3;   // row index over (b, i, h): h fastest (matches the tensor layout)
+  const int sub8 = (int)(t & 7);
+  const int64_t total = (int64_t)B * len * H;
+  float acc = 0.f;
+  int b = 0, i = 0, h = 0;
+  const bool ok = r < total;
+  if (ok) {
+    h = (int)(r % H);
+    i = (int)((r / H) % len);
+    b = (int)(r / ((int64_t)H * len));
+    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(d_out, b, i, h)) + sub8);
+    const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(out, b, i, h)) + sub8);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[y]));
+      const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[y]));
+      acc = fmaf(gf.x, of.x, acc);
+      acc = fmaf(gf.y, of.y, acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (ok && sub8 == 0) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + ((int64_t)(b * H + h) * len + i));
+    rowstat[(int64_t)(b * H + h) * lp + i] = make_float4(st.x * LOG2E, 1.f / st.y, acc, 0.f);
+  }
+}
+
+// ============================================================================================
 // Query-centric pass
 // ============================================================================================
 namespace bq {
@@ -193,7 +230,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&bars->ds_full[s], NEW);
     }
     mbar_init(&bars->dq_full, 1);
-    mbar_init(&bars->dar_full, 128);
+    mbar_init(&bars->dar_full, NALL);
     fence_barrier_init();
   }
   if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
@@ -286,6 +323,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   } else {
     // ===================== elementwise warps (NP threads per row) =====================
     using namespace rowscore;
+    if (tid == 0) TRACE(1, 0);
     const int row = (warp & 3) * 32 + lane;
     const int set = warp / (4 * NP);     // which chunk parity this warp serves
     const int part = (warp >> 2) % NP;   // which W-column slice of the chunk
@@ -315,32 +353,20 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
       if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
     }
-    // row constants
+    // row constants (written by tc_bwd_prep_kernel)
     float m2 = 0.f, linv = 0.f, delta = 0.f;
     const int64_t srow = (int64_t)(b * a.H + h) * a.rows.len + i;
     const int64_t prow = (int64_t)(b * a.H + h) * p.lp + i;
     if (row_ok) {
-      const uint4* go = reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(a.d_out, b, i, h));
-      const uint4* oo = reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(a.out, b, i, h));
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const uint4 g4 = __ldg(go + x), o4 = __ldg(oo + x);
-        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[y]));
-          const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[y]));
-          delta = fmaf(gf.x, of.x, delta);
-          delta = fmaf(gf.y, of.y, delta);
-        }
-      }
-      const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + srow);
-      m2 = st.x * LOG2E;
-      linv = 1.f / st.y;
-      if (bidx == 0) p.rowstat[prow] = make_float4(m2, linv, delta, 0.f);
+      const float4 rs4 = __ldg(p.rowstat + prow);
+      m2 = rs4.x;
+      linv = rs4.y;
+      delta = rs4.z;
     }
+    if (tid == 0) TRACE(1, 1);
     if (rpad && bidx == 0) {   // warp-uniform: the four (set 0, part 0) warps extract allrel
       mbar_wait_warp(&bars->rel_full, 0);
+      if (tid == 0) TRACE(1, 2);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int c0 = 0; c0 < rpad; c0 += 16) {
@@ -351,15 +377,22 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int x = 0; x < 16; ++x) {
           const int pid = c0 + x;
           const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
-          if (pid < R) {
-            const float val = (__uint_as_float(v[x]) + bv) * a.scale;
-            rel_s[slot_of_id(pid, pd, perm) * TM + row] = val;
-            if (row_ok) p.allrel_ws[prow * p.rw + pid] = val;
-          }
+          const float val = pid < R ? (__uint_as_float(v[x]) + bv) * a.scale : 0.f;
+          if (pid < R) rel_s[slot_of_id(pid, pd, perm) * TM + row] = val;
+          v[x] = __float_as_uint(val);
+        }
+        if (row_ok) {   // 16 ids = 4 x 16-byte stores (workspace rows are padded to a multiple of 4 ids)
+#pragma unroll
+          for (int x4 = 0; x4 < 4; ++x4)
+            if (c0 + 4 * x4 < p.rw)
+              *reinterpret_cast<uint4*>(p.allrel_ws + prow * p.rw + c0 + 4 * x4) =
+                  make_uint4(v[4 * x4], v[4 * x4 + 1], v[4 * x4 + 2], v[4 * x4 + 3]);
         }
       }
     }
+    if (tid == 0) TRACE(1, 3);
     named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
+    if (tid == 0) TRACE(1, 4);
     init_row(rc0, sc0, b, rel_s);
     init_row(rc1, sc1, b, rel_s);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
@@ -379,7 +412,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         GroupLanes nl{0, -1};
         if (c + SETS < c_end) nl = load_group_lanes(sc, b, kb + (c + SETS - c_begin) * TN + 32 * win, lane);
         const GroupPlan gp = classify<W>(sc, rc, gl, wrow0, g0, lane, a.neg, sub);
+        if (tid == 0) TRACE(1, 8 + 3 * c);
         mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        if (tid == 0) TRACE(1, 9 + 3 * c);
         tc_fence_after_sync();
         uint32_t ds_pk[W / 2];
         if (gp.mode == GM_DEAD) {
@@ -450,6 +485,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->ds_full[c & 1]);
+        if (tid == 0) TRACE(1, 10 + 3 * c);
         gl = nl;
       }
     };
@@ -467,35 +503,51 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       flush(2 * dd + 2, accX1);
     }
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
+    if (tid == 0) TRACE(1, 5);
     named_bar_sync(1, NALL);  // all bin arrays complete
-    if (rpad && bidx == 0) {
+    if (rpad) {
+      // every thread of the row packs a slice of 8 ids: sum over the NB private bin arrays,
+      // publish dallrel (fp32, id order) and write the bf16 A-operand columns for dQ += dallrel.E
 #pragma unroll 1
-      for (int c0 = 0; c0 < rpad; c0 += 16) {
-        uint32_t pk[8];
+      for (int c0 = 8 * bidx; c0 < rpad; c0 += 8 * NB) {
+        uint32_t pk[4];
+        float w8[8];
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
-          float w2[2];
+          const int pid = c0 + x;
+          float w = 0.f;
+          if (pid < R) {
+            const int sl = slot_of_id(pid, pd, perm);
 #pragma unroll
-          for (int y = 0; y < 2; ++y) {
-            const int pid = c0 + 2 * x + y;
-            float w = 0.f;
-            if (pid < R) {
-              const int sl = slot_of_id(pid, pd, perm);
-#pragma unroll
-              for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
-              if (row_ok) a.dallrel[srow * R + pid] = w;
-            }
-            w2[y] = w;
+            for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
           }
-          pk[x] = pack_bf16x2(w2[0], w2[1]);
+          w8[x] = w;
         }
-        tmem_st8(tmem + T_REL + lane_sel + c0 / 2, pk);
+        if (row_ok) {
+          float* dst = a.dallrel + srow * R + c0;
+          if ((R & 3) == 0 && c0 + 8 <= R) {
+            *reinterpret_cast<float4*>(dst) = make_float4(w8[0], w8[1], w8[2], w8[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(w8[4], w8[5], w8[6], w8[7]);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if (c0 + x < R) dst[x] = w8[x];
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) pk[x] = pack_bf16x2(w8[2 * x], w8[2 * x + 1]);
+        // 4 packed columns; tcgen05.st needs the whole warp: the loop bounds are warp-uniform
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tmem + T_REL + lane_sel + c0 / 2),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                     : "memory");
       }
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->dar_full);
     }
+    if (tid == 0) TRACE(1, 6);
     mbar_wait_warp(&bars->dq_full, 0);
+    if (tid == 0) TRACE(1, 7);
     tc_fence_after_sync();
     constexpr int WO = 64 / NB;   // output columns per thread
     uint32_t dq_raw[WO];
@@ -1155,6 +1207,13 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
     me = mq;
   }
   if (e) return MLT_ERR_UNSUPPORTED;
+  {
+    const int64_t threads = (int64_t)a.B * a.rows.len * a.H * 8;
+    tc_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.out, a.d_out, a.stats, p.rowstat, a.B, a.H,
+                                                                       a.rows.len, p.lp);
+    cudaError_t pe = cudaGetLastError();
+    if (pe != cudaSuccess) return (int)pe;
+  }
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
   // chunks per tile: with many chunks (dense global rows) two warp sets on alternate chunks win;
   // with few (long rows: band + G/64) the extra per-tile prologue work does not pay off.

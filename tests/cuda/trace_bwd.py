@@ -20,6 +20,6 @@ buf = (ctypes.c_ulonglong * (3 * 256))()
 print('rc', lib.mlt_debug_read_trace_b(buf))
 t = np.array(buf[:], dtype=np.int64).reshape(3, 256)
 t0 = t[t > 0].min()
-for role, name in enumerate(['elementwise', 'producer', 'mma']):
+for role, name in enumerate(['kv_elementwise', 'bq_elementwise', 'kv_mma']):
   vals = [(i, int(v - t0)) for i, v in enumerate(t[role]) if v > 0]
   print(name, vals)
