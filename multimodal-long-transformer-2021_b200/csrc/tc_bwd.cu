@@ -209,7 +209,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr int RB = 128 / NB;        // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
+  // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + SM_REL);
   float* bins = reinterpret_cast<float*>(smem + SM_BIN);
@@ -883,7 +885,9 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   constexpr int WP = 4 * NP * SETS, WM = 4 * NP * SETS + 1;
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
+  // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TM;

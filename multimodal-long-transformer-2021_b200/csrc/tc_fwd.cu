@@ -107,7 +107,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               const __grid_constant__ CUtensorMap map_v1, const __grid_constant__ CUtensorMap map_e,
               const TcFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
+  // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + SM_REL);
   const FwdArgs& a = p.a;
