@@ -534,6 +534,7 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   ql.out = to_t4(p->long_out); ql.d_out = to_t4(g->d_long_out); ql.d_q = to_t4(g->d_long_q);
   ql.stats = p->long_stats; ql.delta = wl.delta; ql.allrel = wl.allrel; ql.dallrel = wl.dallrel;
   ql.B = p->B; ql.H = p->H; ql.scale = p->scale; ql.neg = p->neg;
+  ql.tg_partial = wl.partial; ql.tg_partial_bias = wl.partial_bias;
   BwdQArgs qg{};
   qg.rows = glob_rows;
   qg.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_g2g);
@@ -542,6 +543,7 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   qg.out = to_t4(p->global_out); qg.d_out = to_t4(g->d_global_out); qg.d_q = to_t4(g->d_global_q);
   qg.stats = p->global_stats; qg.delta = wg.delta; qg.allrel = wg.allrel; qg.dallrel = wg.dallrel;
   qg.B = p->B; qg.H = p->H; qg.scale = p->scale; qg.neg = p->neg;
+  qg.tg_partial = wg.partial; qg.tg_partial_bias = wg.partial_bias;
   // long keys: from long queries (band, l2l) and global queries (dense, g2l)
   BwdKVArgs kl{};
   kl.k = to_t4(p->long_k); kl.v = to_t4(p->long_v); kl.d_k = to_t4(g->d_long_k); kl.d_v = to_t4(g->d_long_v);
@@ -590,16 +592,18 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
     TableGradArgs tl{to_t4(p->long_q), p->L, wl.dallrel, wl.partial, wl.partial_bias, g->d_long_emb,
                      g->d_long_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->L), p->scale};
     {
-      ProfileScope ps("simt_table_grad_long", bh * 2 * dd * RR * p->L,
-                      qkv_bytes(bh, p->L, p->d, p->dtype, 1), s2, 2);
-      MLT_CUDA(simt_launch_table_grad(tl, p->dtype, s2));
+      ProfileScope ps(tc ? "table_grad_reduce_long" : "simt_table_grad_long", bh * 2 * dd * RR * p->L,
+                      qkv_bytes(bh, p->L, p->d, p->dtype, 1), s2, tc ? 1 : 2);
+      if (tc) MLT_CUDA(simt_launch_table_grad_reduce(tl, s2));   // partials came from tc_bwd_q_kernel
+      else MLT_CUDA(simt_launch_table_grad(tl, p->dtype, s2));
     }
     TableGradArgs tg{to_t4(p->global_q), p->G, wg.dallrel, wg.partial, wg.partial_bias, g->d_global_emb,
                      g->d_global_bias, p->B, p->H, p->R, p->d, simt_table_grad_chunks(p->G), p->scale};
     {
-      ProfileScope ps("simt_table_grad_global", bh * 2 * dd * RR * p->G,
-                      qkv_bytes(bh, p->G, p->d, p->dtype, 1), s2, 2);
-      MLT_CUDA(simt_launch_table_grad(tg, p->dtype, s2));
+      ProfileScope ps(tc ? "table_grad_reduce_global" : "simt_table_grad_global", bh * 2 * dd * RR * p->G,
+                      qkv_bytes(bh, p->G, p->d, p->dtype, 1), s2, tc ? 1 : 2);
+      if (tc) MLT_CUDA(simt_launch_table_grad_reduce(tg, s2));
+      else MLT_CUDA(simt_launch_table_grad(tg, p->dtype, s2));
     }
   }
   MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),

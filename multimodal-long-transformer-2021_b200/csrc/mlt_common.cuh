@@ -80,6 +80,10 @@ struct BwdQArgs {
   float* delta;    // ws [B, H, Lq]
   float* allrel;   // ws [B, H, Lq, R]
   float* dallrel;  // ws [B, H, Lq, R]
+  // tcgen05 path only: per-tile table-gradient partials [(b * ntile + tile) * H + h][R][d] and
+  // [...][R] (layout of TableGradArgs::partial / partial_bias); dallrel is then not written.
+  float* tg_partial;
+  float* tg_partial_bias;
   int B, H;
   float scale, neg;
 };
@@ -259,6 +263,8 @@ cudaError_t simt_launch_fwd(const FwdArgs& a, int dtype, int d, cudaStream_t st)
 cudaError_t simt_launch_bwd_q(const BwdQArgs& a, int dtype, int d, cudaStream_t st);
 cudaError_t simt_launch_bwd_kv(const BwdKVArgs& a, int dtype, int d, cudaStream_t st);
 cudaError_t simt_launch_table_grad(const TableGradArgs& a, int dtype, cudaStream_t st);
+// stage 2 only (fixed-order sum of the partials): used when the tcgen05 backward produced them
+cudaError_t simt_launch_table_grad_reduce(const TableGradArgs& a, cudaStream_t st);
 int simt_table_grad_chunks(int len);
 bool simt_supports_head_dim(int d);
 

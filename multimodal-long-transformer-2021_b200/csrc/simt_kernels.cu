@@ -577,6 +577,11 @@ cudaError_t simt_launch_bwd_q(const BwdQArgs& a, int dtype, int d, cudaStream_t 
 cudaError_t simt_launch_bwd_kv(const BwdKVArgs& a, int dtype, int d, cudaStream_t st) {
   MLT_DISPATCH(launch_bwd_kv_t, a);
 }
+cudaError_t simt_launch_table_grad_reduce(const TableGradArgs& a, cudaStream_t st) {
+  const int total = a.R * a.H * a.d + a.R * a.H;
+  table_grad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
 cudaError_t simt_launch_table_grad(const TableGradArgs& a, int dtype, cudaStream_t st) {
   const int d = a.d;
   MLT_DISPATCH(launch_table_grad_t, a);

@@ -117,10 +117,12 @@ constexpr int SM_E = SM_DO + TM * 128;         // 8 KB
 constexpr int SM_KV = SM_E + 64 * 128;         // NST x 16 KB
 constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64][128] f32
 constexpr int SM_BIN = SM_REL + 64 * TM * 4;         // 2 x [64][128] f32
-constexpr int SM_BAR = SM_BIN + 2 * 64 * TM * 4;
+constexpr int SM_A = SM_BIN + 2 * 64 * TM * 4;      // dallrel^T tile, bf16, [128 rows][64 ids] SW128 (16 KB)
+constexpr int SM_BS = SM_A + TM * 128;              // bias partial sums [4 quadrants][64]
+constexpr int SM_BAR = SM_BS + 4 * 64 * 4;
 constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
 // TMEM columns
-constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_REL = 320;
+constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_REL = 320, T_DE = 384;
 
 struct Bars {
   uint64_t q_full, rel_full;
@@ -316,6 +318,16 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int kk = 0; kk < rpad / 16; ++kk)
                 umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, make_smem_desc_sw128(e_addr + kk * 2048, 16, 1024),
                         idesc_dq, 1u);
+              if (a.tg_partial) {
+                // table-gradient partial of this tile: dE[64 ids x 64] = dallrel^T . Q  (M = 64, both
+                // operands MN-major: K = the tile's 128 rows)
+                const uint32_t idesc_de = make_idesc_bf16(64, 64, 1, 1);
+                const uint32_t a_addr = smem_u32(smem + SM_A);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  umma_ss(tmem + T_DE, make_smem_desc_sw128(a_addr + kk * 2048, 16, 1024),
+                          make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_de, kk > 0);
+              }
             }
             umma_commit(&bars->dq_full);
           }
@@ -340,6 +352,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool perm = (2 * pd + 1 <= R);
     float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
     for (int x = lane + 32 * (warp & 3); x < RB * TM; x += 128) bin[x] = 0.f;
+    for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
     SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
     SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
     RowCtx rc0, rc1;
@@ -525,7 +538,25 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
           w8[x] = w;
         }
-        if (row_ok) {
+        if (a.tg_partial) {
+          // rows beyond the sequence end contribute nothing (their bins may hold garbage-free zeros,
+          // but Q rows are zero-filled by TMA anyway)
+          const uint4 pk4 = make_uint4(pack_bf16x2(w8[0], w8[1]), pack_bf16x2(w8[2], w8[3]),
+                                       pack_bf16x2(w8[4], w8[5]), pack_bf16x2(w8[6], w8[7]));
+          *reinterpret_cast<uint4*>(smem + SM_A + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = pk4;
+          // bias partial: sum over the 32 rows of this warp, one value per id
+          float* bs = reinterpret_cast<float*>(smem + SM_BS) + (warp & 3) * 64 + c0;
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            float v = row_ok ? w8[x] : 0.f;
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (lane == 0) bs[x] = v;
+          }
+        } else if (row_ok) {
           float* dst = a.dallrel + srow * R + c0;
           if ((R & 3) == 0 && c0 + 8 <= R) {
             *reinterpret_cast<float4*>(dst) = make_float4(w8[0], w8[1], w8[2], w8[3]);
@@ -544,6 +575,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                      : "memory");
       }
       tmem_wait_st();
+      fence_proxy_async_smem();   // the dallrel^T tile was written through the generic proxy
       tc_fence_before_sync();
       mbar_arrive(&bars->dar_full);
     }
@@ -551,6 +583,30 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_wait_warp(&bars->dq_full, 0);
     if (tid == 0) TRACE(1, 7);
     tc_fence_after_sync();
+    if (rpad && a.tg_partial) {
+      const int64_t pidx = ((int64_t)(b * gridDim.x + blockIdx.x) * a.H + h);
+      if (bidx == 0) {   // warp-uniform: four warps, lanes with (lane % 32) < 16 hold the 64 id rows
+        const int pid = (warp & 3) * 16 + lane;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(tmem + T_DE + lane_sel + hh * 32, v);
+          tmem_wait_ld();
+          if (lane < 16 && pid < R) {
+            float4* dst = reinterpret_cast<float4*>(a.tg_partial + (pidx * R + pid) * 64 + hh * 32);
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              dst[x] = make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
+                                   __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
+          }
+        }
+      }
+      named_bar_sync(1, NALL);   // bias sums of all four row quadrants are in smem
+      if (tid < R) {
+        const float* bs = reinterpret_cast<const float*>(smem + SM_BS);
+        a.tg_partial_bias[pidx * R + tid] = (bs[tid] + bs[64 + tid]) + (bs[128 + tid] + bs[192 + tid]);
+      }
+    }
     constexpr int WO = 64 / NB;   // output columns per thread
     uint32_t dq_raw[WO];
     tmem_ldN(tmem + T_DQ + lane_sel + bidx * WO, dq_raw);

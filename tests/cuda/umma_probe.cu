@@ -58,6 +58,13 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     tma_load_4d(k_s, &map_k, &bar_load, 0, a.row0_k, a.h, a.b);
     tma_load_4d(v_s, &map_v, &bar_load, 0, a.row0_k, a.h, a.b);
   }
+  if (a.mode == 5) {
+    uint32_t z[32];
+    for (int c = 0; c < 32; ++c) z[c] = 0x7fc00000u;  // NaN marker: untouched lanes stay NaN
+    tmem_st32(t_acc + lane_sel, z);
+    tmem_st32(t_acc + lane_sel + 32, z);
+    tmem_wait_st();
+  }
   // P (row = tid, 64 key columns)
   float prow[64];
   for (int c = 0; c < 64; ++c) prow[c] = a.p_host[tid * 64 + c];
@@ -113,6 +120,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
       for (int kk = 0; kk < 4; ++kk) {
         uint64_t da = make_smem_desc_sw128(smem_u32(p_s) + kk * 32, 16, 1024);
         uint64_t db = make_smem_desc_sw128(smem_u32(v_s) + kk * a.v_kstep, a.v_lbo, a.v_sbo);
+        umma_ss(t_acc, da, db, idesc, kk > 0);
+      }
+    } else if (a.mode == 5) {
+      // M = 64 accumulator layout probe: D[64 x 64] = Q[0:64] . K^T
+      const uint32_t idesc = make_idesc_bf16(64, 64, 0, 0);
+      for (int kk = 0; kk < 4; ++kk) {
+        uint64_t da = make_smem_desc_sw128(smem_u32(q_s) + kk * 32, 16, 1024);
+        uint64_t db = make_smem_desc_sw128(smem_u32(k_s) + kk * 32, 16, 1024);
         umma_ss(t_acc, da, db, idesc, kk > 0);
       }
     } else if (a.mode == 4) {
@@ -213,6 +228,29 @@ int main() {
     }
     double err = run(a, "T4");
     printf("T4 O=P.V (A MN-major smem, 2 M-atoms: lbo=%u sbo=%u): max abs err %.3e -> %s\n", en.lbo, en.sbo, err, err < 1e-3 ? "PASS" : "FAIL");
+  }
+  {
+    ProbeArgs a{}; a.mode = 5; a.row0_q = 64; a.row0_k = 130;
+    std::vector<float> r64(64 * 64);
+    for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) {
+      double s2 = 0; for (int c = 0; c < D; ++c) s2 += (double)at(q, a.row0_q + i, c) * at(k, a.row0_k + j, c);
+      r64[i * 64 + j] = (float)s2;
+    }
+    std::fill(ref.begin(), ref.end(), 0.f);
+    run(a, "T5");
+    // which TMEM lane holds row i?
+    int lane_of[64]; bool ok5 = true;
+    for (int i = 0; i < 64; ++i) {
+      lane_of[i] = -1;
+      for (int l = 0; l < 128; ++l) {
+        double e = 0; for (int j = 0; j < 64; ++j) { double d = fabs((double)out[l * 64 + j] - r64[i * 64 + j]); if (!(d <= e)) e = (d != d) ? 1e30 : d; }
+        if (e < 1e-3) { lane_of[i] = l; break; }
+      }
+      if (lane_of[i] < 0) ok5 = false;
+    }
+    printf("T5 M=64 accumulator layout: row->lane:");
+    for (int i = 0; i < 64; i += 8) printf(" %d->%d", i, lane_of[i]);
+    printf(" ... 15->%d 16->%d 31->%d 32->%d 63->%d -> %s\n", lane_of[15], lane_of[16], lane_of[31], lane_of[32], lane_of[63], ok5 ? "PASS" : "FAIL");
   }
   printf("probe done\n");
   return 0;
