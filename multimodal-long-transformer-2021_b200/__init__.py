@@ -13,4 +13,4 @@ plumbing).  There is no CPU fallback: importing ``ops`` without the built
 from . import feature_utils  # noqa: F401
 from . import synthetic  # noqa: F401
 
-__all__ = ['feature_utils', 'synthetic']
+__all__ = ['feature_utils', 'synthetic', 'sharding']

@@ -264,3 +264,8 @@ class CompactSideInputs:
   global_example_ids: torch.Tensor
   sentence_ids: torch.Tensor
   relative_pos_max_distance: int
+
+  def slice(self, sl):
+    """Batch slice (micro-batching in the training step)."""
+    return CompactSideInputs(self.long_example_ids[sl], self.global_example_ids[sl],
+                             self.sentence_ids[sl], self.relative_pos_max_distance)

@@ -240,6 +240,10 @@ class DenseCompactSideInputs:
     self.num_patch_per_row = num_patch_per_row
     self.num_core_layers = num_core_layers
 
+  def slice(self, sl):
+    return DenseCompactSideInputs(self.q_example_ids[sl], self.k_example_ids[sl], self.max_distance,
+                                  self.num_patch_per_row, self.num_core_layers)
+
 
 class _DenseCfg:
 
