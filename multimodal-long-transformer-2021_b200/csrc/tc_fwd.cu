@@ -1,24 +1,32 @@
 // tcgen05 forward kernel: one 128-row query tile per CTA, joint online softmax over up to two
 // key segments (band / dense), relative-position scores and masks fused into the score tile.
 //
-// Roles (192 threads, 2 CTAs per SM, 256 TMEM columns each):
-//   warps 0-3  softmax / epilogue: thread t owns query row t == TMEM lane t.  Reads S from TMEM,
-//              adds the relative score (gather from a per-row table in smem), applies masks,
-//              online softmax in registers, writes P (bf16) back into TMEM, accumulates O in
-//              registers from the per-chunk P.V results.
-//   warp 4     TMA producer: Q tile, relative-embedding tile, then K/V chunks through a 3-stage
-//              mbarrier ring (SWIZZLE_128B tiles, out-of-range rows zero-filled by TMA).
-//   warp 5     MMA issuer (one elected lane): S_c = Q.K_c^T (SS), O_c = P_c.V_c (TS: P from TMEM,
-//              V MN-major), allrel = Q.E^T.  S is double-buffered so S_{c+1} runs under softmax_c.
+// Roles (256 threads, 2 CTAs per SM, 256 TMEM columns each):
+//   warps 0-3  softmax: thread t owns query row t == TMEM lane t.  The loop is bound by the MUFU
+//              (ex2) rate of the SM (16 / clk, measured by tests/cuda/tmem_bw.cu), so everything
+//              else is kept off these warps: per 32-key group they execute
+//                pass 1   row maximum of the raw Q.K^T accumulator          (0.5 instr / element)
+//                pass 2   p = ex2(fma(x, scale*log2e, c_row)), sum, pack    (3.5 instr / element)
+//              with c_row = (rel + mask)*log2e - max*log2e folded per row; the group's evaluation
+//              form comes ready-made from the planner warp (tc_plan.cuh).
+//   warp 4     TMA producer: Q tile, relative-embedding tile, K/V chunks through a 3-stage ring.
+//   warp 5     MMA issuer (one elected lane): S_c = Q.K_c^T (SS), O += P_c.V_c (TS: P from TMEM,
+//              V MN-major), allrel = Q.E^T.  S is double-buffered: S_{c+1} runs under softmax_c.
+//   warp 6     planner: classifies the (quadrant, group) pairs of each chunk a few chunks ahead.
+//   warp 7     idle (completes the warpgroup).
 //
-// TMEM map (columns): [0,64) S0/P0, [64,128) S1/P1 (also allrel before chunk 1), [128,192) O0,
-// [192,256) O1.
+// O stays in TMEM for the whole tile and is accumulated by the tensor core (FlashAttention-4
+// style lazy rescaling): the running maximum used for the exponentials only moves when the true
+// maximum outgrows it by more than 2^RESCALE_LOG2, in which case the owning warp rescales its O
+// rows in place.  The true maximum is tracked separately and published in the row statistics.
+//
+// TMEM map (columns): [0,64) S0/P0, [64,128) S1/P1, [128,192) O, [192,256) allrel.
 #include "tc_api.cuh"
 
 #include "mlt_common.cuh"
 #include "profile.cuh"
+#include "tc_plan.cuh"
 #include "tc_ptx.cuh"
-#include "tc_rowscore.cuh"
 
 namespace mlt {
 namespace {
@@ -28,15 +36,20 @@ using namespace ptx;
 constexpr int TM = 128;       // query rows per tile
 constexpr int TN = 64;        // keys per chunk
 constexpr int NST = 3;        // K/V ring stages
-constexpr int NTHREADS = 256;   // warpgroup 0: softmax; warpgroup 1: TMA, MMA, 2 idle warps
+constexpr int NPL = 4;        // plan ring slots
+constexpr int NTHREADS = 256;
 constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t T_O = 128, T_REL = 192;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float M_INIT = -1e30f;         // "no live key so far"
+constexpr float RESCALE_LOG2 = 32.f;     // lazy-rescale threshold (log2 units)
 
 constexpr int SM_Q = 0;                          // 16 KB
 constexpr int SM_E = SM_Q + TM * 128;            // 8 KB  (<= 64 ids x 128 B)
 constexpr int SM_KV = SM_E + 64 * 128;           // NST x (K 8 KB + V 8 KB)
-constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64][128] fp32 = 32 KB
-constexpr int SM_BAR = SM_REL + 64 * TM * 4;
+constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64 slots][128 rows] fp32 = 32 KB
+constexpr int SM_PLAN = SM_REL + 64 * TM * 4;        // NPL x ChunkPlan
+constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
 constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;        // slack for 1024-B alignment
 
@@ -61,11 +74,13 @@ struct TcFwdParams {
 };
 
 struct Bars {
-  uint64_t q_full, rel_full, rel_done;
+  uint64_t q_full, rel_full;
   uint64_t kv_full[NST], kv_empty[NST];
   uint64_t s_full[2], p_full[2], o_full[2];
+  uint64_t pl_full[NPL], pl_empty[NPL];
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 
 struct SegRange {
   int kb, ke, n;  // keys [kb, ke), n chunks of TN
@@ -84,43 +99,125 @@ __device__ __forceinline__ SegRange seg_range(const KeySeg& sg, int i0) {
   return r;
 }
 
-__device__ __forceinline__ rowscore::SegCtx make_seg_ctx(const KeySeg& sg, const SegRange& r, int R, int pd,
-                                                        bool perm) {
-  rowscore::SegCtx sc;
-  sc.sg = &sg;
-  sc.kb = r.kb;
+__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+  plan::PSeg s;
+  s.c_begin = r.kb;
+  s.c_end = r.ke;
+  s.c_len = sg.len;
+  s.band = sg.band != 0;
+  s.radius = sg.radius;
+  s.mask_rule = sg.side.mask_rule;
+  s.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  s.D = sg.side.max_distance;
+  s.R = R;
+  s.diag_ok = perm && pd == s.D;
+  s.rows_are_keys = false;
+  s.c_eid = sg.side.k_eid;
+  s.c_eid_stride = sg.side.k_len;
+  s.col_sent = (s.id_rule == IDR_CROSS_KSENT);
+  s.c_sent = s.col_sent ? sg.side.sent : nullptr;
+  s.c_sent_stride = sg.side.sent_len;
+  return s;
+}
+
+// ---- softmax-side contexts -------------------------------------------------------------------
+struct SegC {          // warp-uniform
+  const Side* sd;
+  int ke;              // end of the live key range
+  bool band;
+  int radius;
+  int mask_rule, id_rule;
+  int D, R, pd;
+  bool perm;
+};
+struct RowC {          // per thread and segment
+  int q_e, q_sent;
+  float relP, relN, relX, relX1;
+};
+
+__device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+  SegC sc;
+  sc.sd = &sg.side;
   sc.ke = r.ke;
-  sc.R = R;
-  sc.D = sg.side.max_distance;
-  sc.pd = pd;
-  sc.perm = perm;
   sc.band = sg.band != 0;
   sc.radius = sg.radius;
   sc.mask_rule = sg.side.mask_rule;
   sc.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  sc.D = sg.side.max_distance;
+  sc.R = R;
+  sc.pd = pd;
+  sc.perm = perm;
   return sc;
+}
+
+__device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i, bool row_ok) {
+  rc.q_e = 0;
+  rc.q_sent = -1;
+  if (row_ok && sc.mask_rule == MR_EXAMPLE_ID) rc.q_e = __ldg(sc.sd->q_eid + (int64_t)b * sc.sd->q_len + i);
+  if (row_ok && sc.id_rule == IDR_CROSS_QSENT) rc.q_sent = __ldg(sc.sd->sent + (int64_t)b * sc.sd->sent_len + i);
+}
+__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, int row) {
+  auto rel_at = [&](int id) -> float {
+    return (id >= 0 && id < sc.R) ? rel_s[plan::slot_of_id(id, sc.pd, sc.perm) * TM + row] : 0.f;
+  };
+  const bool on = sc.id_rule != IDR_NONE;
+  rc.relP = on ? rel_at(sc.D) : 0.f;
+  rc.relN = on ? rel_at(2 * sc.D) : 0.f;
+  rc.relX = on ? rel_at(2 * sc.D + 1) : 0.f;
+  rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
+}
+
+// Generic per-element score (any rule).  Dead pairs return -inf.
+__device__ __forceinline__ float score_generic(float x, const SegC& sc, const RowC& rc, int b, int i, int row,
+                                               bool row_ok, int j, int ke_j, int ks_j, const float* rel_s,
+                                               float scale, float neg) {
+  const Side& sd = *sc.sd;
+  const int off = j - i;
+  const bool live = j < sc.ke && (!sc.band || (off <= sc.radius && off >= -sc.radius));
+  if (!live) return -INFINITY;
+  const int col = sc.band ? off + sc.radius : j;
+  bool ok = true;
+  int id = -1;
+  switch (sc.mask_rule) {
+    case MR_EXPLICIT: ok = row_ok ? (__ldg(sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) != 0) : true; break;
+    case MR_EXAMPLE_ID: ok = (rc.q_e == ke_j); break;
+    default: break;
+  }
+  switch (sc.id_rule) {
+    case IDR_EXPLICIT: id = row_ok ? __ldg(sd.ids + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) : -1; break;
+    case IDR_1D: id = rel_id_1d(off, sc.D); break;
+    case IDR_CROSS_QSENT: id = 2 * sc.D + 1 + (rc.q_sent == j ? 1 : 0); break;
+    case IDR_CROSS_KSENT: id = 2 * sc.D + 1 + (ks_j == i ? 1 : 0); break;
+    case IDR_2D: id = rel_id_2d(i, j, sd.npr, sd.core, sc.D); break;
+    default: break;
+  }
+  float rel = 0.f;
+  if (id >= 0 && id < sc.R) rel = rel_s[plan::slot_of_id(id, sc.pd, sc.perm) * TM + row];
+  float v = fmaf(x, scale, rel);
+  if (!ok) v += neg;
+  return v;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k0,
               const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_k1,
               const __grid_constant__ CUtensorMap map_v1, const __grid_constant__ CUtensorMap map_e,
-              const TcFwdParams p) {
+              const __grid_constant__ TcFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
   // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + SM_REL);
+  plan::ChunkPlan* plans = reinterpret_cast<plan::ChunkPlan*>(smem + SM_PLAN);
   const FwdArgs& a = p.a;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TM;
   const int R = a.rows.R, rpad = p.rpad;
 
   if (tid == 0) {
     mbar_init(&bars->q_full, 1);
     mbar_init(&bars->rel_full, 1);
-    mbar_init(&bars->rel_done, 128);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars->kv_full[s], 1);
       mbar_init(&bars->kv_empty[s], 1);
@@ -129,6 +226,10 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_init(&bars->s_full[s], 1);
       mbar_init(&bars->p_full[s], 128);
       mbar_init(&bars->o_full[s], 1);
+    }
+    for (int s = 0; s < NPL; ++s) {
+      mbar_init(&bars->pl_full[s], 1);
+      mbar_init(&bars->pl_empty[s], 1);
     }
     fence_barrier_init();
   }
@@ -142,16 +243,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   SegRange r1{0, 0, 0};
   if (a.nseg > 1) r1 = seg_range(a.seg[1], i0);
   const int nchunks = r0.n + r1.n;
+  const int pd = a.seg[0].side.max_distance;
+  const bool perm = (2 * pd + 1 <= R);
 
-  if (warp >= 4) {
-    // warpgroup 1 (TMA, MMA, 2 idle warps that only complete the warpgroup) gives registers away
-    setmaxnreg_dec<40>();
-  }
-  if (warp >= 6) {
-  } else if (warp == 4) {
+  if (warp == 4) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      TRACE(1, 0);
       prefetch_tensormap(&map_q);
       prefetch_tensormap(&map_k0);
       prefetch_tensormap(&map_v0);
@@ -164,7 +261,6 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const bool first = c < r0.n;
         const int key0 = first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN;
         uint8_t* ks = smem + SM_KV + st * (2 * TN * 128);
-        TRACE(1, 2 + c);
         mbar_arrive_expect_tx(&bars->kv_full[st], 2 * TN * 128);
         tma_load_4d(ks, first ? &map_k0 : &map_k1, &bars->kv_full[st], 0, key0, h, b);
         tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
@@ -176,16 +272,14 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(TM, 64, 0, 1);
       const uint32_t q_addr = smem_u32(smem + SM_Q);
-      TRACE(2, 0);
       mbar_wait(&bars->q_full, 0);
-      TRACE(2, 1);
       tc_fence_after_sync();
       if (rpad) {
         const uint32_t idesc_r = make_idesc_bf16(TM, rpad, 0, 0);
         const uint32_t e_addr = smem_u32(smem + SM_E);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+          umma_ss(tmem + T_REL, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
                   make_smem_desc_sw128(e_addr + kk * 32, 16, 1024), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
       }
@@ -193,8 +287,6 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (c < nchunks) {
           const int st = c % NST;
           mbar_wait(&bars->kv_full[st], (c / NST) & 1);
-          TRACE(2, 2 + 4 * c);
-          if (c == 1 && rpad) mbar_wait(&bars->rel_done, 0);  // allrel aliases S1
           tc_fence_after_sync();
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
@@ -202,165 +294,270 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             umma_ss(tmem + (c & 1) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
                     make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
           umma_commit(&bars->s_full[c & 1]);
-          TRACE(2, 3 + 4 * c);
         }
         if (c >= 1) {
           const int pc = c - 1, st = pc % NST;
           mbar_wait(&bars->p_full[pc & 1], (pc >> 1) & 1);
-          TRACE(2, 4 + 4 * pc);
           tc_fence_after_sync();
+          mbar_arrive(&bars->pl_empty[pc % NPL]);   // every softmax thread is done with plan pc
           const uint32_t v_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128) + TN * 128);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + 128 + (pc & 1) * 64, tmem + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                    make_smem_desc_sw128(v_addr + kk * 2048, 16, 1024), idesc_o, kk > 0);
+            umma_ts(tmem + T_O, tmem + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                    make_smem_desc_sw128(v_addr + kk * 2048, 16, 1024), idesc_o, (pc > 0 || kk > 0));
           umma_commit(&bars->o_full[pc & 1]);
           umma_commit(&bars->kv_empty[st]);
         }
       }
     }
-  } else {
+  } else if (warp == 6) {
+    // ===================== planner =====================
+    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
+    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    // row-side sentence ranges (only the QSENT rule needs them; both segments share the array)
+    const Side* qs_side = nullptr;
+    if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
+    if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
+    const plan::RowSent rs = plan::row_sent_ranges(qs_side ? qs_side->sent : nullptr,
+                                                   qs_side ? qs_side->sent_len : 0, b, i0, a.rows.len, lane);
+    // one call per segment (inlined twice: the segment description stays in registers)
+    auto run = [&](const plan::PSeg& ps, int c_begin, int c_end, int kb) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int sl = c % NPL;
+        if (c >= NPL) mbar_wait_warp(&bars->pl_empty[sl], ((c / NPL) & 1) ^ 1);
+        plan::plan_chunk(ps, b, kb + (c - c_begin) * TN, i0, rs, plans + sl, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->pl_full[sl]);
+      }
+    };
+    run(ps0, 0, r0.n, r0.kb);
+    if (a.nseg > 1) run(ps1, r0.n, nchunks, r1.kb);
+  } else if (warp < 4) {
     // ===================== softmax / epilogue (warps 0-3) =====================
-    setmaxnreg_inc<216>();
-    using namespace rowscore;
-    const int row = tid, lane = tid & 31;
+    const int row = tid;
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
-    const int wrow0 = i0 + warp * 32;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const int pd = a.seg[0].side.max_distance;
-    const bool perm = (2 * pd + 1 <= R);
-    if (tid == 0) TRACE(0, 0);
-    // ---- early global loads: row scalars, bias lanes, first chunk's key lanes ----
-    SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
-    SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
-    RowCtx rc0, rc1;
-    rc0.i = rc1.i = i;
-    rc0.row = rc1.row = row;
-    rc0.row_ok = rc1.row_ok = row_ok;
-    init_row_loads(rc0, sc0, b);
-    init_row_loads(rc1, sc1, b);
-    auto chunk_key0 = [&](int c) { return c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN; };
-    GroupLanes gl0{0, -1}, gl1{0, -1};
-    if (nchunks > 0) {
-      const SegCtx& s = 0 < r0.n ? sc0 : sc1;
-      gl0 = load_group_lanes(s, b, chunk_key0(0), lane);
-      gl1 = load_group_lanes(s, b, chunk_key0(0) + 32, lane);
-    }
-    float bias_l0 = 0.f, bias_l1 = 0.f;  // lane l holds bias[l], bias[32 + l]
+    const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
+    const SegC sc1 = make_segc(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    RowC rc0, rc1;
+    row_loads(rc0, sc0, b, i, row_ok);
+    row_loads(rc1, sc1, b, i, row_ok);
     if (rpad) {
+      // allrel (+ bias) * scale -> slot-ordered per-row table in shared memory
+      float bias_l0 = 0.f, bias_l1 = 0.f;  // lane l holds bias[l], bias[32 + l]
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
       if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
       if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
       mbar_wait_warp(&bars->rel_full, 0);
-      if (tid == 0) TRACE(0, 1);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int c0 = 0; c0 < rpad; c0 += 16) {
-        {
-          uint32_t v[16];
-          tmem_ld16(tmem + 64 + lane_sel + c0, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const int pid = c0 + x;
-            const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
-            if (pid < R) rel_s[slot_of_id(pid, pd, perm) * TM + row] = (__uint_as_float(v[x]) + bv) * a.scale;
-          }
-        }
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&bars->rel_done);
-    }
-    if (tid == 0) TRACE(0, 2);
-    init_row(rc0, sc0, b, rel_s);
-    init_row(rc1, sc1, b, rel_s);
-
-    float m = -1e30f, l = 0.f, alpha_prev = 0.f;
-    float o[64];
-#pragma unroll
-    for (int x = 0; x < 64; ++x) o[x] = 0.f;
-
-    auto add_o = [&](int pc) {   // o = o * alpha_prev + O_pc
-      mbar_wait_warp(&bars->o_full[pc & 1], (pc >> 1) & 1);
-      if (tid == 0) TRACE(0, 7 + 4 * pc);
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld32(tmem + 128 + (pc & 1) * 64 + lane_sel + hh * 32, v);
+        uint32_t v[16];
+        tmem_ld16(tmem + T_REL + lane_sel + c0, v);
         tmem_wait_ld();
-        if (hh == 0) {
 #pragma unroll
-          for (int x = 0; x < 32; ++x) o[x] = fmaf(o[x], alpha_prev, __uint_as_float(v[x]));
-        } else {
-#pragma unroll
-          for (int x = 0; x < 32; ++x) o[32 + x] = fmaf(o[32 + x], alpha_prev, __uint_as_float(v[x]));
+        for (int x = 0; x < 16; ++x) {
+          const int pid = c0 + x;
+          const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
+          if (pid < R) rel_s[plan::slot_of_id(pid, pd, perm) * TM + row] = (__uint_as_float(v[x]) + bv) * a.scale;
         }
       }
-    };
+    }
+    row_consts(rc0, sc0, rel_s, row);   // a thread only reads its own column of rel_s: no barrier
+    row_consts(rc1, sc1, rel_s, row);
+
+    const float scale2 = a.scale * LOG2E;
+    float m = M_INIT;        // maximum the exponentials are taken against (lags the true maximum)
+    float m_true = M_INIT;   // true running maximum
+    float l = 0.f;
     int c = 0;   // chunk counter over both segments
 #pragma unroll 1
     for (int sgi = 0; sgi < a.nseg; ++sgi) {
       // segment context copied once: no per-field selects inside the chunk loop
-      const SegCtx sc = sgi ? sc1 : sc0;
-      const RowCtx rc = sgi ? rc1 : rc0;
+      const SegC sc = sgi ? sc1 : sc0;
+      const RowC rc = sgi ? rc1 : rc0;
       const int seg_n = sgi ? r1.n : r0.n;
       const int seg_kb = sgi ? r1.kb : r0.kb;
+      const bool mre = sc.mask_rule == MR_EXAMPLE_ID;
 #pragma unroll 1
       for (int cc = 0; cc < seg_n; ++cc, ++c) {
         const int key0 = seg_kb + cc * TN;
         const uint32_t t_s = tmem + (c & 1) * 64 + lane_sel;
-        // prefetch the key-side lane scalars of the next chunk
-        GroupLanes nl0{0, -1}, nl1{0, -1};
-        if (cc + 1 < seg_n) {
-          nl0 = load_group_lanes(sc, b, key0 + TN, lane);
-          nl1 = load_group_lanes(sc, b, key0 + TN + 32, lane);
-        } else if (sgi == 0 && a.nseg > 1 && r1.n > 0) {
-          nl0 = load_group_lanes(sc1, b, r1.kb, lane);
-          nl1 = load_group_lanes(sc1, b, r1.kb + 32, lane);
-        }
-        if (tid == 0) TRACE(0, 4 + 4 * c);
+        const plan::ChunkPlan* cp = plans + (c % NPL);
+        mbar_wait_warp(&bars->pl_full[c % NPL], (c / NPL) & 1);
+        const uint2 pw = *reinterpret_cast<const uint2*>(&cp->w0[warp][0]);
+        const int2 pe = *reinterpret_cast<const int2*>(&cp->ce0[warp][0]);
         mbar_wait_warp(&bars->s_full[c & 1], (c >> 1) & 1);
-        if (tid == 0) TRACE(0, 5 + 4 * c);
         tc_fence_after_sync();
-        // ---- pass 1 (per 32-key group, ONE copy of the code): scores -> TMEM, running max ----
+        // ---- pass 1: row maximum; FAST groups leave the raw accumulator in place ----
         float mx = -INFINITY;
         uint32_t dead_mask = 0;
+        float mul0 = 0.f, mul1 = 0.f, add0 = 0.f, add1 = 0.f;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
-          const GroupLanes gl = g ? gl1 : gl0;
-          const int g0 = key0 + 32 * g;
-          const GroupPlan gp = classify(sc, rc, gl, wrow0, g0, lane, a.neg);
-          if (gp.mode == GM_DEAD) {
+          const uint32_t w0 = g ? pw.y : pw.x;
+          const int mode = (int)(w0 & 0xffu);
+          if (mode == plan::DEAD) {
             dead_mask |= 1u << g;
             continue;
           }
-          if (gp.mode == GM_GEN) score_group_generic_tmem(t_s + 32 * g, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
-          float t[32];
-          {
+          const int g0 = key0 + 32 * g;
+          const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
+          const bool masked = mre && !mask_pe && (rc.q_e != (g ? pe.y : pe.x));
+          const float mterm = masked ? a.neg : 0.f;
+          const int ccls = (int)((w0 >> 8) & 0xffu);
+          const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+          float gmul, gadd, gmax;
+          if (mode == plan::FAST) {
+            // every row of the warp masked here and already holding a real maximum: p == 0 exactly
+            if (mre && __all_sync(0xffffffffu, masked && m > -1e8f)) {
+              dead_mask |= 1u << g;
+              continue;
+            }
             uint32_t v[32];
             tmem_ld32(t_s + 32 * g, v);
             tmem_wait_ld();
+            float r4[4];
 #pragma unroll
-            for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
+            for (int y = 0; y < 4; ++y)
+              r4[y] = fmaxf(fmaxf(__uint_as_float(v[8 * y]), __uint_as_float(v[8 * y + 1])), __uint_as_float(v[8 * y + 2]));
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              r4[y] = fmaxf(fmaxf(r4[y], __uint_as_float(v[8 * y + 3])), __uint_as_float(v[8 * y + 4]));
+              r4[y] = fmaxf(fmaxf(r4[y], __uint_as_float(v[8 * y + 5])), __uint_as_float(v[8 * y + 6]));
+              r4[y] = fmaxf(r4[y], __uint_as_float(v[8 * y + 7]));
+            }
+            const float mraw = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
+            const float cadd = relc + mterm;
+            // a masked score is cadd itself: |x * scale| < 32 is absorbed by -1e9 in fp32
+            gmax = masked ? cadd : fmaf(mraw, a.scale, cadd);
+            gmul = masked ? 0.f : scale2;
+            gadd = cadd * LOG2E;
+          } else {
+            if (mode == plan::GEN) {
+              // real loop, TMEM as dynamically indexed scratch: one copy of the generic code
+#pragma unroll 1
+              for (int jj = 0; jj < 32; ++jj) {
+                const uint32_t raw = tmem_ld1(t_s + 32 * g + jj);
+                tmem_wait_ld();
+                const float tv = score_generic(__uint_as_float(raw), sc, rc, b, i, row, row_ok, g0 + jj,
+                                               cp->ce[32 * g + jj], cp->cs[32 * g + jj], rel_s, a.scale, a.neg);
+                __syncwarp();   // score_generic diverges per row; tcgen05.st needs the converged warp
+                tmem_st1(t_s + 32 * g + jj, __float_as_uint(tv));
+              }
+              tmem_wait_st();
+            }
+            float t[32];
+            {
+              uint32_t v[32];
+              tmem_ld32(t_s + 32 * g, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int x = 0; x < 32; ++x) t[x] = __uint_as_float(v[x]);
+            }
+            switch (mode) {
+              case plan::EDGE: {
+                // live columns of this row form one interval [jlo, jhi)
+                const int d0 = g0 - i;
+                int jlo = 0, jhi = min(32, sc.ke - g0);
+                if (sc.band) {
+                  jlo = max(jlo, -sc.radius - d0);
+                  jhi = min(jhi, sc.radius - d0 + 1);
+                }
+                const unsigned span = (unsigned)max(jhi - jlo, 0);
+                const float cadd = relc + mterm;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const float v = fmaf(t[jj], a.scale, cadd);
+                  t[jj] = ((unsigned)(jj - jlo) < span) ? v : -INFINITY;
+                }
+                break;
+              }
+              case plan::DIAG: {
+                const int d0 = g0 - i + sc.D;  // slot = clamp(off, -D, D) + D = clamp(d0 + jj, 0, 2D)
+                const float* base = rel_s + row;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const int s = min(max(d0 + jj, 0), 2 * sc.D);
+                  t[jj] = fmaf(t[jj], a.scale, base[s * TM] + mterm);
+                }
+                break;
+              }
+              case plan::QS: {
+                const int d0 = rc.q_sent - g0;  // special column index within the group
+                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) t[jj] = fmaf(t[jj], a.scale, d0 == jj ? c1 : c0);
+                break;
+              }
+              case plan::KS: {
+                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) t[jj] = fmaf(t[jj], a.scale, cp->cs[32 * g + jj] == i ? c1 : c0);
+                break;
+              }
+              default:
+                break;  // GEN: evaluated above
+            }
+            if (mask_pe) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) t[jj] += (cp->ce[32 * g + jj] == rc.q_e) ? 0.f : a.neg;
+            }
+            float r4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int x = 0; x < 32; x += 8) {
+#pragma unroll
+              for (int y = 0; y < 4; ++y) r4[y] = fmaxf(fmaxf(r4[y], t[x + 2 * y]), t[x + 2 * y + 1]);
+            }
+            gmax = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
+            if (mode != plan::GEN) {
+              uint32_t v[32];
+#pragma unroll
+              for (int x = 0; x < 32; ++x) v[x] = __float_as_uint(t[x]);
+              tmem_st32(t_s + 32 * g, v);
+            }
+            gmul = LOG2E;
+            gadd = 0.f;
           }
-          score_group<0>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg);
-#pragma unroll
-          for (int x = 0; x < 32; ++x) mx = fmaxf(mx, t[x]);
-          if (gp.mode != GM_GEN) {
-            uint32_t v[32];
-#pragma unroll
-            for (int x = 0; x < 32; ++x) v[x] = __float_as_uint(t[x]);
-            tmem_st32(t_s + 32 * g, v);
+          mx = fmaxf(mx, gmax);
+          if (g == 0) {
+            mul0 = gmul;
+            add0 = gadd;
+          } else {
+            mul1 = gmul;
+            add1 = gadd;
           }
         }
         tmem_wait_st();
-        const float m_new = fmaxf(m, mx);
-        const float alpha = ex2((m - m_new) * LOG2E);
-        const float mb = m_new * LOG2E;
-        // ---- pass 2: p = exp2(t * log2e - mb), row sum, P (bf16) back into TMEM ----
-        float lsum = 0.f;
+        // ---- running maximum with lazy rescaling of O (in TMEM) ----
+        m_true = fmaxf(m_true, mx);
+        const bool fresh = (m == M_INIT);   // nothing live so far: O row == 0 and l == 0
+        const bool grow = !fresh && (m_true - m) * LOG2E > RESCALE_LOG2;
+        if (fresh) m = m_true;
+        if (__any_sync(0xffffffffu, grow)) {
+          // P.V of the previous chunk must have landed before O is touched.  (o_full alternates
+          // between two barriers: P.V of chunk c-3 is known complete once S_c has been seen, so
+          // the barrier of chunk c-1 is at most one phase away and the parity wait is exact.)
+          mbar_wait_warp(&bars->o_full[(c - 1) & 1], ((c - 1) >> 1) & 1);
+          tc_fence_after_sync();
+          const float f = grow ? ex2((m - m_true) * LOG2E) : 1.f;
+          if (grow) m = m_true;
+          l *= f;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(tmem + T_O + lane_sel + hh * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 32; ++x) v[x] = __float_as_uint(__uint_as_float(v[x]) * f);
+            tmem_st32(tmem + T_O + lane_sel + hh * 32, v);
+          }
+          tmem_wait_st();
+        }
+        const float mb = m * LOG2E;
+        // ---- pass 2: p = exp2(x * mul + add - mb), row sum, P (bf16) back into TMEM ----
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           uint32_t pk[16];
@@ -368,15 +565,23 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
             for (int x = 0; x < 16; ++x) pk[x] = 0u;
           } else {
+            const float gmul = g ? mul1 : mul0;
+            const float gsub = (g ? add1 : add0) - mb;
             uint32_t v[32];
             tmem_ld32(t_s + 32 * g, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int x = 0; x < 16; ++x) {
-              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), LOG2E, -mb));
-              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), LOG2E, -mb));
-              lsum += p0 + p1;
+            for (int x = 0; x < 16; x += 2) {
+              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
+              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
+              const float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, gsub));
+              const float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, gsub));
+              ls0 += p0;
+              ls1 += p1;
+              ls2 += p2;
+              ls3 += p3;
               pk[x] = pack_bf16x2(p0, p1);
+              pk[x + 1] = pack_bf16x2(p2, p3);
             }
           }
           // P of keys [32g, 32g+32) -> packed columns [32g, 32g+16): stays inside this group's own
@@ -386,33 +591,39 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[c & 1]);
-        if (tid == 0) TRACE(0, 6 + 4 * c);
-        l = l * alpha + lsum;
-        m = m_new;
-        gl0 = nl0;
-        gl1 = nl1;
-        if (c >= 1) add_o(c - 1);   // uses alpha_prev = alpha of chunk c-1
-        alpha_prev = alpha;
+        l += (ls0 + ls1) + (ls2 + ls3);
       }
     }
-    if (nchunks >= 1) add_o(nchunks - 1);
-    if (row_ok) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.out, b, i, h);
+    // ---- epilogue: O / l ----
+    if (nchunks >= 1) {
+      mbar_wait_warp(&bars->o_full[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
+      tc_fence_after_sync();
+    }
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.out, b, i, h);
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      tmem_ld32(tmem + T_O + lane_sel + hh * 32, v);
+      tmem_wait_ld();
+      if (row_ok) {
 #pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        uint4 w;
-        w.x = pack_bf16x2(o[8 * x + 0] * inv, o[8 * x + 1] * inv);
-        w.y = pack_bf16x2(o[8 * x + 2] * inv, o[8 * x + 3] * inv);
-        w.z = pack_bf16x2(o[8 * x + 4] * inv, o[8 * x + 5] * inv);
-        w.w = pack_bf16x2(o[8 * x + 6] * inv, o[8 * x + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + 8 * x) = w;
+        for (int x = 0; x < 4; ++x) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * x + 0]) * inv, __uint_as_float(v[8 * x + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(v[8 * x + 2]) * inv, __uint_as_float(v[8 * x + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(v[8 * x + 4]) * inv, __uint_as_float(v[8 * x + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(v[8 * x + 6]) * inv, __uint_as_float(v[8 * x + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * x) = w;
+        }
       }
+    }
+    if (row_ok) {
+      // statistics against the TRUE maximum: (m_true, sum exp(t - m_true))
       float2* st = reinterpret_cast<float2*>(a.stats) + ((int64_t)(b * a.H + h) * a.rows.len + i);
-      *st = make_float2(m, l);
+      *st = make_float2(m_true, l * ex2((m - m_true) * LOG2E));
     }
   }
-  if (tid == 0) TRACE(0, 3);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem);

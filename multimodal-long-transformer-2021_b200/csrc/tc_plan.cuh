@@ -1,0 +1,183 @@
+// Chunk planner for the tcgen05 kernels.
+//
+// A score tile is 128 rows x 64 columns; its elementwise work is done per (32-row warp quadrant,
+// 32-column group).  For every such pair a *planner warp* (one spare warp of the CTA, running a few
+// chunks ahead) decides ONCE which evaluation form applies and publishes the decision in a small
+// shared-memory ring, so that the elementwise warps -- the critical resource of these kernels, they
+// are bound by the MUFU (ex2) rate -- spend no instructions on classification:
+//   DEAD  every pair outside the band / beyond the column range          -> no work, P = 0
+//   FAST  all live, mask uniform over the columns, relative term constant per row
+//         -> p = ex2(fma(x, scale*log2e, c_row)): ONE FMA per element, nothing written back
+//   EDGE  as FAST but the band edge / sequence end cuts the group
+//   DIAG  1-D rule near the diagonal: gather from the slot-ordered row table
+//   QS    cross block that contains the sentence column of some row      (+ select)
+//   KS    cross block that contains columns belonging to some row's sentence (+ select)
+//   GEN   anything else (explicit int32 side inputs, 2-D ids, ...)
+// "Row" = the index the thread owns (TMEM lane), "column" = the index that varies inside a chunk.
+// In the forward and the query-centric backward rows are queries and columns are keys; in the
+// key-centric backward rows are keys and columns are queries (the planner is told which).
+// The ring slot also carries the per-column scalars (example id, sentence id) of the chunk, read
+// by the rare per-element forms as warp-broadcast LDS.
+#pragma once
+
+#include "mlt_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mlt {
+namespace plan {
+
+enum Mode : int { DEAD = 0, FAST, EDGE, DIAG, QS, KS, GEN };
+// constant relative classes of a group (which per-row constant applies)
+enum CCls : int { C_NONE = 0, C_POS = 1, C_NEG = 2, C_CROSS = 3 };
+
+constexpr uint32_t F_MASK_PE = 1u << 16;   // example-id mask changes inside the group
+
+struct ChunkPlan {          // one ring slot (576 B)
+  uint32_t w0[4][2];        // [row quadrant][group]: mode | ccls << 8 | flags
+  int32_t ce0[4][2];        // example id shared by the group's columns (uniform-mask groups)
+  int32_t ce[64];           // column example ids
+  int32_t cs[64];           // column sentence ids (rule KSENT on query-rows / QSENT on key-rows)
+};
+
+__host__ __device__ __forceinline__ int slot_of_id(int id, int D, bool perm) {
+  if (!perm) return id;
+  if (id <= D) return D + id;
+  if (id <= 2 * D) return 2 * D - id;
+  return id;
+}
+
+// Warp-uniform description of one (row set, column segment) block for the planner.
+struct PSeg {
+  int c_begin, c_end;    // live column range of this tile inside the segment
+  int c_len;             // length of the column sequence (loads are clipped to it)
+  bool band;
+  int radius;
+  int mask_rule, id_rule;
+  int D, R;
+  bool diag_ok;          // the slot-ordered row table matches this segment's 1-D rule
+  bool rows_are_keys;    // key-centric pass: offset = row - column instead of column - row
+  const int32_t* c_eid;  // per-column example ids  [B, c_len] (or null)
+  const int32_t* c_sent; // per-column sentence ids [B, c_len] (or null)
+  int64_t c_eid_stride, c_sent_stride;
+  bool col_sent;         // sentence ids live on the column side (KS form); else on the row side (QS)
+};
+
+// Per-tile row-side sentence ranges (QS form): [rs_min[w], rs_max[w]] of quadrant w.
+struct RowSent {
+  int mn[4], mx[4];
+};
+
+// Whole warp.  col0 = first column of the chunk, row0 = first row of the tile.
+__device__ __forceinline__ void plan_chunk(const PSeg& s, int b, int col0, int row0, const RowSent& rs,
+                                           ChunkPlan* out, int lane) {
+  int e0 = 0, e1 = 0, s0 = -1, s1 = -1;
+  const int j0 = col0 + lane, j1 = col0 + 32 + lane;
+  if (s.mask_rule == MR_EXAMPLE_ID) {
+    if (j0 >= 0 && j0 < s.c_len) e0 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j0);
+    if (j1 >= 0 && j1 < s.c_len) e1 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j1);
+  }
+  if (s.col_sent) {
+    if (j0 >= 0 && j0 < s.c_len) s0 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j0);
+    if (j1 >= 0 && j1 < s.c_len) s1 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j1);
+  }
+  out->ce[lane] = e0;
+  out->ce[32 + lane] = e1;
+  out->cs[lane] = s0;
+  out->cs[32 + lane] = s1;
+  // group-uniform facts
+  const int f0 = __shfl_sync(0xffffffffu, e0, 0), f1 = __shfl_sync(0xffffffffu, e1, 0);
+  const bool uni0 = __all_sync(0xffffffffu, j0 >= s.c_end || e0 == f0);
+  const bool uni1 = __all_sync(0xffffffffu, j1 >= s.c_end || e1 == f1);
+  int smin0 = 0x7fffffff, smax0 = -1, smin1 = 0x7fffffff, smax1 = -1;
+  if (s.col_sent) {
+    smin0 = __reduce_min_sync(0xffffffffu, s0 < 0 ? 0x7fffffff : s0);
+    smax0 = __reduce_max_sync(0xffffffffu, s0);
+    smin1 = __reduce_min_sync(0xffffffffu, s1 < 0 ? 0x7fffffff : s1);
+    smax1 = __reduce_max_sync(0xffffffffu, s1);
+  }
+  if (lane < 8) {
+    const int w = lane >> 1, g = lane & 1;
+    const int a = row0 + 32 * w;          // first row of the quadrant
+    const int g0 = col0 + 32 * g;         // first column of the group
+    // offset = key - query
+    int o_min, o_max;
+    if (!s.rows_are_keys) {
+      o_min = g0 - (a + 31);
+      o_max = g0 + 31 - a;
+    } else {
+      o_min = a - (g0 + 31);
+      o_max = a + 31 - g0;
+    }
+    uint32_t mode, ccls = C_NONE, flags = 0;
+    const bool dead = g0 >= s.c_end || (s.band && (o_min > s.radius || o_max < -s.radius));
+    if (dead) {
+      mode = DEAD;
+    } else {
+      const bool all_live = (g0 + 31 < s.c_end) && (!s.band || (o_min >= -s.radius && o_max <= s.radius));
+      bool gen = false;
+      if (s.mask_rule == MR_EXPLICIT) gen = true;
+      if (s.mask_rule == MR_EXAMPLE_ID && !(g ? uni1 : uni0)) flags |= F_MASK_PE;
+      int rcls = 0;  // 0 const, 1 diag, 2 qs, 3 ks, 4 generic
+      switch (s.id_rule) {
+        case IDR_NONE:
+          break;
+        case IDR_1D:
+          if (!s.diag_ok) rcls = 4;
+          else if (o_min >= s.D) ccls = C_POS;
+          else if (o_max <= -s.D) ccls = C_NEG;
+          else rcls = 1;
+          break;
+        case IDR_CROSS_QSENT:
+        case IDR_CROSS_KSENT:
+          if (2 * s.D + 2 >= s.R) { rcls = 4; break; }
+          ccls = C_CROSS;
+          if (s.col_sent) {   // sentence id on the column side: does a column's sentence hit a row?
+            const int smin = g ? smin1 : smin0, smax = g ? smax1 : smax0;
+            if (!(smax < a || smin > a + 31)) rcls = 3;
+          } else {            // sentence id on the row side: does a row's sentence hit a column?
+            const int rmn = w == 0 ? rs.mn[0] : (w == 1 ? rs.mn[1] : (w == 2 ? rs.mn[2] : rs.mn[3]));
+            const int rmx = w == 0 ? rs.mx[0] : (w == 1 ? rs.mx[1] : (w == 2 ? rs.mx[2] : rs.mx[3]));
+            if (!(rmx < g0 || rmn > g0 + 31)) rcls = 2;
+          }
+          break;
+        default:
+          rcls = 4;
+      }
+      if (gen || rcls == 4) {
+        mode = GEN;
+        flags = 0;
+      } else if (rcls == 0) {
+        // FAST folds the mask into one per-row constant: a mask that changes inside the group
+        // takes the EDGE form (per-element post-pass)
+        mode = (all_live && !(flags & F_MASK_PE)) ? FAST : EDGE;
+      } else if (!all_live) {
+        mode = GEN;
+        flags = 0;
+      } else {
+        mode = rcls == 1 ? DIAG : (rcls == 2 ? QS : KS);
+      }
+    }
+#ifdef MLT_FORCE_GEN
+    if (mode != DEAD) { mode = GEN; flags = 0; }
+#endif
+    out->w0[w][g] = mode | (ccls << 8) | flags;
+    out->ce0[w][g] = g ? f1 : f0;
+  }
+}
+
+// Row-side sentence ranges of the tile (whole warp; rows beyond `len` are ignored).
+__device__ __forceinline__ RowSent row_sent_ranges(const int32_t* sent, int64_t stride, int b, int row0, int len,
+                                                   int lane) {
+  RowSent rs;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int i = row0 + 32 * w + lane;
+    const int v = (sent && i < len) ? __ldg(sent + (int64_t)b * stride + i) : -1;
+    rs.mn[w] = __reduce_min_sync(0xffffffffu, v < 0 ? 0x7fffffff : v);
+    rs.mx[w] = __reduce_max_sync(0xffffffffu, v);
+  }
+  return rs;
+}
+
+}  // namespace plan
+}  // namespace mlt
