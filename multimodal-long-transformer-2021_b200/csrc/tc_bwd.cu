@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "mlt_common.cuh"
+#include "tc_plan.cuh"
 #include "tc_ptx.cuh"
 #include "tc_rowscore.cuh"
 
@@ -119,7 +120,9 @@ constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64][128] f32
 constexpr int SM_BIN = SM_REL + 64 * TM * 4;         // 2 x [64][128] f32
 constexpr int SM_A = SM_BIN + 2 * 64 * TM * 4;      // dallrel^T tile, bf16, [128 rows][64 ids] SW128 (16 KB)
 constexpr int SM_BS = SM_A + TM * 128;              // bias partial sums [4 quadrants][64]
-constexpr int SM_BAR = SM_BS + 4 * 64 * 4;
+constexpr int SM_PLAN = SM_BS + 4 * 64 * 4;         // 4 x ChunkPlan
+constexpr int SM_META = SM_PLAN + 4 * (int)sizeof(plan::ChunkPlan);   // 64 x RelMeta
+constexpr int SM_BAR = SM_META + 64 * (int)sizeof(plan::RelMeta);
 constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
 // TMEM columns
 constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_REL = 320, T_DE = 384;
@@ -128,8 +131,10 @@ struct Bars {
   uint64_t q_full, rel_full;
   uint64_t kv_full[NST], kv_empty[NST];
   uint64_t sdp_full[2], ds_full[2], dq_full, dar_full;
+  uint64_t pl_full[4], pl_empty[4];
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 }  // namespace bq
 
 struct SegRange {
@@ -155,59 +160,130 @@ struct TcBwdQParams {
   float* allrel_ws;   // ws [B, H, lp, rw] (allrel * scale)
 };
 
-__device__ __forceinline__ rowscore::SegCtx make_seg_ctx(const KeySeg& sg, const SegRange& r, int R, int pd,
-                                                        bool perm) {
-  rowscore::SegCtx sc;
-  sc.sg = &sg;
-  sc.kb = r.kb;
+// ---- row-side contexts of the query-centric pass (rows = queries, columns = keys) -------------
+struct SegC {          // warp-uniform
+  const Side* sd;
+  int ke;              // end of the live key range
+  bool band;
+  int radius;
+  int mask_rule, id_rule;
+  int D, R, pd;
+  bool perm;
+};
+struct RowC {          // per thread and segment
+  int q_e, q_sent;
+  float relP, relN, relX, relX1;
+};
+
+__device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+  SegC sc;
+  sc.sd = &sg.side;
   sc.ke = r.ke;
-  sc.R = R;
-  sc.D = sg.side.max_distance;
-  sc.pd = pd;
-  sc.perm = perm;
   sc.band = sg.band != 0;
   sc.radius = sg.radius;
   sc.mask_rule = sg.side.mask_rule;
   sc.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  sc.D = sg.side.max_distance;
+  sc.R = R;
+  sc.pd = pd;
+  sc.perm = perm;
   return sc;
 }
 
-// GM_GEN groups of the query-centric backward: real loop over the 32 columns, TMEM as scratch.
-// Reads S and dP columns, leaves ds (fp32) in the S column, updates the row's bins.
-template <int W>
-__device__ __forceinline__ void bwd_q_group_generic_tmem(uint32_t t_s, uint32_t t_dp, const rowscore::SegCtx& sc,
-                                                         const rowscore::RowCtx& rc, const rowscore::GroupLanes& gl,
-                                                         int b, int g0, const float* rel_s, float* bin, float scale,
-                                                         float neg, float m2, float linv, float delta, int sub) {
-#pragma unroll 1
-  for (int jj = 0; jj < W; ++jj) {
-    const uint32_t raw = tmem_ld1(t_s + jj);
-    const uint32_t dpr = tmem_ld1(t_dp + jj);
-    tmem_wait_ld();
-    int slot;
-    const float t = rowscore::score_generic(__uint_as_float(raw), sc, rc, gl, b, g0, jj, rel_s, scale, neg, slot, sub);
-    const float pv = ex2(fmaf(t, LOG2E, -m2)) * linv;
-    const float ds = (t == -INFINITY) ? 0.f : pv * (__uint_as_float(dpr) - delta);
-    if (slot >= 0) bin[slot * TM + rc.row] += ds;
-    tmem_st1(t_s + jj, __float_as_uint(ds));
-  }
-  tmem_wait_st();
+__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+  plan::PSeg s;
+  s.c_begin = r.kb;
+  s.c_end = r.ke;
+  s.c_len = sg.len;
+  s.band = sg.band != 0;
+  s.radius = sg.radius;
+  s.mask_rule = sg.side.mask_rule;
+  s.id_rule = R > 0 ? sg.side.id_rule : IDR_NONE;
+  s.D = sg.side.max_distance;
+  s.R = R;
+  s.diag_ok = perm && pd == s.D;
+  s.rows_are_keys = false;
+  s.c_eid = sg.side.k_eid;
+  s.c_eid_stride = sg.side.k_len;
+  s.col_sent = (s.id_rule == IDR_CROSS_KSENT);
+  s.c_sent = s.col_sent ? sg.side.sent : nullptr;
+  s.c_sent_stride = sg.side.sent_len;
+  return s;
 }
 
-// NP threads per row inside a warp set; SETS warp sets take alternate chunks (S / dP are
-// double-buffered by chunk parity, so set s owns buffer s).
-template <int NP, int SETS>
-__global__ void __launch_bounds__(nthreads<NP * SETS>(), 1)
+__device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i, bool row_ok) {
+  rc.q_e = 0;
+  rc.q_sent = -1;
+  if (row_ok && sc.mask_rule == MR_EXAMPLE_ID) rc.q_e = __ldg(sc.sd->q_eid + (int64_t)b * sc.sd->q_len + i);
+  if (row_ok && sc.id_rule == IDR_CROSS_QSENT) rc.q_sent = __ldg(sc.sd->sent + (int64_t)b * sc.sd->sent_len + i);
+}
+__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, int row) {
+  auto rel_at = [&](int id) -> float {
+    return (id >= 0 && id < sc.R) ? rel_s[plan::slot_of_id(id, sc.pd, sc.perm) * TM + row] : 0.f;
+  };
+  const bool on = sc.id_rule != IDR_NONE;
+  rc.relP = on ? rel_at(sc.D) : 0.f;
+  rc.relN = on ? rel_at(2 * sc.D) : 0.f;
+  rc.relX = on ? rel_at(2 * sc.D + 1) : 0.f;
+  rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
+}
+
+// Generic per-element score (any rule).  Dead pairs return -inf; `slot` = bin slot or -1.
+__device__ __forceinline__ float score_generic_q(float x, const SegC& sc, const RowC& rc, int b, int i, int row,
+                                                 bool row_ok, int j, int ke_j, int ks_j, const float* rel_s,
+                                                 float scale, float neg, int& slot) {
+  const Side& sd = *sc.sd;
+  const int off = j - i;
+  slot = -1;
+  const bool live = j < sc.ke && (!sc.band || (off <= sc.radius && off >= -sc.radius));
+  if (!live) return -INFINITY;
+  const int col = sc.band ? off + sc.radius : j;
+  bool ok = true;
+  int id = -1;
+  switch (sc.mask_rule) {
+    case MR_EXPLICIT: ok = row_ok ? (__ldg(sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) != 0) : true; break;
+    case MR_EXAMPLE_ID: ok = (rc.q_e == ke_j); break;
+    default: break;
+  }
+  switch (sc.id_rule) {
+    case IDR_EXPLICIT: id = row_ok ? __ldg(sd.ids + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) : -1; break;
+    case IDR_1D: id = rel_id_1d(off, sc.D); break;
+    case IDR_CROSS_QSENT: id = 2 * sc.D + 1 + (rc.q_sent == j ? 1 : 0); break;
+    case IDR_CROSS_KSENT: id = 2 * sc.D + 1 + (ks_j == i ? 1 : 0); break;
+    case IDR_2D: id = rel_id_2d(i, j, sd.npr, sd.core, sc.D); break;
+    default: break;
+  }
+  float rel = 0.f;
+  if (id >= 0 && id < sc.R) {
+    slot = plan::slot_of_id(id, sc.pd, sc.perm);
+    rel = rel_s[slot * TM + row];
+  }
+  float v = fmaf(x, scale, rel);
+  if (!ok) v += neg;
+  return v;
+}
+
+// Query-centric backward.  Each elementwise thread owns (row, one 32-key group) of the chunks its
+// warp set serves: NP = 2 threads per row, SETS warp sets on alternate chunks (S / dP are
+// double-buffered by chunk parity, so set s owns buffer s).  The evaluation form of every
+// (quadrant, group) pair comes from the planner warp (tc_plan.cuh).
+constexpr int NP = 2;
+constexpr int NPL = 4;   // plan ring slots
+template <int SETS>
+constexpr int bq_threads() { return (4 * NP * SETS + 3) * 32; }
+
+template <int SETS>
+__global__ void __launch_bounds__(bq_threads<SETS>(), 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
-                const __grid_constant__ CUtensorMap map_e, const TcBwdQParams p) {
+                const __grid_constant__ CUtensorMap map_e, const __grid_constant__ TcBwdQParams p) {
   using namespace bq;
-  constexpr int W = 64 / NP;          // columns per elementwise thread and chunk
+  constexpr int W = 32;               // columns per elementwise thread and chunk
   constexpr int NEW = 128 * NP;       // elementwise threads per set
   constexpr int NALL = NEW * SETS;    // all elementwise threads
   constexpr int NB = NP * SETS;       // private bin arrays per row
-  constexpr int WP = 4 * NB, WM = 4 * NB + 1;   // producer / MMA warp
+  constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = 4 * NB + 2;   // producer / MMA / planner warp
   constexpr int RB = 128 / NB;        // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
@@ -217,6 +293,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + SM_REL);
   float* bins = reinterpret_cast<float*>(smem + SM_BIN);
+  plan::ChunkPlan* plans = reinterpret_cast<plan::ChunkPlan*>(smem + SM_PLAN);
+  plan::RelMeta* relmeta = reinterpret_cast<plan::RelMeta*>(smem + SM_META);
   const BwdQArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TM;
@@ -235,6 +313,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dar_full, NALL);
+    for (int s = 0; s < NPL; ++s) {
+      mbar_init(&bars->pl_full[s], 1);
+      mbar_init(&bars->pl_empty[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
@@ -247,6 +329,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   SegRange r1{0, 0, 0};
   if (a.nseg > 1) r1 = seg_range(a.seg[1], i0);
   const int nchunks = r0.n + r1.n;
+  const int pd = a.seg[0].side.max_distance;
+  const bool perm = (2 * pd + 1 <= R);
 
   if (warp == WP) {
     if (elect_one()) {
@@ -284,6 +368,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int c = 0; c <= nchunks; ++c) {
         if (c < nchunks) {
           const int st = c % NST;
+          mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
           mbar_wait(&bars->kv_full[st], (c / NST) & 1);
           tc_fence_after_sync();
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
@@ -302,10 +387,11 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int pc = c - 1, st = pc % NST;
           mbar_wait(&bars->ds_full[pc & 1], (pc >> 1) & 1);
           tc_fence_after_sync();
+          mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + T_DQ, tmem + T_DP + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
+            umma_ts(tmem + T_DQ, tmem + T_DP + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
                     make_smem_desc_sw128(k_addr + kk * 2048, 16, 1024), idesc_dq, (pc > 0 || kk > 0));
           umma_commit(&bars->kv_empty[st]);
           if (pc == nchunks - 1) {
@@ -334,139 +420,239 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
+  } else if (warp == WPL) {
+    // ===================== planner =====================
+    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
+    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    const Side* qs_side = nullptr;
+    if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
+    if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
+    const plan::RowSent rs = plan::row_sent_ranges(qs_side ? qs_side->sent : nullptr,
+                                                   qs_side ? qs_side->sent_len : 0, b, i0, a.rows.len, lane);
+    auto run = [&](const plan::PSeg& ps, int c_begin, int c_end, int kb) {
+      for (int c = c_begin; c < c_end; ++c) {
+        const int sl = c % NPL;
+        if (c >= NPL) mbar_wait_warp(&bars->pl_empty[sl], ((c / NPL) & 1) ^ 1);
+        plan::plan_chunk(ps, b, kb + (c - c_begin) * TN, i0, rs, plans + sl, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->pl_full[sl]);
+      }
+    };
+    run(ps0, 0, r0.n, r0.kb);
+    if (a.nseg > 1) run(ps1, r0.n, nchunks, r1.kb);
   } else {
-    // ===================== elementwise warps (NP threads per row) =====================
-    using namespace rowscore;
+    // ===================== elementwise warps (2 threads per row) =====================
     if (tid == 0) TRACE(1, 0);
-    const int row = (warp & 3) * 32 + lane;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
     const int set = warp / (4 * NP);     // which chunk parity this warp serves
-    const int part = (warp >> 2) % NP;   // which W-column slice of the chunk
+    const int part = (warp >> 2) % NP;   // which 32-key group of the chunk
     const int bidx = set * NP + part;    // private bin array / output column slice
-    const int win = (part * W) / 32;     // 32-key lane window holding the slice
-    const int sub = (part * W) % 32;     // offset of the slice inside the window
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
-    const int wrow0 = i0 + (warp & 3) * 32;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const int pd = a.seg[0].side.max_distance;
-    const bool perm = (2 * pd + 1 <= R);
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
-    for (int x = lane + 32 * (warp & 3); x < RB * TM; x += 128) bin[x] = 0.f;
+    for (int x = lane + 32 * quad; x < RB * TM; x += 128) bin[x] = 0.f;
     for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
-    SegCtx sc0 = make_seg_ctx(a.seg[0], r0, R, pd, perm);
-    SegCtx sc1 = make_seg_ctx(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
-    RowCtx rc0, rc1;
-    rc0.i = rc1.i = i;
-    rc0.row = rc1.row = row;
-    rc0.row_ok = rc1.row_ok = row_ok;
-    init_row_loads(rc0, sc0, b);
-    init_row_loads(rc1, sc1, b);
-    auto chunk_key0 = [&](int c) { return c < r0.n ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN; };
-    float bias_l0 = 0.f, bias_l1 = 0.f;
-    if (rpad && bidx == 0) {
-      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
-      if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
-      if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
-    }
-    // row constants (written by tc_bwd_prep_kernel)
-    float m2 = 0.f, linv = 0.f, delta = 0.f;
+    const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
+    const SegC sc1 = make_segc(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    RowC rc0, rc1;
+    row_loads(rc0, sc0, b, i, row_ok);
+    row_loads(rc1, sc1, b, i, row_ok);
+    // row constants (written by tc_bwd_prep_kernel): p = exp2(t * log2e - m2l), m2l = m*log2e + log2(l)
+    float m2l = INFINITY, m2 = 0.f, delta = 0.f;
     const int64_t srow = (int64_t)(b * a.H + h) * a.rows.len + i;
     const int64_t prow = (int64_t)(b * a.H + h) * p.lp + i;
     if (row_ok) {
       const float4 rs4 = __ldg(p.rowstat + prow);
       m2 = rs4.x;
-      linv = rs4.y;
+      m2l = rs4.x - __log2f(rs4.y);
       delta = rs4.z;
     }
+    if (rpad && tid < 64)
+      plan::rel_meta_init(relmeta, tid, reinterpret_cast<const __nv_bfloat16*>(a.rows.bias), a.H, h, R, pd, perm,
+                          a.scale);
     if (tid == 0) TRACE(1, 1);
+    named_bar_sync(1, NALL);   // relmeta visible
     if (rpad && bidx == 0) {   // warp-uniform: the four (set 0, part 0) warps extract allrel
       mbar_wait_warp(&bars->rel_full, 0);
       if (tid == 0) TRACE(1, 2);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int c0 = 0; c0 < rpad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + T_REL + lane_sel + c0, v);
-        tmem_wait_ld();
+      float* ws_row = p.allrel_ws + prow * p.rw;
+      const int rw = p.rw;
+      plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale,
+                            [&](int c0, const float (&val)[16]) {
+                              if (row_ok) {   // 16 ids = 4 x 16-byte stores (rows padded to a multiple of 4 ids)
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          const int pid = c0 + x;
-          const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
-          const float val = pid < R ? (__uint_as_float(v[x]) + bv) * a.scale : 0.f;
-          if (pid < R) rel_s[slot_of_id(pid, pd, perm) * TM + row] = val;
-          v[x] = __float_as_uint(val);
-        }
-        if (row_ok) {   // 16 ids = 4 x 16-byte stores (workspace rows are padded to a multiple of 4 ids)
-#pragma unroll
-          for (int x4 = 0; x4 < 4; ++x4)
-            if (c0 + 4 * x4 < p.rw)
-              *reinterpret_cast<uint4*>(p.allrel_ws + prow * p.rw + c0 + 4 * x4) =
-                  make_uint4(v[4 * x4], v[4 * x4 + 1], v[4 * x4 + 2], v[4 * x4 + 3]);
-        }
-      }
+                                for (int x4 = 0; x4 < 4; ++x4)
+                                  if (c0 + 4 * x4 < rw)
+                                    *reinterpret_cast<float4*>(ws_row + c0 + 4 * x4) =
+                                        make_float4(c0 + 4 * x4 < R ? val[4 * x4] : 0.f, c0 + 4 * x4 + 1 < R ? val[4 * x4 + 1] : 0.f,
+                                                    c0 + 4 * x4 + 2 < R ? val[4 * x4 + 2] : 0.f, c0 + 4 * x4 + 3 < R ? val[4 * x4 + 3] : 0.f);
+                              }
+                            });
     }
     if (tid == 0) TRACE(1, 3);
     named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
     if (tid == 0) TRACE(1, 4);
-    init_row(rc0, sc0, b, rel_s);
-    init_row(rc1, sc1, b, rel_s);
+    row_consts(rc0, sc0, rel_s, row);
+    row_consts(rc1, sc1, rel_s, row);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
     float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
+    const float scale2 = a.scale * LOG2E;
 
     // One call per key segment (inlined twice: no per-field selects inside the chunk loop).
     // Chunks [c_begin, c_end) belong to this segment; this warp set handles c % SETS == set.
-    auto run_chunks = [&](const SegCtx sc, const RowCtx rc, int c_begin, int c_end, int kb) {
+    auto run_chunks = [&](const SegC sc, const RowC rc, int c_begin, int c_end, int kb) {
       int c = c_begin + ((set - c_begin) % SETS + SETS) % SETS;
-      if (c >= c_end) return;
-      GroupLanes gl = load_group_lanes(sc, b, kb + (c - c_begin) * TN + 32 * win, lane);
+      const bool mre = sc.mask_rule == MR_EXAMPLE_ID;
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
         const int g0 = kb + (c - c_begin) * TN + part * W;
         const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
         const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
-        GroupLanes nl{0, -1};
-        if (c + SETS < c_end) nl = load_group_lanes(sc, b, kb + (c + SETS - c_begin) * TN + 32 * win, lane);
-        const GroupPlan gp = classify<W>(sc, rc, gl, wrow0, g0, lane, a.neg, sub);
+        const plan::ChunkPlan* cp = plans + (c % NPL);
         if (tid == 0) TRACE(1, 8 + 3 * c);
+        // the MMA warp issued S_c / dP_c only after plan c had been published
         mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
         if (tid == 0) TRACE(1, 9 + 3 * c);
         tc_fence_after_sync();
+        const uint32_t w0 = cp->q[quad][part];
+        const int ce0 = (int)cp->q[quad][2 + part];
+        const int mode = (int)(w0 & 0xffu);
+        const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
+        const bool masked = mre && !mask_pe && (rc.q_e != ce0);
+        const float mterm = masked ? a.neg : 0.f;
+        const int ccls = (int)((w0 >> 8) & 0xffu);
+        const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
         uint32_t ds_pk[W / 2];
-        if (gp.mode == GM_DEAD) {
+        bool zero = (mode == plan::DEAD);
+        // every row of the warp masked for the whole group while holding a real maximum: p == 0 exactly
+        if (!zero && mode == plan::FAST && mre && __all_sync(0xffffffffu, masked && m2 > -1e8f)) zero = true;
+        if (zero) {
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = 0u;
+        } else if (mode == plan::FAST) {
+          uint32_t v[W], w[W];
+          tmem_ld32(t_s, v);
+          tmem_ld32(t_dp, w);
+          tmem_wait_ld();
+          const float cadd = relc + mterm;
+          // a masked score is cadd itself (|x * scale| < 32 is absorbed by -1e9 in fp32)
+          const float gmul = masked ? 0.f : scale2;
+          const float gsub = fmaf(cadd, LOG2E, -m2l);
+          float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int x = 0; x < W / 2; ++x) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
+            const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
+            const float d0 = p0 * (__uint_as_float(w[2 * x]) - delta);
+            const float d1 = p1 * (__uint_as_float(w[2 * x + 1]) - delta);
+            t0 += d0;
+            t1 += d1;
+            ds_pk[x] = pack_bf16x2(d0, d1);
+          }
+          const float tot = t0 + t1;
+          if (ccls == plan::C_POS) accP += tot;
+          else if (ccls == plan::C_NEG) accN += tot;
+          else if (ccls == plan::C_CROSS) accX += tot;
         } else {
           float ds[W];
-          if (gp.mode == GM_GEN) {
-            bwd_q_group_generic_tmem<W>(t_s, t_dp, sc, rc, gl, b, g0, rel_s, bin, a.scale, a.neg, m2, linv, delta, sub);
+          if (mode == plan::GEN) {
+            // real loop, TMEM as dynamically indexed scratch: one copy of the generic code
+#pragma unroll 1
+            for (int jj = 0; jj < W; ++jj) {
+              const uint32_t raw = tmem_ld1(t_s + jj);
+              const uint32_t dpr = tmem_ld1(t_dp + jj);
+              tmem_wait_ld();
+              int slot;
+              const float t = score_generic_q(__uint_as_float(raw), sc, rc, b, i, row, row_ok, g0 + jj,
+                                              cp->ce[part * W + jj], cp->cs[part * W + jj], rel_s, a.scale, a.neg, slot);
+              const float pv = ex2(fmaf(t, LOG2E, -m2l));   // dead: t = -inf -> 0
+              const float dsv = (t == -INFINITY) ? 0.f : pv * (__uint_as_float(dpr) - delta);
+              if (slot >= 0) bin[slot * TM + row] += dsv;
+              __syncwarp();   // score_generic diverges per row; tcgen05.st needs the converged warp
+              tmem_st1(t_s + jj, __float_as_uint(dsv));
+            }
+            tmem_wait_st();
             uint32_t v[W];
-            tmem_ldN(t_s, v);
+            tmem_ld32(t_s, v);
             tmem_wait_ld();
 #pragma unroll
             for (int x = 0; x < W; ++x) ds[x] = __uint_as_float(v[x]);
           } else {
             float t[W];
-            uint32_t v[W];
-            tmem_ldN(t_s, v);
-            tmem_wait_ld();
+            uint32_t w[W];
+            {
+              uint32_t v[W];
+              tmem_ld32(t_s, v);
+              tmem_ld32(t_dp, w);
+              tmem_wait_ld();
 #pragma unroll
-            for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
-            score_group<0, W, W>(t, gp, sc, rc, gl, b, g0, rel_s, a.scale, a.neg, sub);
-            tmem_ldN(t_dp, v);
-            tmem_wait_ld();
-            float tot = 0.f;
-#pragma unroll
-            for (int x = 0; x < W; ++x) {
-              const float pv = ex2(fmaf(t[x], LOG2E, -m2)) * linv;   // dead: t = -inf -> 0
-              ds[x] = pv * (__uint_as_float(v[x]) - delta);
-              tot += ds[x];
+              for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
             }
+            switch (mode) {
+              case plan::EDGE: {
+                const int d0 = g0 - i;
+                int jlo = 0, jhi = min(W, sc.ke - g0);
+                if (sc.band) {
+                  jlo = max(jlo, -sc.radius - d0);
+                  jhi = min(jhi, sc.radius - d0 + 1);
+                }
+                const unsigned span = (unsigned)max(jhi - jlo, 0);
+                const float cadd = relc + mterm;
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) {
+                  const float v = fmaf(t[jj], a.scale, cadd);
+                  t[jj] = ((unsigned)(jj - jlo) < span) ? v : -INFINITY;
+                }
+                break;
+              }
+              case plan::DIAG: {
+                const int d0 = g0 - i + sc.D;
+                const float* base = rel_s + row;
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) {
+                  const int sl = min(max(d0 + jj, 0), 2 * sc.D);
+                  t[jj] = fmaf(t[jj], a.scale, base[sl * TM] + mterm);
+                }
+                break;
+              }
+              case plan::QS: {
+                const int d0 = rc.q_sent - g0;
+                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) t[jj] = fmaf(t[jj], a.scale, d0 == jj ? c1 : c0);
+                break;
+              }
+              default: {   // KS
+                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) t[jj] = fmaf(t[jj], a.scale, cp->cs[part * W + jj] == i ? c1 : c0);
+                break;
+              }
+            }
+            if (mask_pe) {
+#pragma unroll
+              for (int jj = 0; jj < W; ++jj) t[jj] += (cp->ce[part * W + jj] == rc.q_e) ? 0.f : a.neg;
+            }
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int x = 0; x < W; x += 2) {
+              const float p0 = ex2(fmaf(t[x], LOG2E, -m2l));   // dead: t = -inf -> 0
+              const float p1 = ex2(fmaf(t[x + 1], LOG2E, -m2l));
+              ds[x] = p0 * (__uint_as_float(w[x]) - delta);
+              ds[x + 1] = p1 * (__uint_as_float(w[x + 1]) - delta);
+              t0 += ds[x];
+              t1 += ds[x + 1];
+            }
+            const float tot = t0 + t1;
             // ---- relative-id bins ----
-            if (gp.mode == GM_FAST || gp.mode == GM_EDGE) {
-              if (gp.ccls == 1) accP += tot;
-              else if (gp.ccls == 2) accN += tot;
-              else if (gp.ccls == 3) accX += tot;
-            } else if (gp.mode == GM_DIAG) {
+            if (mode == plan::EDGE) {
+              if (ccls == plan::C_POS) accP += tot;
+              else if (ccls == plan::C_NEG) accN += tot;
+              else if (ccls == plan::C_CROSS) accX += tot;
+            } else if (mode == plan::DIAG) {
               const int d0 = g0 - i + sc.D;
               float* base = bin + row;
 #pragma unroll
@@ -474,20 +660,17 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const int sl = min(max(d0 + x, 0), 2 * sc.D);
                 base[sl * TM] += ds[x];
               }
-            } else if (gp.mode == GM_QS) {
+            } else if (mode == plan::QS) {
               const int d0 = rc.q_sent - g0;
               float sp = 0.f;
 #pragma unroll
               for (int x = 0; x < W; ++x) sp += (d0 == x) ? ds[x] : 0.f;
               accX1 += sp;
               accX += tot - sp;
-            } else {  // GM_KS
+            } else {  // KS
               float sp = 0.f;
 #pragma unroll
-              for (int x = 0; x < W; ++x) {
-                const int ks_j = __shfl_sync(0xffffffffu, gl.ks_l, sub + x);
-                sp += (ks_j == i) ? ds[x] : 0.f;
-              }
+              for (int x = 0; x < W; ++x) sp += (cp->cs[part * W + x] == i) ? ds[x] : 0.f;
               accX1 += sp;
               accX += tot - sp;
             }
@@ -495,13 +678,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
         }
-        // each part packs into its OWN column range (other parts may still be reading their inputs)
-        tmem_stN(t_dp, ds_pk);
+        // each part packs into its OWN column range (the other part may still be reading its inputs)
+        tmem_st16(t_dp, ds_pk);
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->ds_full[c & 1]);
         if (tid == 0) TRACE(1, 10 + 3 * c);
-        gl = nl;
       }
     };
     run_chunks(sc0, rc0, 0, r0.n, r0.kb);
@@ -509,7 +691,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // flush the constant-class accumulators into this part's bins
     if (R > 0) {
       auto flush = [&](int id, float v) {
-        if (id >= 0 && id < R) bin[slot_of_id(id, pd, perm) * TM + row] += v;
+        if (id >= 0 && id < R) bin[plan::slot_of_id(id, pd, perm) * TM + row] += v;
       };
       const int dd = sc0.D;   // both segments of a row set share max_distance
       flush(dd, accP);
@@ -532,7 +714,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int pid = c0 + x;
           float w = 0.f;
           if (pid < R) {
-            const int sl = slot_of_id(pid, pd, perm);
+            const int sl = plan::slot_of_id(pid, pd, perm);
 #pragma unroll
             for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
           }
@@ -545,7 +727,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                        pack_bf16x2(w8[4], w8[5]), pack_bf16x2(w8[6], w8[7]));
           *reinterpret_cast<uint4*>(smem + SM_A + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = pk4;
           // bias partial: sum over the 32 rows of this warp, one value per id
-          float* bs = reinterpret_cast<float*>(smem + SM_BS) + (warp & 3) * 64 + c0;
+          float* bs = reinterpret_cast<float*>(smem + SM_BS) + quad * 64 + c0;
 #pragma unroll
           for (int x = 0; x < 8; ++x) {
             float v = row_ok ? w8[x] : 0.f;
@@ -586,7 +768,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (rpad && a.tg_partial) {
       const int64_t pidx = ((int64_t)(b * gridDim.x + blockIdx.x) * a.H + h);
       if (bidx == 0) {   // warp-uniform: four warps, lanes with (lane % 32) < 16 hold the 64 id rows
-        const int pid = (warp & 3) * 16 + lane;
+        const int pid = quad * 16 + lane;
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t v[32];
@@ -1236,9 +1418,9 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(uns
 
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1282,9 +1464,9 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   static const int force_sets = getenv("MLT_BWD_SETS") ? atoi(getenv("MLT_BWD_SETS")) : 0;
   const bool two_sets = force_sets ? force_sets == 2 : est_chunks >= 16;
   if (R <= 32 && two_sets)   // 4 private bin arrays of 32 slots
-    tc_bwd_q_kernel<2, 2><<<grid, nthreads<4>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<2><<<grid, bq_threads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else
-    tc_bwd_q_kernel<2, 1><<<grid, nthreads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<1><<<grid, bq_threads<1>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 

@@ -49,7 +49,8 @@ constexpr int SM_E = SM_Q + TM * 128;            // 8 KB  (<= 64 ids x 128 B)
 constexpr int SM_KV = SM_E + 64 * 128;           // NST x (K 8 KB + V 8 KB)
 constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64 slots][128 rows] fp32 = 32 KB
 constexpr int SM_PLAN = SM_REL + 64 * TM * 4;        // NPL x ChunkPlan
-constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
+constexpr int SM_META = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);   // 64 x RelMeta
+constexpr int SM_BAR = SM_META + 64 * (int)sizeof(plan::RelMeta);
 constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;        // slack for 1024-B alignment
 
@@ -210,6 +211,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   float* rel_s = reinterpret_cast<float*>(smem + SM_REL);
   plan::ChunkPlan* plans = reinterpret_cast<plan::ChunkPlan*>(smem + SM_PLAN);
+  plan::RelMeta* relmeta = reinterpret_cast<plan::RelMeta*>(smem + SM_META);
   const FwdArgs& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TM;
@@ -272,7 +274,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(TM, 64, 0, 1);
       const uint32_t q_addr = smem_u32(smem + SM_Q);
+      TRACE(2, 0);
       mbar_wait(&bars->q_full, 0);
+      TRACE(2, 1);
       tc_fence_after_sync();
       if (rpad) {
         const uint32_t idesc_r = make_idesc_bf16(TM, rpad, 0, 0);
@@ -286,6 +290,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       for (int c = 0; c <= nchunks; ++c) {
         if (c < nchunks) {
           const int st = c % NST;
+          mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the softmax warps by s_full
           mbar_wait(&bars->kv_full[st], (c / NST) & 1);
           tc_fence_after_sync();
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
@@ -294,6 +299,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             umma_ss(tmem + (c & 1) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
                     make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
           umma_commit(&bars->s_full[c & 1]);
+          TRACE(2, 2 + 2 * c);
         }
         if (c >= 1) {
           const int pc = c - 1, st = pc % NST;
@@ -307,6 +313,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     make_smem_desc_sw128(v_addr + kk * 2048, 16, 1024), idesc_o, (pc > 0 || kk > 0));
           umma_commit(&bars->o_full[pc & 1]);
           umma_commit(&bars->kv_empty[st]);
+          TRACE(2, 3 + 2 * pc);
         }
       }
     }
@@ -338,6 +345,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    if (tid == 0) TRACE(0, 0);
     const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
     const SegC sc1 = make_segc(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
     RowC rc0, rc1;
@@ -345,28 +353,19 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     row_loads(rc1, sc1, b, i, row_ok);
     if (rpad) {
       // allrel (+ bias) * scale -> slot-ordered per-row table in shared memory
-      float bias_l0 = 0.f, bias_l1 = 0.f;  // lane l holds bias[l], bias[32 + l]
-      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.rows.bias);
-      if (lane < R) bias_l0 = __bfloat162float(bias[lane * a.H + h]);
-      if (lane + 32 < R) bias_l1 = __bfloat162float(bias[(lane + 32) * a.H + h]);
+      if (tid < 64)
+        plan::rel_meta_init(relmeta, tid, reinterpret_cast<const __nv_bfloat16*>(a.rows.bias), a.H, h, R, pd, perm,
+                            a.scale);
+      named_bar_sync(1, 128);
       mbar_wait_warp(&bars->rel_full, 0);
+      if (tid == 0) TRACE(0, 1);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int c0 = 0; c0 < rpad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + T_REL + lane_sel + c0, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          const int pid = c0 + x;
-          const float bv = __shfl_sync(0xffffffffu, c0 < 32 ? bias_l0 : bias_l1, pid & 31);
-          if (pid < R) rel_s[plan::slot_of_id(pid, pd, perm) * TM + row] = (__uint_as_float(v[x]) + bv) * a.scale;
-        }
-      }
+      plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale, [](int, const float (&)[16]) {});
     }
     row_consts(rc0, sc0, rel_s, row);   // a thread only reads its own column of rel_s: no barrier
     row_consts(rc1, sc1, rel_s, row);
 
+    if (tid == 0) TRACE(0, 2);
     const float scale2 = a.scale * LOG2E;
     float m = M_INIT;        // maximum the exponentials are taken against (lags the true maximum)
     float m_true = M_INIT;   // true running maximum
@@ -385,10 +384,13 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int key0 = seg_kb + cc * TN;
         const uint32_t t_s = tmem + (c & 1) * 64 + lane_sel;
         const plan::ChunkPlan* cp = plans + (c % NPL);
-        mbar_wait_warp(&bars->pl_full[c % NPL], (c / NPL) & 1);
-        const uint2 pw = *reinterpret_cast<const uint2*>(&cp->w0[warp][0]);
-        const int2 pe = *reinterpret_cast<const int2*>(&cp->ce0[warp][0]);
+        if (tid == 0) TRACE(0, 4 + 3 * c);
+        // the MMA warp issued S_c only after plan c had been published: one wait covers both
         mbar_wait_warp(&bars->s_full[c & 1], (c >> 1) & 1);
+        const uint4 pq = *reinterpret_cast<const uint4*>(&cp->q[warp][0]);
+        const uint2 pw = make_uint2(pq.x, pq.y);
+        const int2 pe = make_int2((int)pq.z, (int)pq.w);
+        if (tid == 0) TRACE(0, 5 + 3 * c);
         tc_fence_after_sync();
         // ---- pass 1: row maximum; FAST groups leave the raw accumulator in place ----
         float mx = -INFINITY;
@@ -591,6 +593,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[c & 1]);
+        if (tid == 0) TRACE(0, 6 + 3 * c);
         l += (ls0 + ls1) + (ls2 + ls3);
       }
     }
@@ -623,6 +626,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       float2* st = reinterpret_cast<float2*>(a.stats) + ((int64_t)(b * a.H + h) * a.rows.len + i);
       *st = make_float2(m_true, l * ex2((m - m_true) * LOG2E));
     }
+    if (tid == 0) TRACE(0, 3);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -33,8 +33,10 @@ enum CCls : int { C_NONE = 0, C_POS = 1, C_NEG = 2, C_CROSS = 3 };
 constexpr uint32_t F_MASK_PE = 1u << 16;   // example-id mask changes inside the group
 
 struct ChunkPlan {          // one ring slot (576 B)
-  uint32_t w0[4][2];        // [row quadrant][group]: mode | ccls << 8 | flags
-  int32_t ce0[4][2];        // example id shared by the group's columns (uniform-mask groups)
+  // [row quadrant]: { w0 of group 0, w0 of group 1, ce0 of group 0, ce0 of group 1 } (one LDS.128)
+  //   w0  = mode | ccls << 8 | flags
+  //   ce0 = example id shared by the group's columns (uniform-mask groups)
+  uint32_t q[4][4];
   int32_t ce[64];           // column example ids
   int32_t cs[64];           // column sentence ids (rule KSENT on query-rows / QSENT on key-rows)
 };
@@ -160,8 +162,48 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, int b, int col0, int r
 #ifdef MLT_FORCE_GEN
     if (mode != DEAD) { mode = GEN; flags = 0; }
 #endif
-    out->w0[w][g] = mode | (ccls << 8) | flags;
-    out->ce0[w][g] = g ? f1 : f0;
+    out->q[w][g] = mode | (ccls << 8) | flags;
+    out->q[w][2 + g] = (uint32_t)(g ? f1 : f0);
+  }
+}
+
+// ---- per-row relative table ---------------------------------------------------------------------
+// allrel = Q.E^T sits in TMEM (lane = row, column = id).  The elementwise warps need it as
+// rel_s[slot][row] = (allrel[row, id] + bias[id]) * scale in shared memory (slot order, see
+// slot_of_id).  relmeta[id] = (bias[id] * scale, slot * rows-per-tile) is prepared once per tile by
+// 64 threads, so that the transposition costs 4 instructions per id and row.
+struct RelMeta {
+  float bias_scaled;
+  int slot_off;     // slot * 128 (element offset of the slot's row vector)
+};
+
+// Called by threads t = 0..63 of the elementwise group (followed by a barrier of that group).
+__device__ __forceinline__ void rel_meta_init(RelMeta* meta, int t, const __nv_bfloat16* bias, int H, int h,
+                                              int R, int D, bool perm, float scale) {
+  RelMeta m;
+  m.bias_scaled = (t < R) ? __bfloat162float(bias[t * H + h]) * scale : 0.f;
+  m.slot_off = (t < R ? slot_of_id(t, D, perm) : t) * 128;   // ids >= R: identity (free slots, value 0)
+  meta[t] = m;
+}
+
+// Whole warp; `taddr` = lane-selected TMEM address of allrel column 0.  Returns nothing; the
+// optional `keep` callback receives (id, value) for callers that also publish the id-ordered row.
+template <typename F>
+__device__ __forceinline__ void rel_table_build(uint32_t taddr, const RelMeta* meta, float* rel_s, int row,
+                                                int rpad, float scale, F&& keep) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < rpad; c0 += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld16(taddr + c0, v);
+    ptx::tmem_wait_ld();
+    float val[16];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) {
+      const RelMeta m = meta[c0 + x];   // warp-broadcast LDS.64
+      val[x] = fmaf(__uint_as_float(v[x]), scale, m.bias_scaled);
+      rel_s[m.slot_off + row] = val[x];
+    }
+    keep(c0, val);
   }
 }
 
