@@ -156,8 +156,15 @@ __device__ __forceinline__ SegRange seg_range(const KeySeg& sg, int i0) {
 struct TcBwdQParams {
   BwdQArgs a;
   int rpad, rw, lp;   // R padded to 16 (MMA N), to 4 (workspace row), rows padded (workspace)
-  float4* rowstat;    // ws [B, H, lp] = (m * log2e, 1 / l, delta, 0)
-  float* allrel_ws;   // ws [B, H, lp, rw] (allrel * scale)
+  float4* rowstat;    // ws [B, H, lp] = (m * log2e, 1 / l, delta, 0)     (tc_bwd_prep_kernel)
+  // ws [B, H, lp / 64, rw + 4, 64]: the per-row records the key-centric pass consumes, exponent-ready,
+  // stored field-major per block of 64 rows (one contiguous bulk copy per query chunk; in shared
+  // memory field f of query x sits at f * 64 + x: immediate offsets, warp-broadcast reads):
+  //   field 0      -(m*log2e + log2 l)               exponent term of an element without relative score
+  //   field 1      log2 of p for a MASKED element    log2(1/l) on fully-masked rows, -inf otherwise
+  //   field 2      delta = sum_c dO*O      field 3: 0
+  //   field 4 + id allrel[id]*scale*log2e - (m*log2e + log2 l)
+  float* rec_ws;
 };
 
 // ---- row-side contexts of the query-centric pass (rows = queries, columns = keys) -------------
@@ -228,17 +235,18 @@ __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float
   rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
 }
 
-// Generic per-element score (any rule).  Dead pairs return -inf; `slot` = bin slot or -1.
-__device__ __forceinline__ float score_generic_q(float x, const SegC& sc, const RowC& rc, int b, int i, int row,
-                                                 bool row_ok, int j, int ke_j, int ks_j, const float* rel_s,
-                                                 float scale, float neg, int& slot) {
+// Generic per-element evaluation (any rule): relative term (already * scale), mask and liveness.
+__device__ __forceinline__ void eval_generic_q(const SegC& sc, const RowC& rc, int b, int i, int row, bool row_ok,
+                                               int j, int ke_j, int ks_j, const float* rel_s, bool& live,
+                                               bool& ok, float& rel, int& slot) {
   const Side& sd = *sc.sd;
   const int off = j - i;
   slot = -1;
-  const bool live = j < sc.ke && (!sc.band || (off <= sc.radius && off >= -sc.radius));
-  if (!live) return -INFINITY;
+  ok = true;
+  rel = 0.f;
+  live = j < sc.ke && (!sc.band || (off <= sc.radius && off >= -sc.radius));
+  if (!live) return;
   const int col = sc.band ? off + sc.radius : j;
-  bool ok = true;
   int id = -1;
   switch (sc.mask_rule) {
     case MR_EXPLICIT: ok = row_ok ? (__ldg(sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) != 0) : true; break;
@@ -253,16 +261,19 @@ __device__ __forceinline__ float score_generic_q(float x, const SegC& sc, const 
     case IDR_2D: id = rel_id_2d(i, j, sd.npr, sd.core, sc.D); break;
     default: break;
   }
-  float rel = 0.f;
   if (id >= 0 && id < sc.R) {
     slot = plan::slot_of_id(id, sc.pd, sc.perm);
     rel = rel_s[slot * TM + row];
   }
-  float v = fmaf(x, scale, rel);
-  if (!ok) v += neg;
-  return v;
 }
 
+// Probabilities in the backward passes are evaluated in exponent form,
+//     p = exp2(x * scale*log2e + rel*log2e - (m*log2e + log2 l))          unmasked element
+//     p = 1/l on a fully-masked row, 0 otherwise                          masked element
+// (in fp32 a masked score is the additive constant itself -- |s| < 32 is absorbed by -1e9 -- so a
+// masked element never needs the large numbers; this keeps the folded constants free of
+// cancellation).
+//
 // Query-centric backward.  Each elementwise thread owns (row, one 32-key group) of the chunks its
 // warp set serves: NP = 2 threads per row, SETS warp sets on alternate chunks (S / dP are
 // double-buffered by chunk parity, so set s owns buffer s).  The evaluation form of every
@@ -427,19 +438,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const Side* qs_side = nullptr;
     if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
     if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
-    const plan::RowSent rs = plan::row_sent_ranges(qs_side ? qs_side->sent : nullptr,
-                                                   qs_side ? qs_side->sent_len : 0, b, i0, a.rows.len, lane);
-    auto run = [&](const plan::PSeg& ps, int c_begin, int c_end, int kb) {
-      for (int c = c_begin; c < c_end; ++c) {
-        const int sl = c % NPL;
-        if (c >= NPL) mbar_wait_warp(&bars->pl_empty[sl], ((c / NPL) & 1) ^ 1);
-        plan::plan_chunk(ps, b, kb + (c - c_begin) * TN, i0, rs, plans + sl, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->pl_full[sl]);
-      }
-    };
-    run(ps0, 0, r0.n, r0.kb);
-    if (a.nseg > 1) run(ps1, r0.n, nchunks, r1.kb);
+    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.kb, r1.kb, b, i0, qs_side ? qs_side->sent : nullptr,
+                                qs_side ? qs_side->sent_len : 0, a.rows.len, plans, bars->pl_full, bars->pl_empty, lane);
   } else {
     // ===================== elementwise warps (2 threads per row) =====================
     if (tid == 0) TRACE(1, 0);
@@ -459,15 +459,29 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     RowC rc0, rc1;
     row_loads(rc0, sc0, b, i, row_ok);
     row_loads(rc1, sc1, b, i, row_ok);
-    // row constants (written by tc_bwd_prep_kernel): p = exp2(t * log2e - m2l), m2l = m*log2e + log2(l)
-    float m2l = INFINITY, m2 = 0.f, delta = 0.f;
+    // row constants (written by tc_bwd_prep_kernel)
+    float nm2l = -INFINITY;   // -(m*log2e + log2 l): rows beyond the end evaluate to p = 0
+    float lpm = -INFINITY;    // log2 of p of a masked element
+    float delta = 0.f;
+    bool real_max = true;     // the row maximum is an unmasked score
     const int64_t srow = (int64_t)(b * a.H + h) * a.rows.len + i;
     const int64_t prow = (int64_t)(b * a.H + h) * p.lp + i;
     if (row_ok) {
       const float4 rs4 = __ldg(p.rowstat + prow);
-      m2 = rs4.x;
-      m2l = rs4.x - __log2f(rs4.y);
+      const float ll = __log2f(rs4.y);   // log2(1/l)
+      nm2l = ll - rs4.x;
+      real_max = rs4.x > -1e8f;
+      lpm = real_max ? -INFINITY : ll;
       delta = rs4.z;
+    }
+    const int rs_stride = p.rw + 4;
+    // field 0 of this row: block (i / 64), lane (i % 64); consecutive fields are 64 floats apart
+    float* rec_row = p.rec_ws + (((int64_t)(b * a.H + h) * (p.lp >> 6) + (i >> 6)) * rs_stride) * 64 + (i & 63);
+    if (bidx == 0 && row_ok) {
+      rec_row[0] = nm2l;
+      rec_row[64] = lpm;
+      rec_row[128] = delta;
+      rec_row[192] = 0.f;
     }
     if (rpad && tid < 64)
       plan::rel_meta_init(relmeta, tid, reinterpret_cast<const __nv_bfloat16*>(a.rows.bias), a.H, h, R, pd, perm,
@@ -478,17 +492,14 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait_warp(&bars->rel_full, 0);
       if (tid == 0) TRACE(1, 2);
       tc_fence_after_sync();
-      float* ws_row = p.allrel_ws + prow * p.rw;
+      float* ws_row = rec_row + 4 * 64;
       const int rw = p.rw;
       plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale,
                             [&](int c0, const float (&val)[16]) {
-                              if (row_ok) {   // 16 ids = 4 x 16-byte stores (rows padded to a multiple of 4 ids)
+                              if (row_ok) {   // one coalesced 128-byte store per id and warp
 #pragma unroll
-                                for (int x4 = 0; x4 < 4; ++x4)
-                                  if (c0 + 4 * x4 < rw)
-                                    *reinterpret_cast<float4*>(ws_row + c0 + 4 * x4) =
-                                        make_float4(c0 + 4 * x4 < R ? val[4 * x4] : 0.f, c0 + 4 * x4 + 1 < R ? val[4 * x4 + 1] : 0.f,
-                                                    c0 + 4 * x4 + 2 < R ? val[4 * x4 + 2] : 0.f, c0 + 4 * x4 + 3 < R ? val[4 * x4 + 3] : 0.f);
+                                for (int x = 0; x < 16; ++x)
+                                  if (c0 + x < rw) ws_row[(c0 + x) * 64] = fmaf(val[x], LOG2E, nm2l);
                               }
                             });
     }
@@ -522,13 +533,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int mode = (int)(w0 & 0xffu);
         const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
         const bool masked = mre && !mask_pe && (rc.q_e != ce0);
-        const float mterm = masked ? a.neg : 0.f;
         const int ccls = (int)((w0 >> 8) & 0xffu);
         const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
         uint32_t ds_pk[W / 2];
         bool zero = (mode == plan::DEAD);
         // every row of the warp masked for the whole group while holding a real maximum: p == 0 exactly
-        if (!zero && mode == plan::FAST && mre && __all_sync(0xffffffffu, masked && m2 > -1e8f)) zero = true;
+        if (!zero && mode == plan::FAST && mre && __all_sync(0xffffffffu, masked && real_max)) zero = true;
         if (zero) {
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = 0u;
@@ -537,10 +547,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           tmem_ld32(t_s, v);
           tmem_ld32(t_dp, w);
           tmem_wait_ld();
-          const float cadd = relc + mterm;
-          // a masked score is cadd itself (|x * scale| < 32 is absorbed by -1e9 in fp32)
           const float gmul = masked ? 0.f : scale2;
-          const float gsub = fmaf(cadd, LOG2E, -m2l);
+          const float gsub = masked ? lpm : fmaf(relc, LOG2E, nm2l);
           float t0 = 0.f, t1 = 0.f;
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) {
@@ -566,11 +574,13 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const uint32_t dpr = tmem_ld1(t_dp + jj);
               tmem_wait_ld();
               int slot;
-              const float t = score_generic_q(__uint_as_float(raw), sc, rc, b, i, row, row_ok, g0 + jj,
-                                              cp->ce[part * W + jj], cp->cs[part * W + jj], rel_s, a.scale, a.neg, slot);
-              const float pv = ex2(fmaf(t, LOG2E, -m2l));   // dead: t = -inf -> 0
-              const float dsv = (t == -INFINITY) ? 0.f : pv * (__uint_as_float(dpr) - delta);
-              if (slot >= 0) bin[slot * TM + row] += dsv;
+              bool live, ok;
+              float rel;
+              eval_generic_q(sc, rc, b, i, row, row_ok, g0 + jj, cp->ce[part * W + jj], cp->cs[part * W + jj], rel_s,
+                             live, ok, rel, slot);
+              const float pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, fmaf(rel, LOG2E, nm2l)) : lpm);
+              const float dsv = live ? pv * (__uint_as_float(dpr) - delta) : 0.f;
+              if (live && slot >= 0) bin[slot * TM + row] += dsv;
               __syncwarp();   // score_generic diverges per row; tcgen05.st needs the converged warp
               tmem_st1(t_s + jj, __float_as_uint(dsv));
             }
@@ -581,7 +591,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int x = 0; x < W; ++x) ds[x] = __uint_as_float(v[x]);
           } else {
-            float t[W];
+            // e[jj] = exponent of element jj (log2 units); dead elements get -inf, masked ones lpm
+            float e[W];
             uint32_t w[W];
             {
               uint32_t v[W];
@@ -589,7 +600,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               tmem_ld32(t_dp, w);
               tmem_wait_ld();
 #pragma unroll
-              for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
+              for (int x = 0; x < W; ++x) e[x] = __uint_as_float(v[x]);
             }
             switch (mode) {
               case plan::EDGE: {
@@ -600,11 +611,11 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                   jhi = min(jhi, sc.radius - d0 + 1);
                 }
                 const unsigned span = (unsigned)max(jhi - jlo, 0);
-                const float cadd = relc + mterm;
+                const float c2 = fmaf(relc, LOG2E, nm2l);
 #pragma unroll
                 for (int jj = 0; jj < W; ++jj) {
-                  const float v = fmaf(t[jj], a.scale, cadd);
-                  t[jj] = ((unsigned)(jj - jlo) < span) ? v : -INFINITY;
+                  const float v = fmaf(e[jj], scale2, c2);
+                  e[jj] = ((unsigned)(jj - jlo) < span) ? v : -INFINITY;
                 }
                 break;
               }
@@ -614,33 +625,37 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                 for (int jj = 0; jj < W; ++jj) {
                   const int sl = min(max(d0 + jj, 0), 2 * sc.D);
-                  t[jj] = fmaf(t[jj], a.scale, base[sl * TM] + mterm);
+                  e[jj] = fmaf(e[jj], scale2, fmaf(base[sl * TM], LOG2E, nm2l));
                 }
                 break;
               }
               case plan::QS: {
                 const int d0 = rc.q_sent - g0;
-                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+                const float c0 = fmaf(rc.relX, LOG2E, nm2l), c1 = fmaf(rc.relX1, LOG2E, nm2l);
 #pragma unroll
-                for (int jj = 0; jj < W; ++jj) t[jj] = fmaf(t[jj], a.scale, d0 == jj ? c1 : c0);
+                for (int jj = 0; jj < W; ++jj) e[jj] = fmaf(e[jj], scale2, d0 == jj ? c1 : c0);
                 break;
               }
               default: {   // KS
-                const float c0 = rc.relX + mterm, c1 = rc.relX1 + mterm;
+                const float c0 = fmaf(rc.relX, LOG2E, nm2l), c1 = fmaf(rc.relX1, LOG2E, nm2l);
 #pragma unroll
-                for (int jj = 0; jj < W; ++jj) t[jj] = fmaf(t[jj], a.scale, cp->cs[part * W + jj] == i ? c1 : c0);
+                for (int jj = 0; jj < W; ++jj) e[jj] = fmaf(e[jj], scale2, cp->cs[part * W + jj] == i ? c1 : c0);
                 break;
               }
             }
             if (mask_pe) {
 #pragma unroll
-              for (int jj = 0; jj < W; ++jj) t[jj] += (cp->ce[part * W + jj] == rc.q_e) ? 0.f : a.neg;
+              for (int jj = 0; jj < W; ++jj)
+                e[jj] = (cp->ce[part * W + jj] == rc.q_e || e[jj] == -INFINITY) ? e[jj] : lpm;
+            } else if (mre) {
+#pragma unroll
+              for (int jj = 0; jj < W; ++jj) e[jj] = (masked && e[jj] != -INFINITY) ? lpm : e[jj];
             }
             float t0 = 0.f, t1 = 0.f;
 #pragma unroll
             for (int x = 0; x < W; x += 2) {
-              const float p0 = ex2(fmaf(t[x], LOG2E, -m2l));   // dead: t = -inf -> 0
-              const float p1 = ex2(fmaf(t[x + 1], LOG2E, -m2l));
+              const float p0 = ex2(e[x]);
+              const float p1 = ex2(e[x + 1]);
               ds[x] = p0 * (__uint_as_float(w[x]) - delta);
               ds[x + 1] = p1 * (__uint_as_float(w[x + 1]) - delta);
               t0 += ds[x];
@@ -653,13 +668,25 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               else if (ccls == plan::C_NEG) accN += tot;
               else if (ccls == plan::C_CROSS) accX += tot;
             } else if (mode == plan::DIAG) {
+              // slot = clamp(d0 + x, 0, 2D).  The clamped ends are the constant classes (offset <= -D,
+              // offset >= D): register accumulators.  Every interior slot belongs to exactly one key
+              // of the row (offset = slot - D), so it is written once: a plain store, no
+              // read-modify-write chain through shared memory.
               const int d0 = g0 - i + sc.D;
               float* base = bin + row;
+              float eN0 = 0.f, eN1 = 0.f, eP0 = 0.f, eP1 = 0.f;
 #pragma unroll
-              for (int x = 0; x < W; ++x) {
-                const int sl = min(max(d0 + x, 0), 2 * sc.D);
-                base[sl * TM] += ds[x];
+              for (int x = 0; x < W; x += 2) {
+                const int s0 = d0 + x, s1 = d0 + x + 1;
+                eN0 += (s0 <= 0) ? ds[x] : 0.f;
+                eN1 += (s1 <= 0) ? ds[x + 1] : 0.f;
+                eP0 += (s0 >= 2 * sc.D) ? ds[x] : 0.f;
+                eP1 += (s1 >= 2 * sc.D) ? ds[x + 1] : 0.f;
+                if (s0 > 0 && s0 < 2 * sc.D) base[s0 * TM] = ds[x];
+                if (s1 > 0 && s1 < 2 * sc.D) base[s1 * TM] = ds[x + 1];
               }
+              accN += eN0 + eN1;
+              accP += eP0 + eP1;
             } else if (mode == plan::QS) {
               const int d0 = rc.q_sent - g0;
               float sp = 0.f;
@@ -728,15 +755,23 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           *reinterpret_cast<uint4*>(smem + SM_A + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = pk4;
           // bias partial: sum over the 32 rows of this warp, one value per id
           float* bs = reinterpret_cast<float*>(smem + SM_BS) + quad * 64 + c0;
+          {
+            // 8 values per lane -> 8 sums over the 32 lanes with 9 shuffles: every exchange step
+            // halves the number of values a lane carries (lane bits 4, 3, 2 select the id)
+            const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0;
+            float b4[4], b2[2];
 #pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            float v = row_ok ? w8[x] : 0.f;
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if (lane == 0) bs[x] = v;
+            for (int k = 0; k < 4; ++k) {
+              const float lo = row_ok ? w8[k] : 0.f, hi = row_ok ? w8[k + 4] : 0.f;
+              b4[k] = (h4 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h4 ? lo : hi, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              b2[k] = (h3 ? b4[k + 2] : b4[k]) + __shfl_xor_sync(0xffffffffu, h3 ? b4[k] : b4[k + 2], 8);
+            float r = (h2 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? b2[0] : b2[1], 4);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            if ((lane & 3) == 0) bs[(h4 ? 4 : 0) + (h3 ? 2 : 0) + (h2 ? 1 : 0)] = r;
           }
         } else if (row_ok) {
           float* dst = a.dallrel + srow * R + c0;
@@ -819,12 +854,14 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ============================================================================================
 namespace bk {
 constexpr int NST = 3;
+// (plan ring: NPL slots, shared constant above)
+constexpr int RSMAX = 64 + 4;                   // floats per row record (header + R <= 64 ids)
 constexpr int SM_K = 0;                         // 16 KB
 constexpr int SM_V = SM_K + TM * 128;           // 16 KB
 constexpr int SM_QD = SM_V + TM * 128;          // NST x (Q 8 KB + dO 8 KB)
-constexpr int SM_RS = SM_QD + NST * 2 * TN * 128;       // NST x [64] float4 rowstat
-constexpr int SM_RELQ = SM_RS + NST * TN * 16;          // NST x [64][64] f32 allrel rows
-constexpr int SM_BAR = SM_RELQ + NST * TN * 64 * 4;
+constexpr int SM_REC = SM_QD + NST * 2 * TN * 128;      // NST x [64] row records (see TcBwdQParams::rec_ws)
+constexpr int SM_PLAN = SM_REC + NST * TN * RSMAX * 4;  // NPL x ChunkPlan
+constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
 constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
 constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320;
 
@@ -832,14 +869,15 @@ struct Bars {
   uint64_t kv_full;
   uint64_t qd_full[NST], qd_empty[NST];
   uint64_t sdp_full[2], pds_full[2], acc_full;
+  uint64_t pl_full[NPL], pl_empty[NPL];
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 256, "barrier block");
 }  // namespace bk
 
 struct TcQuerySource {
   QuerySource q;
-  const float4* rowstat;  // [B, H, lp]
-  const float* allrel_ws; // [B, H, lp, rw]
+  const float* rec_ws;    // [B, H, lp, rw + 4] row records written by the query-centric pass
   int lp, rw;
 };
 
@@ -859,7 +897,7 @@ __device__ __forceinline__ SrcRange src_range(const TcQuerySource& s, int j0) {
   SrcRange r;
   const int lq = s.q.rows.len;
   if (s.q.band) {
-    r.ib = max(0, j0 - s.q.radius) & ~3;   // 16-byte aligned bulk copies of the row records
+    r.ib = max(0, j0 - s.q.radius) & ~63;  // query chunks coincide with the 64-row record blocks
     r.ie = min(lq, j0 + TM + s.q.radius);
   } else {
     r.ib = 0;
@@ -869,132 +907,73 @@ __device__ __forceinline__ SrcRange src_range(const TcQuerySource& s, int j0) {
   return r;
 }
 
-// ---- column-centric scoring: the thread owns KEY row j, the 32 columns of a group are queries.
-// Same warp-uniform classification idea as tc_rowscore.cuh with the roles swapped: query-side
-// scalars are lane-held, the relative term comes from the staged per-query rows relq[ii][id].
-namespace colscore {
-using rowscore::GMode;
-using rowscore::GM_DEAD; using rowscore::GM_FAST; using rowscore::GM_EDGE; using rowscore::GM_DIAG;
-using rowscore::GM_QS; using rowscore::GM_KS; using rowscore::GM_GEN;
-
-struct SrcCtx {          // warp-uniform, one per query source
-  const TcQuerySource* src;
-  int ib, ie;            // query range of this key tile
+// ---- key-centric contexts (rows = keys, columns = queries) -------------------------------------
+struct SrcC {            // warp-uniform, one per query source
+  const Side* sd;
+  int ie;                // end of the live query range
   int R, D, rw;
   bool band;
   int radius;
   int mask_rule, id_rule;
 };
-struct KeyCtx {          // per thread
-  int j, row;
-  bool key_ok;
+struct KeyC {            // per thread and source
   int k_e, k_sent;
 };
-struct QLanes {          // lane l holds the scalars of query (g0 + l)
-  int qe_l, qs_l;
-};
-struct Plan {
-  int mode;
-  int cid;               // id of the constant relative class (-1: none)
-  float mrow;
-  bool mask_pe;
-};
 
-__device__ __forceinline__ QLanes load_q_lanes(const SrcCtx& sc, int b, int g0, int lane) {
-  QLanes ql{0, -1};
-  const Side& sd = sc.src->q.side;
-  const int i = g0 + lane;
-  if (i >= 0 && i < sc.src->q.rows.len) {
-    if (sc.mask_rule == MR_EXAMPLE_ID) ql.qe_l = __ldg(sd.q_eid + (int64_t)b * sd.q_len + i);
-    if (sc.id_rule == IDR_CROSS_QSENT) ql.qs_l = __ldg(sd.sent + (int64_t)b * sd.sent_len + i);
-  }
-  return ql;
+__device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRange& r) {
+  SrcC sc;
+  sc.sd = &src.q.side;
+  sc.ie = r.ie;
+  sc.R = src.q.rows.R;
+  sc.D = src.q.side.max_distance;
+  sc.rw = src.rw + 4;   // record stride (floats)
+  sc.band = src.q.band != 0;
+  sc.radius = src.q.radius;
+  sc.mask_rule = src.q.side.mask_rule;
+  sc.id_rule = sc.R > 0 ? src.q.side.id_rule : IDR_NONE;
+  return sc;
 }
 
-__device__ __forceinline__ void init_key(KeyCtx& kc, const SrcCtx& sc, int b) {
-  const Side& sd = sc.src->q.side;
+__device__ __forceinline__ plan::PSeg make_kv_pseg(const TcQuerySource& src, const SrcRange& r) {
+  plan::PSeg s;
+  const Side& sd = src.q.side;
+  s.c_begin = r.ib;
+  s.c_end = r.ie;
+  s.c_len = src.q.rows.len;
+  s.band = src.q.band != 0;
+  s.radius = src.q.radius;
+  s.mask_rule = sd.mask_rule;
+  s.id_rule = src.q.rows.R > 0 ? sd.id_rule : IDR_NONE;
+  s.D = sd.max_distance;
+  s.R = src.q.rows.R;
+  s.diag_ok = (2 * s.D + 1 <= s.R);   // the key-centric DIAG form gathers by id: no slot table involved
+  s.rows_are_keys = true;
+  s.c_eid = sd.q_eid;
+  s.c_eid_stride = sd.q_len;
+  // QSENT: the sentence id belongs to the query = column side; KSENT: to the key = row side
+  s.col_sent = (s.id_rule == IDR_CROSS_QSENT);
+  s.c_sent = s.col_sent ? sd.sent : nullptr;
+  s.c_sent_stride = sd.sent_len;
+  return s;
+}
+
+__device__ __forceinline__ void key_loads(KeyC& kc, const SrcC& sc, int b, int j, bool key_ok) {
   kc.k_e = 0;
   kc.k_sent = -1;
-  if (kc.key_ok && sc.mask_rule == MR_EXAMPLE_ID) kc.k_e = __ldg(sd.k_eid + (int64_t)b * sd.k_len + kc.j);
-  if (kc.key_ok && sc.id_rule == IDR_CROSS_KSENT) kc.k_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + kc.j);
+  if (key_ok && sc.mask_rule == MR_EXAMPLE_ID) kc.k_e = __ldg(sc.sd->k_eid + (int64_t)b * sc.sd->k_len + j);
+  if (key_ok && sc.id_rule == IDR_CROSS_KSENT) kc.k_sent = __ldg(sc.sd->sent + (int64_t)b * sc.sd->sent_len + j);
 }
 
-// a = first key row of the warp, g0 = first query of the group.  off = key - query.
-template <int W>
-__device__ __forceinline__ Plan classify(const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql, int a, int g0,
-                                         int lane, float neg, int sub) {
-  Plan pl;
-  pl.cid = -1;
-  pl.mrow = 0.f;
-  pl.mask_pe = false;
-  const int o_min = a - (g0 + W - 1), o_max = a + 31 - g0;
-  const bool dead = g0 >= sc.ie || (sc.band && (o_min > sc.radius || o_max < -sc.radius));
-  if (dead) {
-    pl.mode = GM_DEAD;
-    return pl;
-  }
-  const bool all_live = (g0 + W - 1 < sc.ie) && (!sc.band || (o_min >= -sc.radius && o_max <= sc.radius));
-  bool gen = false;
-  if (sc.mask_rule == MR_EXPLICIT) {
-    gen = true;
-  } else if (sc.mask_rule == MR_EXAMPLE_ID) {
-    const int qe0 = __shfl_sync(0xffffffffu, ql.qe_l, sub);
-    const bool lane_oob = (g0 - sub + lane >= sc.ie) || (W < 32 && (lane < sub || lane >= sub + W));
-    const bool uni = __all_sync(0xffffffffu, lane_oob || ql.qe_l == qe0);
-    pl.mask_pe = !uni;
-    pl.mrow = uni ? ((kc.k_e == qe0) ? 0.f : neg) : 0.f;
-  }
-  int rcls = 0;  // 0 const, 1 diag, 2 qs, 3 ks, 4 generic
-  switch (sc.id_rule) {
-    case IDR_NONE:
-      break;
-    case IDR_1D:
-      if (2 * sc.D + 1 > sc.R) rcls = 4;
-      else if (o_min >= sc.D) pl.cid = sc.D;
-      else if (o_max <= -sc.D) pl.cid = 2 * sc.D;
-      else rcls = 1;
-      break;
-    case IDR_CROSS_QSENT:
-      if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
-      pl.cid = 2 * sc.D + 1;
-      if (__any_sync(0xffffffffu, ql.qs_l >= a && ql.qs_l <= a + 31 && (W == 32 || (lane >= sub && lane < sub + W)))) rcls = 2;
-      break;
-    case IDR_CROSS_KSENT:
-      if (2 * sc.D + 2 >= sc.R) { rcls = 4; break; }
-      pl.cid = 2 * sc.D + 1;
-      if (__any_sync(0xffffffffu, kc.k_sent >= g0 && kc.k_sent < g0 + W)) rcls = 3;
-      break;
-    default:
-      rcls = 4;
-  }
-  if (gen || rcls == 4) {
-    pl.mode = GM_GEN;
-    pl.mask_pe = false;
-  } else if (rcls == 0) {
-    pl.mode = all_live ? GM_FAST : GM_EDGE;
-  } else if (!all_live) {
-    pl.mode = GM_GEN;
-    pl.mask_pe = false;
-  } else {
-    pl.mode = rcls == 1 ? GM_DIAG : (rcls == 2 ? GM_QS : GM_KS);
-  }
-  return pl;
-}
-
-// Generic per-element evaluation; returns the score or -inf when (i, j) is dead.
-__device__ __forceinline__ float score_generic(float x, const SrcCtx& sc, const KeyCtx& kc, const QLanes& ql,
-                                               int b, int g0, int ii, const float* relq, float scale, float neg,
-                                               int sub) {
-  const Side& sd = sc.src->q.side;
-  const int i = g0 + ii;
-  const int off = kc.j - i;
-  const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, sub + ii);
-  const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, sub + ii);
-  const bool live = kc.key_ok && i < sc.ie && (!sc.band || (off <= sc.radius && off >= -sc.radius));
-  if (!live) return -INFINITY;
-  const int col = sc.band ? off + sc.radius : kc.j;
-  bool ok = true;
-  int id = -1;
+// Generic per-element evaluation: liveness, mask, relative id (or -1).
+__device__ __forceinline__ void eval_generic_kv(const SrcC& sc, const KeyC& kc, int b, int i, int j, bool key_ok,
+                                                int qe_i, int qs_i, bool& live, bool& ok, int& id) {
+  const Side& sd = *sc.sd;
+  const int off = j - i;
+  ok = true;
+  id = -1;
+  live = key_ok && i < sc.ie && (!sc.band || (off <= sc.radius && off >= -sc.radius));
+  if (!live) return;
+  const int col = sc.band ? off + sc.radius : j;
   switch (sc.mask_rule) {
     case MR_EXPLICIT: ok = __ldg(sd.mask + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col) != 0; break;
     case MR_EXAMPLE_ID: ok = (qe_i == kc.k_e); break;
@@ -1003,130 +982,40 @@ __device__ __forceinline__ float score_generic(float x, const SrcCtx& sc, const 
   switch (sc.id_rule) {
     case IDR_EXPLICIT: id = __ldg(sd.ids + (int64_t)b * sd.sb + (int64_t)i * sd.sq + col); break;
     case IDR_1D: id = rel_id_1d(off, sc.D); break;
-    case IDR_CROSS_QSENT: id = 2 * sc.D + 1 + (qs_i == kc.j ? 1 : 0); break;
+    case IDR_CROSS_QSENT: id = 2 * sc.D + 1 + (qs_i == j ? 1 : 0); break;
     case IDR_CROSS_KSENT: id = 2 * sc.D + 1 + (kc.k_sent == i ? 1 : 0); break;
-    case IDR_2D: id = rel_id_2d(i, kc.j, sd.npr, sd.core, sc.D); break;
+    case IDR_2D: id = rel_id_2d(i, j, sd.npr, sd.core, sc.D); break;
     default: break;
   }
-  const float rel = (id >= 0 && id < sc.R) ? relq[ii * sc.rw + id] : 0.f;
-  float v = fmaf(x, scale, rel);
-  if (!ok) v += neg;
-  return v;
+  if (id >= sc.R) id = -1;
 }
 
-// Scores of one 32-query group in place.  `mode` is warp-uniform; GM_GEN is handled elsewhere.
-template <int W>
-__device__ __forceinline__ void score_group(float (&t)[W], const Plan& pl, const SrcCtx& sc, const KeyCtx& kc,
-                                            const QLanes& ql, int g0, const float* relq, float scale, float neg,
-                                            int sub) {
-  const int rw = sc.rw;
-  switch (pl.mode) {
-    case GM_FAST:
-      if (pl.cid >= 0) {
-#pragma unroll
-        for (int ii = 0; ii < W; ++ii) t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid] + pl.mrow);
-      } else {
-#pragma unroll
-        for (int ii = 0; ii < W; ++ii) t[ii] = fmaf(t[ii], scale, pl.mrow);
-      }
-      break;
-    case GM_EDGE: {
-      const int d0 = kc.j - g0;  // off = d0 - ii
-      int ilo = 0, ihi = min(W, sc.ie - g0);
-      if (sc.band) {
-        ilo = max(ilo, d0 - sc.radius);
-        ihi = min(ihi, d0 + sc.radius + 1);
-      }
-      if (!kc.key_ok) ihi = ilo;
-      const unsigned span = (unsigned)max(ihi - ilo, 0);
-      const int cid = pl.cid >= 0 ? pl.cid : 0;
-      const float use = pl.cid >= 0 ? 1.f : 0.f;
-#pragma unroll
-      for (int ii = 0; ii < W; ++ii) {
-        const float v = fmaf(t[ii], scale, fmaf(use, relq[ii * rw + cid], pl.mrow));
-        t[ii] = ((unsigned)(ii - ilo) < span) ? v : -INFINITY;
-      }
-      break;
-    }
-    case GM_DIAG: {
-      const int d0 = kc.j - g0;
-#pragma unroll
-      for (int ii = 0; ii < W; ++ii) {
-        const int o = min(max(d0 - ii, -sc.D), sc.D);
-        const int id = o >= 0 ? o : sc.D - o;
-        t[ii] = fmaf(t[ii], scale, relq[ii * rw + id] + pl.mrow);
-      }
-      break;
-    }
-    case GM_QS: {
-#pragma unroll
-      for (int ii = 0; ii < W; ++ii) {
-        const int qs_i = __shfl_sync(0xffffffffu, ql.qs_l, sub + ii);
-        t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (qs_i == kc.j ? 1 : 0)] + pl.mrow);
-      }
-      break;
-    }
-    case GM_KS: {
-      const int sp = kc.k_sent - g0;
-#pragma unroll
-      for (int ii = 0; ii < W; ++ii)
-        t[ii] = fmaf(t[ii], scale, relq[ii * rw + pl.cid + (sp == ii ? 1 : 0)] + pl.mrow);
-      break;
-    }
-    default:
-      return;
-  }
-  if (pl.mask_pe) {
-#pragma unroll
-    for (int ii = 0; ii < W; ++ii) {
-      const int qe_i = __shfl_sync(0xffffffffu, ql.qe_l, sub + ii);
-      t[ii] += (qe_i == kc.k_e) ? 0.f : neg;
-    }
-  }
-}
-
-// GM_GEN: real loop, TMEM as scratch.  Leaves p (fp32) in the S^T column and ds in the dP^T column.
-template <int W>
-__device__ __forceinline__ void group_generic_tmem(uint32_t t_s, uint32_t t_dp, const SrcCtx& sc, const KeyCtx& kc,
-                                                   const QLanes& ql, int b, int g0, const float4* rs,
-                                                   const float* relq, float scale, float neg, int sub) {
-#pragma unroll 1
-  for (int ii = 0; ii < W; ++ii) {
-    const uint32_t raw = tmem_ld1(t_s + ii);
-    const uint32_t dpr = tmem_ld1(t_dp + ii);
-    tmem_wait_ld();
-    const float t = score_generic(__uint_as_float(raw), sc, kc, ql, b, g0, ii, relq, scale, neg, sub);
-    float pv = 0.f, ds = 0.f;
-    if (t != -INFINITY) {
-      const float4 st = rs[ii];
-      pv = ex2(fmaf(t, LOG2E, -st.x)) * st.y;
-      ds = pv * (__uint_as_float(dpr) - st.z);
-    }
-    tmem_st1(t_s + ii, __float_as_uint(pv));
-    tmem_st1(t_dp + ii, __float_as_uint(ds));
-  }
-  tmem_wait_st();
-}
-}  // namespace colscore
-
-// NP threads per row inside a warp set; SETS warp sets take alternate chunks (S^T / dP^T are
-// double-buffered by chunk parity, so set s simply owns buffer s).
 template <int NP, int SETS>
-__global__ void __launch_bounds__(nthreads<NP * SETS>(), 1)
+constexpr int bk_threads() { return (4 * NP * SETS + 3) * 32; }
+
+// NP threads per key row inside a warp set (each owns W = 64 / NP query columns of a chunk); SETS
+// warp sets take alternate chunks (S^T / dP^T are double-buffered by chunk parity, so set s owns
+// buffer s).  A planner warp classifies the (quadrant, group) pairs of each chunk (tc_plan.cuh); the
+// per-query constants arrive exponent-ready in the row records the query-centric pass published
+// (TcBwdQParams::rec_ws), so the common element costs
+//     p = ex2(fma(x, scale*log2e, rec[i][4 + id])),  ds = p * (dp - rec[i][2]).
+template <int NP, int SETS>
+__global__ void __launch_bounds__(bk_threads<NP, SETS>(), 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
                  const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_do1,
-                 const TcBwdKVParams p) {
+                 const __grid_constant__ TcBwdKVParams p) {
   using namespace bk;
   constexpr int W = 64 / NP;
   constexpr int NEW = 128 * NP;                  // elementwise threads per set
-  constexpr int WP = 4 * NP * SETS, WM = 4 * NP * SETS + 1;
+  constexpr int WP = 4 * NP * SETS, WM = WP + 1, WH = WP + 2;
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
   // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
+  plan::ChunkPlan* plans = reinterpret_cast<plan::ChunkPlan*>(smem + SM_PLAN);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TM;
 
@@ -1135,6 +1024,10 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars->qd_full[s], 1);
       mbar_init(&bars->qd_empty[s], 1);
+    }
+    for (int s = 0; s < NPL; ++s) {
+      mbar_init(&bars->pl_full[s], 1);
+      mbar_init(&bars->pl_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->sdp_full[s], 1);
@@ -1165,16 +1058,14 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         const bool first = c < r0.n;
         const TcQuerySource& src = first ? p.src[0] : p.src[1];
         const int q0 = first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN;
-        const int rw = src.rw;
+        const int rs = src.rw + 4;
         uint8_t* qs = smem + SM_QD + st * (2 * TN * 128);
-        const int64_t prow = (int64_t)(b * p.H + h) * src.lp + q0;
-        const uint32_t rel_bytes = rw > 0 ? TN * rw * 4 : 0;
-        mbar_arrive_expect_tx(&bars->qd_full[st], 2 * TN * 128 + TN * 16 + rel_bytes);
+        const int64_t prow = ((int64_t)(b * p.H + h) * (src.lp >> 6) + (q0 >> 6)) * 64;   // record block of q0
+        const uint32_t rec_bytes = TN * rs * 4;
+        mbar_arrive_expect_tx(&bars->qd_full[st], 2 * TN * 128 + rec_bytes);
         tma_load_4d(qs, first ? &map_q0 : &map_q1, &bars->qd_full[st], 0, q0, h, b);
         tma_load_4d(qs + TN * 128, first ? &map_do0 : &map_do1, &bars->qd_full[st], 0, q0, h, b);
-        bulk_g2s(smem + SM_RS + st * TN * 16, src.rowstat + prow, TN * 16, &bars->qd_full[st]);
-        if (rel_bytes)
-          bulk_g2s(smem + SM_RELQ + st * TN * 64 * 4, src.allrel_ws + prow * rw, rel_bytes, &bars->qd_full[st]);
+        bulk_g2s(smem + SM_REC + st * TN * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
       }
     }
   } else if (warp == WM) {
@@ -1187,6 +1078,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       for (int c = 0; c <= nchunks; ++c) {
         if (c < nchunks) {
           const int st = c % NST;
+          mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
           mbar_wait(&bars->qd_full[st], (c / NST) & 1);
           TRACE(2, 4 * c);
           tc_fence_after_sync();
@@ -1208,6 +1100,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           mbar_wait(&bars->pds_full[pc & 1], (pc >> 1) & 1);
           TRACE(2, 4 * pc + 2);
           tc_fence_after_sync();
+          mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
           const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
           const uint32_t do_addr = q_addr + TN * 128;
 #pragma unroll
@@ -1224,58 +1117,82 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         }
       }
     }
+  } else if (warp == WH) {
+    // ===================== planner =====================
+    const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0);
+    const plan::PSeg ps1 = make_kv_pseg(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
+    const Side* ks_side = nullptr;   // row-side (key) sentence ids: rule KSENT
+    if (ps0.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[0].q.side;
+    if (p.nsrc > 1 && ps1.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[1].q.side;
+    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.ib, r1.ib, b, j0, ks_side ? ks_side->sent : nullptr,
+                                ks_side ? ks_side->sent_len : 0, p.len, plans, bars->pl_full, bars->pl_empty, lane);
   } else {
-    using namespace colscore;
-    const int row = (warp & 3) * 32 + lane;
+    // ===================== elementwise warps =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
     const int set = warp / (4 * NP);            // which chunk parity this warp serves
     const int part = (warp >> 2) % NP;
-    const int win = (part * W) / 32, sub = (part * W) % 32;
+    const int grp = (part * W) / 32;            // which 32-column group of the chunk the slice lies in
     const int j = j0 + row;
     const bool key_ok = j < p.len;
-    const int wrow0 = j0 + (warp & 3) * 32;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    auto make_src = [&](const TcQuerySource& src, const SrcRange& r) {
-      SrcCtx sc;
-      sc.src = &src;
-      sc.ib = r.ib;
-      sc.ie = r.ie;
-      sc.R = src.q.rows.R;
-      sc.D = src.q.side.max_distance;
-      sc.rw = src.rw;
-      sc.band = src.q.band != 0;
-      sc.radius = src.q.radius;
-      sc.mask_rule = src.q.side.mask_rule;
-      sc.id_rule = sc.R > 0 ? src.q.side.id_rule : IDR_NONE;
-      return sc;
-    };
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const float scale2 = p.scale * LOG2E;
     // One call per query source (inlined twice: no per-field selects inside the chunk loop).
     // Chunks [c_begin, c_end) belong to this source; this warp set handles those with c % SETS == set.
-    auto run_chunks = [&](const SrcCtx sc, const KeyCtx kc, int c_begin, int c_end, int ib) {
+    auto run_chunks = [&](const SrcC sc, const KeyC kc, int c_begin, int c_end, int ib) {
       int c = c_begin + ((set - c_begin) % SETS + SETS) % SETS;
-      if (c >= c_end) return;
-      QLanes ql = load_q_lanes(sc, b, ib + (c - c_begin) * TN + 32 * win, lane);
+      const bool mre = sc.mask_rule == MR_EXAMPLE_ID;
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
         const int st = c % NST;
-        const int g0 = ib + (c - c_begin) * TN + part * W;
+        const int g0 = ib + (c - c_begin) * TN + part * W;   // first query of this thread's slice
         const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
         const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
-        QLanes nl{0, -1};
-        if (c + SETS < c_end) nl = load_q_lanes(sc, b, ib + (c + SETS - c_begin) * TN + 32 * win, lane);
-        const Plan pl = classify<W>(sc, kc, ql, wrow0, g0, lane, p.neg, sub);
+        const plan::ChunkPlan* cp = plans + (c % NPL);
         if (tid == 0) TRACE(0, 4 * c);
-        mbar_wait_warp(&bars->qd_full[st], (c / NST) & 1);   // rowstat / allrel rows of this chunk
+        // the MMA warp issued S^T_c / dP^T_c only after plan c had been published and the row
+        // records of the chunk had landed
         mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
         if (tid == 0) TRACE(0, 4 * c + 1);
         tc_fence_after_sync();
-        const float4* rs = reinterpret_cast<const float4*>(smem + SM_RS + st * TN * 16) + part * W;
-        const float* relq = reinterpret_cast<const float*>(smem + SM_RELQ + st * TN * 64 * 4) + part * W * sc.rw;
+        // record fields of this thread's query slice: field f of query x at rec[f * 64 + x]
+        const float* rec = reinterpret_cast<const float*>(smem + SM_REC + st * TN * RSMAX * 4) + part * W;
+        const int32_t* ce = cp->ce + part * W;
+        const int32_t* cs = cp->cs + part * W;
+        const uint32_t w0 = cp->q[quad][grp];
+        const int ce0 = (int)cp->q[quad][2 + grp];
+        const int mode = (int)(w0 & 0xffu);
+        const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
+        const bool masked = mre && !mask_pe && (kc.k_e != ce0);
+        const int ccls = (int)((w0 >> 8) & 0xffu);
+        // record field of the group's constant class
+        const int coff = ccls == plan::C_POS ? 4 + sc.D : (ccls == plan::C_NEG ? 4 + 2 * sc.D : (ccls == plan::C_CROSS ? 5 + 2 * sc.D : 0));
         uint32_t p_pk[W / 2], ds_pk[W / 2];
-        if (pl.mode == GM_DEAD) {
+        if (mode == plan::DEAD) {
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
-        } else if (pl.mode == GM_GEN) {
-          group_generic_tmem<W>(t_s, t_dp, sc, kc, ql, b, g0, rs, relq, p.scale, p.neg, sub);
+        } else if (mode == plan::GEN) {
+          // real loop, TMEM as dynamically indexed scratch: one copy of the generic code.
+          // Leaves p (fp32) in the S^T column and ds in the dP^T column.
+#pragma unroll 1
+          for (int ii = 0; ii < W; ++ii) {
+            const uint32_t raw = tmem_ld1(t_s + ii);
+            const uint32_t dpr = tmem_ld1(t_dp + ii);
+            tmem_wait_ld();
+            bool live, ok;
+            int id;
+            eval_generic_kv(sc, kc, b, g0 + ii, j, key_ok, ce[ii], cs[ii], live, ok, id);
+            float pv = 0.f, ds = 0.f;
+            if (live) {
+              const float* r = rec + ii;
+              pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * 64]) : r[64]);
+              ds = pv * (__uint_as_float(dpr) - r[128]);
+            }
+            __syncwarp();   // the generic evaluation diverges per row; tcgen05.st needs the converged warp
+            tmem_st1(t_s + ii, __float_as_uint(pv));
+            tmem_st1(t_dp + ii, __float_as_uint(ds));
+          }
+          tmem_wait_st();
           uint32_t v[W];
           tmem_ldN(t_s, v);
           tmem_wait_ld();
@@ -1286,45 +1203,81 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
         } else {
-          float t[W];
-          uint32_t v[W];
+          uint32_t v[W], w[W];
           tmem_ldN(t_s, v);
+          tmem_ldN(t_dp, w);
           tmem_wait_ld();
-#pragma unroll
-          for (int x = 0; x < W; ++x) t[x] = __uint_as_float(v[x]);
-          score_group<W>(t, pl, sc, kc, ql, g0, relq, p.scale, p.neg, sub);
-          tmem_ldN(t_dp, v);
-          tmem_wait_ld();
-          if (pl.mode == GM_EDGE) {   // dead columns may carry garbage row records: guarded variant
+          // unmasked: exponent = x * scale2 + field(4 + id); masked: the per-query constant field 1
+          const float* dl = rec + 2 * 64;
+          if (mode == plan::FAST) {
+            const float gmul = masked ? 0.f : scale2;
+            const float* cc = rec + (masked ? 1 : coff) * 64;
 #pragma unroll
             for (int x = 0; x < W / 2; ++x) {
-              float pv[2], dsv[2];
-#pragma unroll
-              for (int y = 0; y < 2; ++y) {
-                const int ii = 2 * x + y;
-                const float4 r4 = rs[ii];
-                const float e = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
-                const float d = e * (__uint_as_float(v[ii]) - r4.z);
-                const bool dead = (t[ii] == -INFINITY);
-                pv[y] = dead ? 0.f : e;
-                dsv[y] = dead ? 0.f : d;
-              }
-              p_pk[x] = pack_bf16x2(pv[0], pv[1]);
-              ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
+              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, cc[2 * x]));
+              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, cc[2 * x + 1]));
+              p_pk[x] = pack_bf16x2(p0, p1);
+              ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
             }
           } else {
+            // 1. exponent per element, in place (one code copy per form: `mode` is warp-uniform)
+            float t[W];
+            const int d0 = j - g0;   // offset(key - query) = d0 - x
+            if (mode == plan::EDGE) {
+              const float* cc = rec + coff * 64;
 #pragma unroll
-            for (int x = 0; x < W / 2; ++x) {
-              float pv[2], dsv[2];
+              for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, cc[x]);
+            } else if (mode == plan::DIAG) {
 #pragma unroll
-              for (int y = 0; y < 2; ++y) {
-                const int ii = 2 * x + y;
-                const float4 r4 = rs[ii];   // (m*log2e, 1/l, delta, -): warp-broadcast LDS.128
-                pv[y] = ex2(fmaf(t[ii], LOG2E, -r4.x)) * r4.y;
-                dsv[y] = pv[y] * (__uint_as_float(v[ii]) - r4.z);
+              for (int x = 0; x < W; ++x) {
+                const int o = min(max(d0 - x, -sc.D), sc.D);
+                t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * 64 + x]);
               }
-              p_pk[x] = pack_bf16x2(pv[0], pv[1]);
-              ds_pk[x] = pack_bf16x2(dsv[0], dsv[1]);
+            } else {
+              const float* c0 = rec + (5 + 2 * sc.D) * 64;
+              if (mode == plan::QS) {          // row-side sentence: key j belongs to query (k_sent)
+                const int sp = kc.k_sent - g0;
+#pragma unroll
+                for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(sp == x ? 64 : 0) + x]);
+              } else {                         // KS: column-side sentence: query x's sentence is key j
+#pragma unroll
+                for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(cs[x] == j ? 64 : 0) + x]);
+              }
+            }
+            // 2. masked elements take the per-query constant (field 1)
+            const float* lp = rec + 64;
+            if (mask_pe) {
+#pragma unroll
+              for (int x = 0; x < W; ++x) t[x] = (ce[x] != kc.k_e) ? lp[x] : t[x];
+            } else if (mre && __any_sync(0xffffffffu, masked)) {
+#pragma unroll
+              for (int x = 0; x < W; ++x) t[x] = masked ? lp[x] : t[x];
+            }
+            // 3. probabilities; EDGE: dead columns may carry garbage records -> select, not multiply
+            if (mode == plan::EDGE) {
+              int ilo = 0, ihi = min(W, sc.ie - g0);
+              if (sc.band) {
+                ilo = max(ilo, d0 - sc.radius);
+                ihi = min(ihi, d0 + sc.radius + 1);
+              }
+              if (!key_ok) ihi = ilo;
+              const unsigned span = (unsigned)max(ihi - ilo, 0);
+#pragma unroll
+              for (int x = 0; x < W / 2; ++x) {
+                const bool l0 = (unsigned)(2 * x - ilo) < span, l1 = (unsigned)(2 * x + 1 - ilo) < span;
+                const float p0 = l0 ? ex2(t[2 * x]) : 0.f, p1 = l1 ? ex2(t[2 * x + 1]) : 0.f;
+                const float e0 = l0 ? p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]) : 0.f;
+                const float e1 = l1 ? p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]) : 0.f;
+                p_pk[x] = pack_bf16x2(p0, p1);
+                ds_pk[x] = pack_bf16x2(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < W / 2; ++x) {
+                const float p0 = ex2(t[2 * x]), p1 = ex2(t[2 * x + 1]);
+                p_pk[x] = pack_bf16x2(p0, p1);
+                ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
+              }
             }
           }
         }
@@ -1335,18 +1288,16 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         tc_fence_before_sync();
         mbar_arrive(&bars->pds_full[c & 1]);
         if (tid == 0) TRACE(0, 4 * c + 3);
-        ql = nl;
       }
     };
     {
-      KeyCtx kc;
-      kc.j = j; kc.row = row; kc.key_ok = key_ok;
-      const SrcCtx sc0 = make_src(p.src[0], r0);
-      init_key(kc, sc0, b);
+      KeyC kc;
+      const SrcC sc0 = make_srcc(p.src[0], r0);
+      key_loads(kc, sc0, b, j, key_ok);
       run_chunks(sc0, kc, 0, r0.n, r0.ib);
       if (p.nsrc > 1) {
-        const SrcCtx sc1 = make_src(p.src[1], r1);
-        init_key(kc, sc1, b);
+        const SrcC sc1 = make_srcc(p.src[1], r1);
+        key_loads(kc, sc1, b, j, key_ok);
         run_chunks(sc1, kc, r0.n, nchunks, r1.ib);
       }
     }
@@ -1389,10 +1340,10 @@ inline int pad4(int r) { return (r + 3) / 4 * 4; }
 
 }  // namespace
 
-// Workspace of one row set for the tcgen05 backward (rowstat + allrel), bytes.
+// Workspace of one row set for the tcgen05 backward (rowstat + row records), bytes.
 size_t tc_bwd_rows_ws_bytes(int B, int H, int len, int R) {
   const size_t rows = (size_t)B * H * pad_rows(len);
-  return align256(rows * sizeof(float4)) + align256(rows * pad4(R > 0 ? R : 0) * sizeof(float) + 256);
+  return align256(rows * sizeof(float4)) + align256(rows * (pad4(R > 0 ? R : 0) + 4) * sizeof(float) + 256);
 }
 
 bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d) {
@@ -1433,7 +1384,7 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   char* w = reinterpret_cast<char*>(ws);
   const size_t rows = (size_t)a.B * a.H * p.lp;
   p.rowstat = reinterpret_cast<float4*>(w);
-  p.allrel_ws = reinterpret_cast<float*>(w + align256(rows * sizeof(float4)));
+  p.rec_ws = reinterpret_cast<float*>(w + align256(rows * sizeof(float4)));
   CUtensorMap mq, mdo, mk0, mv0, mk1, mv1, me;
   int e = 0;
   e |= make_qkv_tensor_map(&mq, a.rows.q.ptr, a.rows.q.sb, a.rows.q.sl, a.rows.q.sh, a.B, a.rows.len, a.H, TM);
@@ -1496,8 +1447,7 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
     t.rw = pad4(q.rows.R);
     char* w = reinterpret_cast<char*>(ws[s < a.nsrc ? s : 0]);
     const size_t rows = (size_t)a.B * a.H * t.lp;
-    t.rowstat = reinterpret_cast<const float4*>(w);
-    t.allrel_ws = reinterpret_cast<const float*>(w + align256(rows * sizeof(float4)));
+    t.rec_ws = reinterpret_cast<const float*>(w + align256(rows * sizeof(float4)));
     e |= make_qkv_tensor_map(&mq[s], q.rows.q.ptr, q.rows.q.sb, q.rows.q.sl, q.rows.q.sh, a.B, lq, a.H, TN);
     e |= make_qkv_tensor_map(&mdo[s], q.d_out.ptr, q.d_out.sb, q.d_out.sl, q.d_out.sh, a.B, lq, a.H, TN);
   }
@@ -1506,9 +1456,9 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   auto src_chunks = [](const QuerySource& q) { return q.band ? (TM + 2 * q.radius + TN - 1) / TN : (q.rows.len + TN - 1) / TN; };
   const int est_chunks = src_chunks(a.src[0]) + (a.nsrc > 1 ? src_chunks(a.src[1]) : 0);
   if (est_chunks >= 16)
-    tc_bwd_kv_kernel<2, 2><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+    tc_bwd_kv_kernel<2, 2><<<grid, bk_threads<2, 2>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   else
-    tc_bwd_kv_kernel<4, 1><<<grid, nthreads<4>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+    tc_bwd_kv_kernel<4, 1><<<grid, bk_threads<4, 1>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();
 }
 

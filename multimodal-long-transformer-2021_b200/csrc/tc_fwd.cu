@@ -325,20 +325,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const Side* qs_side = nullptr;
     if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
     if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
-    const plan::RowSent rs = plan::row_sent_ranges(qs_side ? qs_side->sent : nullptr,
-                                                   qs_side ? qs_side->sent_len : 0, b, i0, a.rows.len, lane);
-    // one call per segment (inlined twice: the segment description stays in registers)
-    auto run = [&](const plan::PSeg& ps, int c_begin, int c_end, int kb) {
-      for (int c = c_begin; c < c_end; ++c) {
-        const int sl = c % NPL;
-        if (c >= NPL) mbar_wait_warp(&bars->pl_empty[sl], ((c / NPL) & 1) ^ 1);
-        plan::plan_chunk(ps, b, kb + (c - c_begin) * TN, i0, rs, plans + sl, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->pl_full[sl]);
-      }
-    };
-    run(ps0, 0, r0.n, r0.kb);
-    if (a.nseg > 1) run(ps1, r0.n, nchunks, r1.kb);
+    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.kb, r1.kb, b, i0, qs_side ? qs_side->sent : nullptr,
+                                qs_side ? qs_side->sent_len : 0, a.rows.len, plans, bars->pl_full, bars->pl_empty, lane);
   } else if (warp < 4) {
     // ===================== softmax / epilogue (warps 0-3) =====================
     const int row = tid;
@@ -435,7 +423,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             // a masked score is cadd itself: |x * scale| < 32 is absorbed by -1e9 in fp32
             gmax = masked ? cadd : fmaf(mraw, a.scale, cadd);
             gmul = masked ? 0.f : scale2;
-            gadd = cadd * LOG2E;
+            gadd = cadd;
           } else {
             if (mode == plan::GEN) {
               // real loop, TMEM as dynamically indexed scratch: one copy of the generic code
@@ -568,7 +556,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             for (int x = 0; x < 16; ++x) pk[x] = 0u;
           } else {
             const float gmul = g ? mul1 : mul0;
-            const float gsub = (g ? add1 : add0) - mb;
+            // exponent = x * mul + add * log2e - mb with the product taken exactly (one FMA): every
+            // form then yields the same value for a score equal to the running maximum
+            const float gsub = fmaf(g ? add1 : add0, LOG2E, -mb);
             uint32_t v[32];
             tmem_ld32(t_s + 32 * g, v);
             tmem_wait_ld();
@@ -622,9 +612,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
     if (row_ok) {
-      // statistics against the TRUE maximum: (m_true, sum exp(t - m_true))
+      // statistics against the TRUE maximum: (m_true, sum exp(t - m_true)).  The exponentials were
+      // taken against mb = fl(m * log2e); r = m * log2e - mb (exact product) is the offset every term
+      // carries -- up to +-64 when the maximum is a masked score (~ -1e9) -- and is divided out.
       float2* st = reinterpret_cast<float2*>(a.stats) + ((int64_t)(b * a.H + h) * a.rows.len + i);
-      *st = make_float2(m_true, l * ex2((m - m_true) * LOG2E));
+      const float r = fmaf(m, LOG2E, -(m * LOG2E));
+      *st = make_float2(m_true, l * ex2((m - m_true) * LOG2E - r));
     }
     if (tid == 0) TRACE(0, 3);
   }

@@ -69,19 +69,30 @@ struct RowSent {
   int mn[4], mx[4];
 };
 
-// Whole warp.  col0 = first column of the chunk, row0 = first row of the tile.
-__device__ __forceinline__ void plan_chunk(const PSeg& s, int b, int col0, int row0, const RowSent& rs,
-                                           ChunkPlan* out, int lane) {
-  int e0 = 0, e1 = 0, s0 = -1, s1 = -1;
+// Per-column scalars of one chunk, one pair per lane (columns col0 + lane and col0 + 32 + lane).
+struct ColLanes {
+  int e0, e1, s0, s1;
+};
+__device__ __forceinline__ ColLanes load_col_lanes(const PSeg& s, int b, int col0, int lane) {
+  ColLanes cl{0, 0, -1, -1};
   const int j0 = col0 + lane, j1 = col0 + 32 + lane;
   if (s.mask_rule == MR_EXAMPLE_ID) {
-    if (j0 >= 0 && j0 < s.c_len) e0 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j0);
-    if (j1 >= 0 && j1 < s.c_len) e1 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j1);
+    if (j0 >= 0 && j0 < s.c_len) cl.e0 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j0);
+    if (j1 >= 0 && j1 < s.c_len) cl.e1 = __ldg(s.c_eid + (int64_t)b * s.c_eid_stride + j1);
   }
   if (s.col_sent) {
-    if (j0 >= 0 && j0 < s.c_len) s0 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j0);
-    if (j1 >= 0 && j1 < s.c_len) s1 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j1);
+    if (j0 >= 0 && j0 < s.c_len) cl.s0 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j0);
+    if (j1 >= 0 && j1 < s.c_len) cl.s1 = __ldg(s.c_sent + (int64_t)b * s.c_sent_stride + j1);
   }
+  return cl;
+}
+
+// Whole warp.  col0 = first column of the chunk, row0 = first row of the tile; `cl` = the chunk's
+// column scalars (load_col_lanes, issued a chunk ahead by the caller).
+__device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, int col0, int row0, const RowSent& rs,
+                                           ChunkPlan* out, int lane) {
+  const int e0 = cl.e0, e1 = cl.e1, s0 = cl.s0, s1 = cl.s1;
+  const int j0 = col0 + lane, j1 = col0 + 32 + lane;
   out->ce[lane] = e0;
   out->ce[32 + lane] = e1;
   out->cs[lane] = s0;
@@ -196,29 +207,74 @@ __device__ __forceinline__ void rel_table_build(uint32_t taddr, const RelMeta* m
     uint32_t v[16];
     ptx::tmem_ld16(taddr + c0, v);
     ptx::tmem_wait_ld();
+    // all loads first: the compiler cannot prove that rel_s and meta do not alias and would
+    // otherwise serialise load -> store -> load
+    RelMeta m[16];
+#pragma unroll
+    for (int x = 0; x < 16; ++x) m[x] = meta[c0 + x];   // warp-broadcast LDS.64
     float val[16];
 #pragma unroll
-    for (int x = 0; x < 16; ++x) {
-      const RelMeta m = meta[c0 + x];   // warp-broadcast LDS.64
-      val[x] = fmaf(__uint_as_float(v[x]), scale, m.bias_scaled);
-      rel_s[m.slot_off + row] = val[x];
-    }
+    for (int x = 0; x < 16; ++x) val[x] = fmaf(__uint_as_float(v[x]), scale, m[x].bias_scaled);
+#pragma unroll
+    for (int x = 0; x < 16; ++x) rel_s[m[x].slot_off + row] = val[x];
     keep(c0, val);
   }
 }
 
 // Row-side sentence ranges of the tile (whole warp; rows beyond `len` are ignored).
-__device__ __forceinline__ RowSent row_sent_ranges(const int32_t* sent, int64_t stride, int b, int row0, int len,
-                                                   int lane) {
-  RowSent rs;
+struct RowSentRaw {
+  int v[4];
+};
+__device__ __forceinline__ RowSentRaw row_sent_load(const int32_t* sent, int64_t stride, int b, int row0, int len,
+                                                    int lane) {
+  RowSentRaw r;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const int i = row0 + 32 * w + lane;
-    const int v = (sent && i < len) ? __ldg(sent + (int64_t)b * stride + i) : -1;
-    rs.mn[w] = __reduce_min_sync(0xffffffffu, v < 0 ? 0x7fffffff : v);
-    rs.mx[w] = __reduce_max_sync(0xffffffffu, v);
+    r.v[w] = (sent && i < len) ? __ldg(sent + (int64_t)b * stride + i) : -1;
+  }
+  return r;
+}
+__device__ __forceinline__ RowSent row_sent_reduce(const RowSentRaw& r) {
+  RowSent rs;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    rs.mn[w] = __reduce_min_sync(0xffffffffu, r.v[w] < 0 ? 0x7fffffff : r.v[w]);
+    rs.mx[w] = __reduce_max_sync(0xffffffffu, r.v[w]);
   }
   return rs;
+}
+
+// The planner warp's loop over the chunks of a tile (up to two column segments).  The global
+// loads of chunk c + 1 are in flight while chunk c is classified; the row-side loads overlap the
+// first chunk's.  `ring` has NPL slots guarded by pl_full / pl_empty mbarriers.
+template <int NPL, int TN>
+__device__ __forceinline__ void planner_loop(const PSeg& ps0, const PSeg& ps1, int n0, int n1, int cb0, int cb1,
+                                             int b, int row0, const int32_t* row_sent, int64_t row_sent_stride,
+                                             int row_len, ChunkPlan* ring, uint64_t* pl_full, uint64_t* pl_empty,
+                                             int lane) {
+  const int nchunks = n0 + n1;
+  if (nchunks == 0) return;
+  const RowSentRaw raw = row_sent_load(row_sent, row_sent_stride, b, row0, row_len, lane);
+  ColLanes cl = (0 < n0) ? load_col_lanes(ps0, b, cb0, lane) : load_col_lanes(ps1, b, cb1, lane);
+  const RowSent rs = row_sent_reduce(raw);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int sl = c % NPL;
+    const bool first = c < n0;
+    const int col0 = first ? cb0 + c * TN : cb1 + (c - n0) * TN;
+    ColLanes nl{0, 0, -1, -1};
+    if (c + 1 < nchunks) {
+      if (c + 1 < n0) nl = load_col_lanes(ps0, b, cb0 + (c + 1) * TN, lane);
+      else nl = load_col_lanes(ps1, b, cb1 + (c + 1 - n0) * TN, lane);
+    }
+    if (c >= NPL) ptx::mbar_wait_warp(&pl_empty[sl], ((c / NPL) & 1) ^ 1);
+    if (first) plan_chunk(ps0, cl, col0, row0, rs, ring + sl, lane);
+    else plan_chunk(ps1, cl, col0, row0, rs, ring + sl, lane);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&pl_full[sl]);
+    cl = nl;
+  }
 }
 
 }  // namespace plan
