@@ -37,7 +37,12 @@ def full(rep):
           'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
           'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
           'smsp__issue_active.avg.pct_of_peak_sustained_active',
-          'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum']
+          'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+          'sm__icc_request_hit_rate.pct',
+          'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+          'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+          'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+          'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio']
   units = dict(zip(hdr, rows[1]))
   out = []
   for r in rows[2:]:
@@ -58,14 +63,40 @@ def main():
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       f.write(f'| `{k}` | {n} | {t:,.0f} | {100 * t / tot:.1f}% |\n')
   with open(f'profiles/{tag}_ncu_full.md', 'w') as f:
-    f.write(f'# {tag}: `ncu --set full --clock-control none` on `tests/cuda/prof_step.py 4 1` '
-            '(workload c3_4096 at batch 4)\n\n')
+    f.write(f'# {tag}: `ncu --set full --clock-control none -k regex:tc_ -c 7` on `bench.py --steps 1 --warmup 3 --no-cpu-baseline` '
+            '(workload c3_4096)\n\n')
     for name, d in full(rep):
       f.write(f'## `{name}` grid {d["launch__grid_size"][0]}\n\n| metric | value | unit |\n|---|---|---|\n')
       for k, (v, u) in d.items():
         f.write(f'| {k} | {v} | {u} |\n')
       f.write('\n')
-  print('wrote', f'profiles/{tag}_launches.md', f'profiles/{tag}_ncu_full.md')
+  # DRAM traffic per launch of every captured kernel, keyed by the name bench.py's per-kernel
+  # timing uses (capture order of one step: fwd global/long rows, bwd_q global/long, bwd_kv long/global)
+  import json
+  traffic = {}
+  for name, d in full(rep):
+    grid = int(d['launch__grid_size'][0])
+    def as_bytes(key):
+      v, u = d[key]
+      scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+      return float(v) * scale
+    kind = 'fwd' if 'fwd' in name else ('bwd_q' if 'bwd_q' in name else ('bwd_kv' if 'bwd_kv' in name else None))
+    if kind is None:
+      continue
+    traffic.setdefault(kind, []).append((grid, as_bytes('dram__bytes_read.sum') + as_bytes('dram__bytes_write.sum')))
+  out = {}
+  for kind, lst in traffic.items():
+    lst.sort()
+    small, large = lst[0], lst[-1]
+    names = {'fwd': ('tc_fwd_global_rows', 'tc_fwd_long_rows'),
+             'bwd_q': ('tc_bwd_q_global_rows', 'tc_bwd_q_long_rows'),
+             'bwd_kv': ('tc_bwd_kv_global_keys', 'tc_bwd_kv_long_keys')}[kind]
+    if len(lst) > 1:
+      out[names[0]] = {'grid': small[0], 'dram_bytes_per_launch': small[1]}
+    out[names[1]] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
+  out['_source'] = f'{tag}: ncu --set full --clock-control none -k regex:tc_ on bench.py --steps 1 --warmup 3 (workload c3_4096, batch 16)'
+  json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
+  print('wrote', f'profiles/{tag}_launches.md', f'profiles/{tag}_ncu_full.md', 'profiles/traffic.json')
 
 
 if __name__ == '__main__':
