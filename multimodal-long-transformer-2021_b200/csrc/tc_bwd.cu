@@ -854,16 +854,23 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ============================================================================================
 namespace bk {
 constexpr int NST = 3;
-// (plan ring: NPL slots, shared constant above)
-constexpr int RSMAX = 64 + 4;                   // floats per row record (header + R <= 64 ids)
-constexpr int SM_K = 0;                         // 16 KB
-constexpr int SM_V = SM_K + TM * 128;           // 16 KB
-constexpr int SM_QD = SM_V + TM * 128;          // NST x (Q 8 KB + dO 8 KB)
-constexpr int SM_REC = SM_QD + NST * 2 * TN * 128;      // NST x [64] row records (see TcBwdQParams::rec_ws)
-constexpr int SM_PLAN = SM_REC + NST * TN * RSMAX * 4;  // NPL x ChunkPlan
-constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
-constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
-constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320;
+// SLIM: a 256-column / ~111 KB configuration that lets TWO CTAs share an SM (relative vocabulary
+// <= 32, S^T / dP^T single-buffered, the producer warp doubles as the planner).  The long-key tiles
+// have few chunks, so start-up and drain of one CTA are hidden by the other instead of by
+// double buffering.
+template <bool SLIM>
+struct Cfg {
+  static constexpr int RSMAX = (SLIM ? 32 : 64) + 4;     // floats per row record (header + ids)
+  static constexpr int SM_K = 0;                         // 16 KB
+  static constexpr int SM_V = SM_K + TM * 128;           // 16 KB
+  static constexpr int SM_QD = SM_V + TM * 128;          // NST x (Q 8 KB + dO 8 KB)
+  static constexpr int SM_REC = SM_QD + NST * 2 * TN * 128;      // NST x [64] row records (see TcBwdQParams::rec_ws)
+  static constexpr int SM_PLAN = SM_REC + NST * TN * RSMAX * 4;  // NPL x ChunkPlan
+  static constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
+  static constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
+  static constexpr uint32_t TCOLS = SLIM ? 256 : 512;
+  static constexpr uint32_t T_S = 0, T_DP = SLIM ? 64 : 128, T_DV = SLIM ? 128 : 256, T_DK = SLIM ? 192 : 320;
+};
 
 struct Bars {
   uint64_t kv_full;
@@ -990,8 +997,8 @@ __device__ __forceinline__ void eval_generic_kv(const SrcC& sc, const KeyC& kc, 
   if (id >= sc.R) id = -1;
 }
 
-template <int NP, int SETS>
-constexpr int bk_threads() { return (4 * NP * SETS + 3) * 32; }
+template <int NP, int SETS, bool SLIM>
+constexpr int bk_threads() { return (4 * NP * SETS + (SLIM ? 2 : 3)) * 32; }
 
 // NP threads per key row inside a warp set (each owns W = 64 / NP query columns of a chunk); SETS
 // warp sets take alternate chunks (S^T / dP^T are double-buffered by chunk parity, so set s owns
@@ -999,17 +1006,26 @@ constexpr int bk_threads() { return (4 * NP * SETS + 3) * 32; }
 // per-query constants arrive exponent-ready in the row records the query-centric pass published
 // (TcBwdQParams::rec_ws), so the common element costs
 //     p = ex2(fma(x, scale*log2e, rec[i][4 + id])),  ds = p * (dp - rec[i][2]).
-template <int NP, int SETS>
-__global__ void __launch_bounds__(bk_threads<NP, SETS>(), 1)
+template <int NP, int SETS, bool SLIM>
+__global__ void __launch_bounds__(bk_threads<NP, SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
                  const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_do1,
                  const __grid_constant__ TcBwdKVParams p) {
   using namespace bk;
-  constexpr int W = 64 / NP;
+  using C = Cfg<SLIM>;
+  constexpr int SM_K = C::SM_K, SM_V = C::SM_V, SM_QD = C::SM_QD, SM_REC = C::SM_REC, SM_PLAN = C::SM_PLAN,
+                SM_BAR = C::SM_BAR, RSMAX = C::RSMAX;
+  constexpr uint32_t T_S = C::T_S, T_DP = C::T_DP, T_DV = C::T_DV, T_DK = C::T_DK;
+  constexpr int W = 64 / NP;                     // query columns per elementwise thread and chunk
+  constexpr int WS = SLIM ? 16 : W;              // ... processed in sub-slices of WS (register budget)
   constexpr int NEW = 128 * NP;                  // elementwise threads per set
-  constexpr int WP = 4 * NP * SETS, WM = WP + 1, WH = WP + 2;
+  constexpr int WP = 4 * NP * SETS, WM = WP + 1, WH = SLIM ? WP : WP + 2;   // SLIM: producer == planner
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
+  static_assert(!SLIM || SETS == 1, "the slim configuration has a single S^T / dP^T buffer");
+  // chunk c uses buffer BUF(c) in its PH(c)-th use
+  auto BUF = [](int c) { return SLIM ? 0 : (c & 1); };
+  auto PH = [](int c) { return SLIM ? (c & 1) : ((c >> 1) & 1); };
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
   // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
@@ -1036,7 +1052,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == WM) tmem_alloc<C::TCOLS>(&bars->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -1047,26 +1063,47 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   if (p.nsrc > 1) r1 = src_range(p.src[1], j0);
   const int nchunks = r0.n + r1.n;
 
+  // One query chunk: Q and dO tiles plus the 64-row record block (one elected lane).
+  auto load_chunk = [&](int c) {
+    const int st = c % NST;
+    mbar_wait(&bars->qd_empty[st], ((c / NST) & 1) ^ 1);
+    const bool first = c < r0.n;
+    const TcQuerySource& src = first ? p.src[0] : p.src[1];
+    const int q0 = first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN;
+    const int rs = src.rw + 4;
+    uint8_t* qs = smem + SM_QD + st * (2 * TN * 128);
+    const int64_t prow = ((int64_t)(b * p.H + h) * (src.lp >> 6) + (q0 >> 6)) * 64;   // record block of q0
+    const uint32_t rec_bytes = TN * rs * 4;
+    mbar_arrive_expect_tx(&bars->qd_full[st], 2 * TN * 128 + rec_bytes);
+    tma_load_4d(qs, first ? &map_q0 : &map_q1, &bars->qd_full[st], 0, q0, h, b);
+    tma_load_4d(qs + TN * 128, first ? &map_do0 : &map_do1, &bars->qd_full[st], 0, q0, h, b);
+    bulk_g2s(smem + SM_REC + st * TN * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
+  };
+  auto run_planner = [&](auto pre) {
+    const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0);
+    const plan::PSeg ps1 = make_kv_pseg(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
+    const Side* ks_side = nullptr;   // row-side (key) sentence ids: rule KSENT
+    if (ps0.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[0].q.side;
+    if (p.nsrc > 1 && ps1.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[1].q.side;
+    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.ib, r1.ib, b, j0, ks_side ? ks_side->sent : nullptr,
+                                ks_side ? ks_side->sent_len : 0, p.len, plans, bars->pl_full, bars->pl_empty, lane,
+                                pre);
+  };
+
   if (warp == WP) {
-    if (elect_one()) {
+    if (lane == 0) {
       mbar_arrive_expect_tx(&bars->kv_full, 2 * TM * 128);
       tma_load_4d(smem + SM_K, &map_k, &bars->kv_full, 0, j0, h, b);
       tma_load_4d(smem + SM_V, &map_v, &bars->kv_full, 0, j0, h, b);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % NST;
-        mbar_wait(&bars->qd_empty[st], ((c / NST) & 1) ^ 1);
-        const bool first = c < r0.n;
-        const TcQuerySource& src = first ? p.src[0] : p.src[1];
-        const int q0 = first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN;
-        const int rs = src.rw + 4;
-        uint8_t* qs = smem + SM_QD + st * (2 * TN * 128);
-        const int64_t prow = ((int64_t)(b * p.H + h) * (src.lp >> 6) + (q0 >> 6)) * 64;   // record block of q0
-        const uint32_t rec_bytes = TN * rs * 4;
-        mbar_arrive_expect_tx(&bars->qd_full[st], 2 * TN * 128 + rec_bytes);
-        tma_load_4d(qs, first ? &map_q0 : &map_q1, &bars->qd_full[st], 0, q0, h, b);
-        tma_load_4d(qs + TN * 128, first ? &map_do0 : &map_do1, &bars->qd_full[st], 0, q0, h, b);
-        bulk_g2s(smem + SM_REC + st * TN * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
-      }
+    }
+    if (SLIM) {
+      // producer and planner in one warp: the chunk's loads go out, then the chunk is classified
+      run_planner([&](int c) {
+        if (lane == 0) load_chunk(c);
+        __syncwarp();
+      });
+    } else if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) load_chunk(c);
     }
   } else if (warp == WM) {
     if (elect_one()) {
@@ -1075,57 +1112,61 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       const uint32_t k_addr = smem_u32(smem + SM_K), v_addr = smem_u32(smem + SM_V);
       mbar_wait(&bars->kv_full, 0);
       tc_fence_after_sync();
+      auto issue_sdp = [&](int c) {
+        const int st = c % NST;
+        mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
+        mbar_wait(&bars->qd_full[st], (c / NST) & 1);
+        TRACE(2, 4 * c);
+        tc_fence_after_sync();
+        const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
+        const uint32_t do_addr = q_addr + TN * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // S^T = K . Q_c^T
+          umma_ss(tmem + T_S + BUF(c) * 64, make_smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(q_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dP^T = V . dO_c^T
+          umma_ss(tmem + T_DP + BUF(c) * 64, make_smem_desc_sw128(v_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(do_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&bars->sdp_full[BUF(c)]);
+        TRACE(2, 4 * c + 1);
+      };
+      auto issue_acc = [&](int pc) {
+        const int st = pc % NST;
+        mbar_wait(&bars->pds_full[BUF(pc)], PH(pc));
+        TRACE(2, 4 * pc + 2);
+        tc_fence_after_sync();
+        mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
+        const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
+        const uint32_t do_addr = q_addr + TN * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dV += P^T . dO_c
+          umma_ts(tmem + T_DV, tmem + T_S + BUF(pc) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
+                  make_smem_desc_sw128(do_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dK += dS^T . Q_c
+          umma_ts(tmem + T_DK, tmem + T_DP + BUF(pc) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
+                  make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
+        umma_commit(&bars->qd_empty[st]);
+        TRACE(2, 4 * pc + 3);
+        if (pc == nchunks - 1) umma_commit(&bars->acc_full);
+      };
+      // double-buffered: S/dP of chunk c run ahead of the accumulation of chunk c-1; single buffer
+      // (SLIM): the accumulation MMAs that read P^T / dS^T are issued first (tensor-core MMAs of one
+      // thread execute in issue order, so the overwrite cannot overtake the read)
       for (int c = 0; c <= nchunks; ++c) {
-        if (c < nchunks) {
-          const int st = c % NST;
-          mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
-          mbar_wait(&bars->qd_full[st], (c / NST) & 1);
-          TRACE(2, 4 * c);
-          tc_fence_after_sync();
-          const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
-          const uint32_t do_addr = q_addr + TN * 128;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // S^T = K . Q_c^T
-            umma_ss(tmem + T_S + (c & 1) * 64, make_smem_desc_sw128(k_addr + kk * 32, 16, 1024),
-                    make_smem_desc_sw128(q_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dP^T = V . dO_c^T
-            umma_ss(tmem + T_DP + (c & 1) * 64, make_smem_desc_sw128(v_addr + kk * 32, 16, 1024),
-                    make_smem_desc_sw128(do_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
-          umma_commit(&bars->sdp_full[c & 1]);
-          TRACE(2, 4 * c + 1);
-        }
-        if (c >= 1) {
-          const int pc = c - 1, st = pc % NST;
-          mbar_wait(&bars->pds_full[pc & 1], (pc >> 1) & 1);
-          TRACE(2, 4 * pc + 2);
-          tc_fence_after_sync();
-          mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
-          const uint32_t q_addr = smem_u32(smem + SM_QD + st * (2 * TN * 128));
-          const uint32_t do_addr = q_addr + TN * 128;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dV += P^T . dO_c
-            umma_ts(tmem + T_DV, tmem + T_S + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
-                    make_smem_desc_sw128(do_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T . Q_c
-            umma_ts(tmem + T_DK, tmem + T_DP + (pc & 1) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
-                    make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
-          umma_commit(&bars->qd_empty[st]);
-          TRACE(2, 4 * pc + 3);
-          if (pc == nchunks - 1) umma_commit(&bars->acc_full);
+        if (SLIM) {
+          if (c >= 1) issue_acc(c - 1);
+          if (c < nchunks) issue_sdp(c);
+        } else {
+          if (c < nchunks) issue_sdp(c);
+          if (c >= 1) issue_acc(c - 1);
         }
       }
     }
-  } else if (warp == WH) {
+  } else if (!SLIM && warp == WH) {
     // ===================== planner =====================
-    const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0);
-    const plan::PSeg ps1 = make_kv_pseg(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
-    const Side* ks_side = nullptr;   // row-side (key) sentence ids: rule KSENT
-    if (ps0.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[0].q.side;
-    if (p.nsrc > 1 && ps1.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[1].q.side;
-    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.ib, r1.ib, b, j0, ks_side ? ks_side->sent : nullptr,
-                                ks_side ? ks_side->sent_len : 0, p.len, plans, bars->pl_full, bars->pl_empty, lane);
+    run_planner(plan::NoPre());
   } else {
     // ===================== elementwise warps =====================
     const int quad = warp & 3;
@@ -1145,20 +1186,20 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
         const int st = c % NST;
-        const int g0 = ib + (c - c_begin) * TN + part * W;   // first query of this thread's slice
-        const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
-        const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
+        const int g0w = ib + (c - c_begin) * TN + part * W;   // first query of this thread's slice
+        const uint32_t t_sw = tmem + T_S + BUF(c) * 64 + lane_sel + part * W;
+        const uint32_t t_dpw = tmem + T_DP + BUF(c) * 64 + lane_sel + part * W;
         const plan::ChunkPlan* cp = plans + (c % NPL);
         if (tid == 0) TRACE(0, 4 * c);
         // the MMA warp issued S^T_c / dP^T_c only after plan c had been published and the row
         // records of the chunk had landed
-        mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        mbar_wait_warp(&bars->sdp_full[BUF(c)], PH(c));
         if (tid == 0) TRACE(0, 4 * c + 1);
         tc_fence_after_sync();
         // record fields of this thread's query slice: field f of query x at rec[f * 64 + x]
-        const float* rec = reinterpret_cast<const float*>(smem + SM_REC + st * TN * RSMAX * 4) + part * W;
-        const int32_t* ce = cp->ce + part * W;
-        const int32_t* cs = cp->cs + part * W;
+        const float* recw = reinterpret_cast<const float*>(smem + SM_REC + st * TN * RSMAX * 4) + part * W;
+        const int32_t* cew = cp->ce + part * W;
+        const int32_t* csw = cp->cs + part * W;
         const uint32_t w0 = cp->q[quad][grp];
         const int ce0 = (int)cp->q[quad][2 + grp];
         const int mode = (int)(w0 & 0xffu);
@@ -1167,126 +1208,137 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         const int ccls = (int)((w0 >> 8) & 0xffu);
         // record field of the group's constant class
         const int coff = ccls == plan::C_POS ? 4 + sc.D : (ccls == plan::C_NEG ? 4 + 2 * sc.D : (ccls == plan::C_CROSS ? 5 + 2 * sc.D : 0));
-        uint32_t p_pk[W / 2], ds_pk[W / 2];
-        if (mode == plan::DEAD) {
-#pragma unroll
-          for (int x = 0; x < W / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
-        } else if (mode == plan::GEN) {
-          // real loop, TMEM as dynamically indexed scratch: one copy of the generic code.
-          // Leaves p (fp32) in the S^T column and ds in the dP^T column.
+        // the thread's W columns are processed in sub-slices of WS (SLIM: 16, to stay within the
+        // register budget of two CTAs per SM); packed results of sub-slice hh land in the first half
+        // of the columns already consumed
 #pragma unroll 1
-          for (int ii = 0; ii < W; ++ii) {
-            const uint32_t raw = tmem_ld1(t_s + ii);
-            const uint32_t dpr = tmem_ld1(t_dp + ii);
+        for (int hh = 0; hh < W / WS; ++hh) {
+          const int g0 = g0w + hh * WS;
+          const uint32_t t_s = t_sw + hh * WS, t_dp = t_dpw + hh * WS;
+          const float* rec = recw + hh * WS;
+          const int32_t* ce = cew + hh * WS;
+          const int32_t* cs = csw + hh * WS;
+          uint32_t p_pk[WS / 2], ds_pk[WS / 2];
+          if (mode == plan::DEAD) {
+  #pragma unroll
+            for (int x = 0; x < WS / 2; ++x) { p_pk[x] = 0u; ds_pk[x] = 0u; }
+          } else if (mode == plan::GEN) {
+            // real loop, TMEM as dynamically indexed scratch: one copy of the generic code.
+            // Leaves p (fp32) in the S^T column and ds in the dP^T column.
+  #pragma unroll 1
+            for (int ii = 0; ii < WS; ++ii) {
+              const uint32_t raw = tmem_ld1(t_s + ii);
+              const uint32_t dpr = tmem_ld1(t_dp + ii);
+              tmem_wait_ld();
+              bool live, ok;
+              int id;
+              eval_generic_kv(sc, kc, b, g0 + ii, j, key_ok, ce[ii], cs[ii], live, ok, id);
+              float pv = 0.f, ds = 0.f;
+              if (live) {
+                const float* r = rec + ii;
+                pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * 64]) : r[64]);
+                ds = pv * (__uint_as_float(dpr) - r[128]);
+              }
+              __syncwarp();   // the generic evaluation diverges per row; tcgen05.st needs the converged warp
+              tmem_st1(t_s + ii, __float_as_uint(pv));
+              tmem_st1(t_dp + ii, __float_as_uint(ds));
+            }
+            tmem_wait_st();
+            uint32_t v[WS];
+            tmem_ldN(t_s, v);
             tmem_wait_ld();
-            bool live, ok;
-            int id;
-            eval_generic_kv(sc, kc, b, g0 + ii, j, key_ok, ce[ii], cs[ii], live, ok, id);
-            float pv = 0.f, ds = 0.f;
-            if (live) {
-              const float* r = rec + ii;
-              pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * 64]) : r[64]);
-              ds = pv * (__uint_as_float(dpr) - r[128]);
-            }
-            __syncwarp();   // the generic evaluation diverges per row; tcgen05.st needs the converged warp
-            tmem_st1(t_s + ii, __float_as_uint(pv));
-            tmem_st1(t_dp + ii, __float_as_uint(ds));
-          }
-          tmem_wait_st();
-          uint32_t v[W];
-          tmem_ldN(t_s, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int x = 0; x < W / 2; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-          tmem_ldN(t_dp, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
-        } else {
-          uint32_t v[W], w[W];
-          tmem_ldN(t_s, v);
-          tmem_ldN(t_dp, w);
-          tmem_wait_ld();
-          // unmasked: exponent = x * scale2 + field(4 + id); masked: the per-query constant field 1
-          const float* dl = rec + 2 * 64;
-          if (mode == plan::FAST) {
-            const float gmul = masked ? 0.f : scale2;
-            const float* cc = rec + (masked ? 1 : coff) * 64;
-#pragma unroll
-            for (int x = 0; x < W / 2; ++x) {
-              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, cc[2 * x]));
-              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, cc[2 * x + 1]));
-              p_pk[x] = pack_bf16x2(p0, p1);
-              ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
-            }
+  #pragma unroll
+            for (int x = 0; x < WS / 2; ++x) p_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
+            tmem_ldN(t_dp, v);
+            tmem_wait_ld();
+  #pragma unroll
+            for (int x = 0; x < WS / 2; ++x) ds_pk[x] = pack_bf16x2(__uint_as_float(v[2 * x]), __uint_as_float(v[2 * x + 1]));
           } else {
-            // 1. exponent per element, in place (one code copy per form: `mode` is warp-uniform)
-            float t[W];
-            const int d0 = j - g0;   // offset(key - query) = d0 - x
-            if (mode == plan::EDGE) {
-              const float* cc = rec + coff * 64;
-#pragma unroll
-              for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, cc[x]);
-            } else if (mode == plan::DIAG) {
-#pragma unroll
-              for (int x = 0; x < W; ++x) {
-                const int o = min(max(d0 - x, -sc.D), sc.D);
-                t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * 64 + x]);
-              }
-            } else {
-              const float* c0 = rec + (5 + 2 * sc.D) * 64;
-              if (mode == plan::QS) {          // row-side sentence: key j belongs to query (k_sent)
-                const int sp = kc.k_sent - g0;
-#pragma unroll
-                for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(sp == x ? 64 : 0) + x]);
-              } else {                         // KS: column-side sentence: query x's sentence is key j
-#pragma unroll
-                for (int x = 0; x < W; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(cs[x] == j ? 64 : 0) + x]);
-              }
-            }
-            // 2. masked elements take the per-query constant (field 1)
-            const float* lp = rec + 64;
-            if (mask_pe) {
-#pragma unroll
-              for (int x = 0; x < W; ++x) t[x] = (ce[x] != kc.k_e) ? lp[x] : t[x];
-            } else if (mre && __any_sync(0xffffffffu, masked)) {
-#pragma unroll
-              for (int x = 0; x < W; ++x) t[x] = masked ? lp[x] : t[x];
-            }
-            // 3. probabilities; EDGE: dead columns may carry garbage records -> select, not multiply
-            if (mode == plan::EDGE) {
-              int ilo = 0, ihi = min(W, sc.ie - g0);
-              if (sc.band) {
-                ilo = max(ilo, d0 - sc.radius);
-                ihi = min(ihi, d0 + sc.radius + 1);
-              }
-              if (!key_ok) ihi = ilo;
-              const unsigned span = (unsigned)max(ihi - ilo, 0);
-#pragma unroll
-              for (int x = 0; x < W / 2; ++x) {
-                const bool l0 = (unsigned)(2 * x - ilo) < span, l1 = (unsigned)(2 * x + 1 - ilo) < span;
-                const float p0 = l0 ? ex2(t[2 * x]) : 0.f, p1 = l1 ? ex2(t[2 * x + 1]) : 0.f;
-                const float e0 = l0 ? p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]) : 0.f;
-                const float e1 = l1 ? p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]) : 0.f;
-                p_pk[x] = pack_bf16x2(p0, p1);
-                ds_pk[x] = pack_bf16x2(e0, e1);
-              }
-            } else {
-#pragma unroll
-              for (int x = 0; x < W / 2; ++x) {
-                const float p0 = ex2(t[2 * x]), p1 = ex2(t[2 * x + 1]);
+            uint32_t v[WS], w[WS];
+            tmem_ldN(t_s, v);
+            tmem_ldN(t_dp, w);
+            tmem_wait_ld();
+            // unmasked: exponent = x * scale2 + field(4 + id); masked: the per-query constant field 1
+            const float* dl = rec + 2 * 64;
+            if (mode == plan::FAST) {
+              const float gmul = masked ? 0.f : scale2;
+              const float* cc = rec + (masked ? 1 : coff) * 64;
+  #pragma unroll
+              for (int x = 0; x < WS / 2; ++x) {
+                const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, cc[2 * x]));
+                const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, cc[2 * x + 1]));
                 p_pk[x] = pack_bf16x2(p0, p1);
                 ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
               }
+            } else {
+              // 1. exponent per element, in place (one code copy per form: `mode` is warp-uniform)
+              float t[WS];
+              const int d0 = j - g0;   // offset(key - query) = d0 - x
+              if (mode == plan::EDGE) {
+                const float* cc = rec + coff * 64;
+  #pragma unroll
+                for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, cc[x]);
+              } else if (mode == plan::DIAG) {
+  #pragma unroll
+                for (int x = 0; x < WS; ++x) {
+                  const int o = min(max(d0 - x, -sc.D), sc.D);
+                  t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * 64 + x]);
+                }
+              } else {
+                const float* c0 = rec + (5 + 2 * sc.D) * 64;
+                if (mode == plan::QS) {          // row-side sentence: key j belongs to query (k_sent)
+                  const int sp = kc.k_sent - g0;
+  #pragma unroll
+                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(sp == x ? 64 : 0) + x]);
+                } else {                         // KS: column-side sentence: query x's sentence is key j
+  #pragma unroll
+                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(cs[x] == j ? 64 : 0) + x]);
+                }
+              }
+              // 2. masked elements take the per-query constant (field 1)
+              const float* lp = rec + 64;
+              if (mask_pe) {
+  #pragma unroll
+                for (int x = 0; x < WS; ++x) t[x] = (ce[x] != kc.k_e) ? lp[x] : t[x];
+              } else if (mre && __any_sync(0xffffffffu, masked)) {
+  #pragma unroll
+                for (int x = 0; x < WS; ++x) t[x] = masked ? lp[x] : t[x];
+              }
+              // 3. probabilities; EDGE: dead columns may carry garbage records -> select, not multiply
+              if (mode == plan::EDGE) {
+                int ilo = 0, ihi = min(WS, sc.ie - g0);
+                if (sc.band) {
+                  ilo = max(ilo, d0 - sc.radius);
+                  ihi = min(ihi, d0 + sc.radius + 1);
+                }
+                if (!key_ok) ihi = ilo;
+                const unsigned span = (unsigned)max(ihi - ilo, 0);
+  #pragma unroll
+                for (int x = 0; x < WS / 2; ++x) {
+                  const bool l0 = (unsigned)(2 * x - ilo) < span, l1 = (unsigned)(2 * x + 1 - ilo) < span;
+                  const float p0 = l0 ? ex2(t[2 * x]) : 0.f, p1 = l1 ? ex2(t[2 * x + 1]) : 0.f;
+                  const float e0 = l0 ? p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]) : 0.f;
+                  const float e1 = l1 ? p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]) : 0.f;
+                  p_pk[x] = pack_bf16x2(p0, p1);
+                  ds_pk[x] = pack_bf16x2(e0, e1);
+                }
+              } else {
+  #pragma unroll
+                for (int x = 0; x < WS / 2; ++x) {
+                  const float p0 = ex2(t[2 * x]), p1 = ex2(t[2 * x + 1]);
+                  p_pk[x] = pack_bf16x2(p0, p1);
+                  ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
+                }
+              }
             }
           }
+          tmem_stN(t_sw + hh * (WS / 2), p_pk);
+          tmem_stN(t_dpw + hh * (WS / 2), ds_pk);
         }
         if (tid == 0) TRACE(0, 4 * c + 2);
-        tmem_stN(t_s, p_pk);
-        tmem_stN(t_dp, ds_pk);
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&bars->pds_full[c & 1]);
+        mbar_arrive(&bars->pds_full[BUF(c)]);
         if (tid == 0) TRACE(0, 4 * c + 3);
       }
     };
@@ -1331,7 +1383,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == WM) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == WM) tmem_dealloc<C::TCOLS>(tmem);
 }
 
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -1423,9 +1475,14 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   if (!g_attr_kv) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         bk::Cfg<false>::SM_ALLOC);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::SM_ALLOC);
+      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               bk::Cfg<false>::SM_ALLOC);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               bk::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_kv = true;
   }
@@ -1455,10 +1512,17 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   dim3 grid((a.len + TM - 1) / TM, a.H, a.B);
   auto src_chunks = [](const QuerySource& q) { return q.band ? (TM + 2 * q.radius + TN - 1) / TN : (q.rows.len + TN - 1) / TN; };
   const int est_chunks = src_chunks(a.src[0]) + (a.nsrc > 1 ? src_chunks(a.src[1]) : 0);
-  if (est_chunks >= 16)
-    tc_bwd_kv_kernel<2, 2><<<grid, bk_threads<2, 2>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  // Few chunks per tile (long keys: band + G/64): start-up and drain dominate -> the slim
+  // configuration with two CTAs per SM.  Many chunks (global keys): two warp sets on alternate chunks.
+  static const int force_kv = getenv("MLT_KV_CFG") ? atoi(getenv("MLT_KV_CFG")) : 0;   // 1: <4,1>  2: <2,2>  3: slim
+  const bool slim_ok = p.src[0].rw <= 32 && p.src[1].rw <= 32;
+  const int cfg = force_kv ? force_kv : (est_chunks >= 16 ? 2 : (slim_ok ? 3 : 1));
+  if (cfg == 3 && slim_ok)
+    tc_bwd_kv_kernel<2, 1, true><<<grid, bk_threads<2, 1, true>(), bk::Cfg<true>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  else if (cfg == 2)
+    tc_bwd_kv_kernel<2, 2, false><<<grid, bk_threads<2, 2, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   else
-    tc_bwd_kv_kernel<4, 1><<<grid, bk_threads<4, 1>(), bk::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+    tc_bwd_kv_kernel<4, 1, false><<<grid, bk_threads<4, 1, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();
 }
 

@@ -23,6 +23,8 @@
 // TMEM map (columns): [0,64) S0/P0, [64,128) S1/P1, [128,192) O, [192,256) allrel.
 #include "tc_api.cuh"
 
+#include <cstdlib>
+
 #include "mlt_common.cuh"
 #include "profile.cuh"
 #include "tc_plan.cuh"
@@ -650,8 +652,10 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace(unsig
 
 int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   static bool attr_set = false;
+  // experiment knob: extra dynamic shared memory forces one CTA per SM
+  static const int extra_smem = getenv("MLT_FWD_ONE_CTA") ? 100 * 1024 : 0;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -674,7 +678,7 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
-  tc_fwd_kernel<<<grid, NTHREADS, SM_ALLOC, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
+  tc_fwd_kernel<<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 

@@ -248,11 +248,16 @@ __device__ __forceinline__ RowSent row_sent_reduce(const RowSentRaw& r) {
 // The planner warp's loop over the chunks of a tile (up to two column segments).  The global
 // loads of chunk c + 1 are in flight while chunk c is classified; the row-side loads overlap the
 // first chunk's.  `ring` has NPL slots guarded by pl_full / pl_empty mbarriers.
-template <int NPL, int TN>
+// `pre(c)` runs (whole warp) at the top of iteration c: kernels whose producer warp doubles as the
+// planner issue the chunk's TMA loads there.
+struct NoPre {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <int NPL, int TN, typename Pre = NoPre>
 __device__ __forceinline__ void planner_loop(const PSeg& ps0, const PSeg& ps1, int n0, int n1, int cb0, int cb1,
                                              int b, int row0, const int32_t* row_sent, int64_t row_sent_stride,
                                              int row_len, ChunkPlan* ring, uint64_t* pl_full, uint64_t* pl_empty,
-                                             int lane) {
+                                             int lane, Pre pre = Pre()) {
   const int nchunks = n0 + n1;
   if (nchunks == 0) return;
   const RowSentRaw raw = row_sent_load(row_sent, row_sent_stride, b, row0, row_len, lane);
@@ -260,6 +265,7 @@ __device__ __forceinline__ void planner_loop(const PSeg& ps0, const PSeg& ps1, i
   const RowSent rs = row_sent_reduce(raw);
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
+    pre(c);
     const int sl = c % NPL;
     const bool first = c < n0;
     const int col0 = first ? cb0 + c * TN : cb1 + (c - n0) * TN;
