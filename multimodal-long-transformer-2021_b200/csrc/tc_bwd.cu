@@ -46,7 +46,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 #else
 #define TRACE(role, idx) do {} while (0)
 #endif
-constexpr uint32_t TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -111,25 +110,38 @@ __global__ void __launch_bounds__(256) tc_bwd_prep_kernel(const T4 out, const T4
 // Query-centric pass
 // ============================================================================================
 namespace bq {
-constexpr int NST = 4;
-constexpr int SM_Q = 0;                        // 16 KB
-constexpr int SM_DO = SM_Q + TM * 128;         // 16 KB
-constexpr int SM_E = SM_DO + TM * 128;         // 8 KB
-constexpr int SM_KV = SM_E + 64 * 128;         // NST x 16 KB
-constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;   // [64][128] f32
-constexpr int SM_BIN = SM_REL + 64 * TM * 4;         // 2 x [64][128] f32
-constexpr int SM_A = SM_BIN + 2 * 64 * TM * 4;      // dallrel^T tile, bf16, [128 rows][64 ids] SW128 (16 KB)
-constexpr int SM_BS = SM_A + TM * 128;              // bias partial sums [4 quadrants][64]
-constexpr int SM_PLAN = SM_BS + 4 * 64 * 4;         // 4 x ChunkPlan
-constexpr int SM_META = SM_PLAN + 4 * (int)sizeof(plan::ChunkPlan);   // 64 x RelMeta
-constexpr int SM_BAR = SM_META + 64 * (int)sizeof(plan::RelMeta);
-constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
-// TMEM columns
-constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_REL = 320, T_DE = 384;
+// SLIM: a 256-column / ~105 KB configuration that lets TWO CTAs share an SM (relative vocabulary
+// <= 32, one elementwise thread per row, S / dP single-buffered, two K/V stages, the dallrel^T
+// tile reuses a drained K/V stage).  Used for the long-row tiles, which have few chunks: prologue
+// (table build), epilogue (dallrel assembly) and the MMA round trips of one CTA are covered by
+// the other.
+template <bool SLIM>
+struct Cfg {
+  static constexpr int NST = SLIM ? 2 : 4;
+  static constexpr int NSLOT = SLIM ? 32 : 64;            // relative-table / bin slots
+  static constexpr int SM_Q = 0;                          // 16 KB
+  static constexpr int SM_DO = SM_Q + TM * 128;           // 16 KB
+  static constexpr int SM_E = SM_DO + TM * 128;           // NSLOT x 128 B
+  static constexpr int SM_KV = SM_E + NSLOT * 128;        // NST x 16 KB
+  static constexpr int SM_REL = SM_KV + NST * 2 * TN * 128;    // [NSLOT][128] f32
+  static constexpr int SM_BIN = SM_REL + NSLOT * TM * 4;       // slim: [32][128] f32; else 2 x [64][128] f32
+  static constexpr int SM_BIN_BYTES = SLIM ? 32 * TM * 4 : 2 * 64 * TM * 4;
+  // dallrel^T tile, bf16, [128 rows][64 ids] SW128 (16 KB); slim: a drained K/V stage
+  static constexpr int SM_A = SLIM ? SM_KV : SM_BIN + SM_BIN_BYTES;
+  static constexpr int SM_BS = SLIM ? SM_BIN + SM_BIN_BYTES : SM_A + TM * 128;   // bias partial sums [4 quadrants][64]
+  static constexpr int SM_PLAN = SM_BS + 4 * 64 * 4;         // 4 x ChunkPlan
+  static constexpr int SM_META = SM_PLAN + 4 * (int)sizeof(plan::ChunkPlan);   // 64 x RelMeta
+  static constexpr int SM_BAR = SM_META + 64 * (int)sizeof(plan::RelMeta);
+  static constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
+  // TMEM columns
+  static constexpr uint32_t TCOLS = SLIM ? 256 : 512;
+  static constexpr uint32_t T_S = 0, T_DP = SLIM ? 64 : 128, T_DQ = SLIM ? 128 : 256, T_REL = SLIM ? 192 : 320,
+                            T_DE = SLIM ? 0 : 384;   // slim: the table-gradient tile reuses the drained S columns
+};
 
 struct Bars {
   uint64_t q_full, rel_full;
-  uint64_t kv_full[NST], kv_empty[NST];
+  uint64_t kv_full[4], kv_empty[4];
   uint64_t sdp_full[2], ds_full[2], dq_full, dar_full;
   uint64_t pl_full[4], pl_empty[4];
   uint32_t tmem_base;
@@ -278,25 +290,35 @@ __device__ __forceinline__ void eval_generic_q(const SegC& sc, const RowC& rc, i
 // warp set serves: NP = 2 threads per row, SETS warp sets on alternate chunks (S / dP are
 // double-buffered by chunk parity, so set s owns buffer s).  The evaluation form of every
 // (quadrant, group) pair comes from the planner warp (tc_plan.cuh).
-constexpr int NP = 2;
 constexpr int NPL = 4;   // plan ring slots
-template <int SETS>
-constexpr int bq_threads() { return (4 * NP * SETS + 3) * 32; }
+template <int SETS, bool SLIM>
+constexpr int bq_threads() { return (4 * (SLIM ? 1 : 2) * SETS + 3) * 32; }
 
-template <int SETS>
-__global__ void __launch_bounds__(bq_threads<SETS>(), 1)
+template <int SETS, bool SLIM>
+__global__ void __launch_bounds__(bq_threads<SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
                 const __grid_constant__ CUtensorMap map_e, const __grid_constant__ TcBwdQParams p) {
   using namespace bq;
-  constexpr int W = 32;               // columns per elementwise thread and chunk
+  using C = Cfg<SLIM>;
+  constexpr int NST = C::NST, SM_Q = C::SM_Q, SM_DO = C::SM_DO, SM_E = C::SM_E, SM_KV = C::SM_KV, SM_REL = C::SM_REL,
+                SM_BIN = C::SM_BIN, SM_A = C::SM_A, SM_BS = C::SM_BS, SM_PLAN = C::SM_PLAN, SM_META = C::SM_META,
+                SM_BAR = C::SM_BAR;
+  constexpr uint32_t T_S = C::T_S, T_DP = C::T_DP, T_DQ = C::T_DQ, T_REL = C::T_REL, T_DE = C::T_DE;
+  constexpr int NP = SLIM ? 1 : 2;    // elementwise threads per row
+  constexpr int W = 32;               // columns per group
+  constexpr int NG = 2 / NP;          // groups of a chunk a thread walks through (slim: both)
   constexpr int NEW = 128 * NP;       // elementwise threads per set
   constexpr int NALL = NEW * SETS;    // all elementwise threads
   constexpr int NB = NP * SETS;       // private bin arrays per row
   constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = 4 * NB + 2;   // producer / MMA / planner warp
-  constexpr int RB = 128 / NB;        // bin slots per array (host guarantees R <= RB)
+  constexpr int RB = SLIM ? 32 : 128 / NB;   // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
+  static_assert(!SLIM || SETS == 1, "the slim configuration has a single S / dP buffer");
+  // chunk c uses buffer BUF(c) in its PH(c)-th use
+  auto BUF = [](int c) { return SLIM ? 0 : (c & 1); };
+  auto PH = [](int c) { return SLIM ? (c & 1) : ((c >> 1) & 1); };
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: keeps the shared address space
   // (LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math)
@@ -330,7 +352,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == WM) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == WM) tmem_alloc<C::TCOLS>(&bars->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -376,58 +398,67 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                   make_smem_desc_sw128(e_addr + kk * 32, 16, 1024), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
       }
-      for (int c = 0; c <= nchunks; ++c) {
-        if (c < nchunks) {
-          const int st = c % NST;
-          mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
-          mbar_wait(&bars->kv_full[st], (c / NST) & 1);
-          tc_fence_after_sync();
-          const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
-          const uint32_t v_addr = k_addr + TN * 128;
+      auto issue_sdp = [&](int c) {
+        const int st = c % NST;
+        mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
+        mbar_wait(&bars->kv_full[st], (c / NST) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
+        const uint32_t v_addr = k_addr + TN * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + T_S + (c & 1) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + T_S + BUF(c) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + T_DP + (c & 1) * 64, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
-                    make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
-          umma_commit(&bars->sdp_full[c & 1]);
-        }
-        if (c >= 1) {
-          const int pc = c - 1, st = pc % NST;
-          mbar_wait(&bars->ds_full[pc & 1], (pc >> 1) & 1);
-          tc_fence_after_sync();
-          mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
-          const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + T_DP + BUF(c) * 64, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&bars->sdp_full[BUF(c)]);
+      };
+      auto issue_dq = [&](int pc) {
+        const int st = pc % NST;
+        mbar_wait(&bars->ds_full[BUF(pc)], PH(pc));
+        tc_fence_after_sync();
+        mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
+        const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ts(tmem + T_DQ, tmem + T_DP + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                    make_smem_desc_sw128(k_addr + kk * 2048, 16, 1024), idesc_dq, (pc > 0 || kk > 0));
-          umma_commit(&bars->kv_empty[st]);
-          if (pc == nchunks - 1) {
-            if (rpad) {
-              // dQ += dallrel . E : A = dallrel (bf16, TMEM columns of the dead allrel region),
-              // B = E tile taken MN-major (K = relative ids)
-              mbar_wait(&bars->dar_full, 0);
-              tc_fence_after_sync();
-              const uint32_t e_addr = smem_u32(smem + SM_E);
-              for (int kk = 0; kk < rpad / 16; ++kk)
-                umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, make_smem_desc_sw128(e_addr + kk * 2048, 16, 1024),
-                        idesc_dq, 1u);
-              if (a.tg_partial) {
-                // table-gradient partial of this tile: dE[64 ids x 64] = dallrel^T . Q  (M = 64, both
-                // operands MN-major: K = the tile's 128 rows)
-                const uint32_t idesc_de = make_idesc_bf16(64, 64, 1, 1);
-                const uint32_t a_addr = smem_u32(smem + SM_A);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ts(tmem + T_DQ, tmem + T_DP + BUF(pc) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                  make_smem_desc_sw128(k_addr + kk * 2048, 16, 1024), idesc_dq, (pc > 0 || kk > 0));
+        umma_commit(&bars->kv_empty[st]);
+        if (pc == nchunks - 1) {
+          if (rpad) {
+            // dQ += dallrel . E : A = dallrel (bf16, TMEM columns of the dead allrel region),
+            // B = E tile taken MN-major (K = relative ids)
+            mbar_wait(&bars->dar_full, 0);
+            tc_fence_after_sync();
+            const uint32_t e_addr = smem_u32(smem + SM_E);
+            for (int kk = 0; kk < rpad / 16; ++kk)
+              umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, make_smem_desc_sw128(e_addr + kk * 2048, 16, 1024),
+                      idesc_dq, 1u);
+            if (a.tg_partial) {
+              // table-gradient partial of this tile: dE[64 ids x 64] = dallrel^T . Q  (M = 64, both
+              // operands MN-major: K = the tile's 128 rows)
+              const uint32_t idesc_de = make_idesc_bf16(64, 64, 1, 1);
+              const uint32_t a_addr = smem_u32(smem + SM_A + (SLIM ? (nchunks % NST) * (2 * TN * 128) : 0));
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                  umma_ss(tmem + T_DE, make_smem_desc_sw128(a_addr + kk * 2048, 16, 1024),
-                          make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_de, kk > 0);
-              }
+              for (int kk = 0; kk < 8; ++kk)
+                umma_ss(tmem + T_DE, make_smem_desc_sw128(a_addr + kk * 2048, 16, 1024),
+                        make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_de, kk > 0);
             }
-            umma_commit(&bars->dq_full);
           }
+          umma_commit(&bars->dq_full);
+        }
+      };
+      // double-buffered: S/dP of chunk c run ahead of dQ of chunk c-1; single buffer (SLIM): the dQ
+      // MMAs that read dS are issued first (MMAs of one thread execute in issue order)
+      for (int c = 0; c <= nchunks; ++c) {
+        if (SLIM) {
+          if (c >= 1) issue_dq(c - 1);
+          if (c < nchunks) issue_sdp(c);
+        } else {
+          if (c < nchunks) issue_sdp(c);
+          if (c >= 1) issue_dq(c - 1);
         }
       }
     }
@@ -441,19 +472,20 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.kb, r1.kb, b, i0, qs_side ? qs_side->sent : nullptr,
                                 qs_side ? qs_side->sent_len : 0, a.rows.len, plans, bars->pl_full, bars->pl_empty, lane);
   } else {
-    // ===================== elementwise warps (2 threads per row) =====================
+    // ===================== elementwise warps (NP threads per row) =====================
     if (tid == 0) TRACE(1, 0);
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int set = warp / (4 * NP);     // which chunk parity this warp serves
-    const int part = (warp >> 2) % NP;   // which 32-key group of the chunk
-    const int bidx = set * NP + part;    // private bin array / output column slice
+    const int part0 = (warp >> 2) % NP;  // which 32-key group of the chunk (slim: both, in turn)
+    const int bidx = set * NP + part0;   // private bin array / output column slice
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
     for (int x = lane + 32 * quad; x < RB * TM; x += 128) bin[x] = 0.f;
-    for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
+    if (!SLIM)   // slim: the tile lives in a K/V stage and is written in full by the epilogue
+      for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
     const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
     const SegC sc1 = make_segc(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
     RowC rc0, rc1;
@@ -519,15 +551,18 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const bool mre = sc.mask_rule == MR_EXAMPLE_ID;
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
-        const int g0 = kb + (c - c_begin) * TN + part * W;
-        const uint32_t t_s = tmem + T_S + (c & 1) * 64 + lane_sel + part * W;
-        const uint32_t t_dp = tmem + T_DP + (c & 1) * 64 + lane_sel + part * W;
         const plan::ChunkPlan* cp = plans + (c % NPL);
         if (tid == 0) TRACE(1, 8 + 3 * c);
         // the MMA warp issued S_c / dP_c only after plan c had been published
-        mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        mbar_wait_warp(&bars->sdp_full[BUF(c)], PH(c));
         if (tid == 0) TRACE(1, 9 + 3 * c);
         tc_fence_after_sync();
+#pragma unroll 1
+        for (int pg = 0; pg < NG; ++pg) {
+        const int part = SLIM ? pg : part0;
+        const int g0 = kb + (c - c_begin) * TN + part * W;
+        const uint32_t t_s = tmem + T_S + BUF(c) * 64 + lane_sel + part * W;
+        const uint32_t t_dp = tmem + T_DP + BUF(c) * 64 + lane_sel + part * W;
         const uint32_t w0 = cp->q[quad][part];
         const int ce0 = (int)cp->q[quad][2 + part];
         const int mode = (int)(w0 & 0xffu);
@@ -705,11 +740,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
         }
-        // each part packs into its OWN column range (the other part may still be reading its inputs)
+        // each group packs into its OWN column range (the other group's inputs are still unread)
         tmem_st16(t_dp, ds_pk);
+        }
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&bars->ds_full[c & 1]);
+        mbar_arrive(&bars->ds_full[BUF(c)]);
         if (tid == 0) TRACE(1, 10 + 3 * c);
       }
     };
@@ -729,7 +765,14 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
     if (tid == 0) TRACE(1, 5);
     named_bar_sync(1, NALL);  // all bin arrays complete
+    // slim: the dallrel^T tile reuses the K/V stage the last chunk did NOT use (its reader, the dQ
+    // MMA of chunk n-2, completed before S/dP of the last chunk were seen)
+    uint8_t* a_tile = smem + SM_A + (SLIM ? (nchunks % NST) * (2 * TN * 128) : 0);
     if (rpad) {
+      if (SLIM && a.tg_partial) {   // id columns beyond rpad: zeros (non-slim: the tile was cleared up front)
+        for (int c0 = rpad; c0 < 64; c0 += 8)
+          *reinterpret_cast<uint4*>(a_tile + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      }
       // every thread of the row packs a slice of 8 ids: sum over the NB private bin arrays,
       // publish dallrel (fp32, id order) and write the bf16 A-operand columns for dQ += dallrel.E
 #pragma unroll 1
@@ -752,7 +795,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           // but Q rows are zero-filled by TMA anyway)
           const uint4 pk4 = make_uint4(pack_bf16x2(w8[0], w8[1]), pack_bf16x2(w8[2], w8[3]),
                                        pack_bf16x2(w8[4], w8[5]), pack_bf16x2(w8[6], w8[7]));
-          *reinterpret_cast<uint4*>(smem + SM_A + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = pk4;
+          *reinterpret_cast<uint4*>(a_tile + row * 128 + ((((c0 >> 3)) ^ (row & 7)) << 4)) = pk4;
           // bias partial: sum over the 32 rows of this warp, one value per id
           float* bs = reinterpret_cast<float*>(smem + SM_BS) + quad * 64 + c0;
           {
@@ -825,28 +868,29 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     constexpr int WO = 64 / NB;   // output columns per thread
-    uint32_t dq_raw[WO];
-    tmem_ldN(tmem + T_DQ + lane_sel + bidx * WO, dq_raw);
-    tmem_wait_ld();
-    float dq[WO];
+    constexpr int WL = WO > 32 ? 32 : WO;   // ... read in pieces of at most 32 columns
+#pragma unroll 1
+    for (int hh = 0; hh < WO / WL; ++hh) {
+      uint32_t dq_raw[WL];
+      tmem_ldN(tmem + T_DQ + lane_sel + bidx * WO + hh * WL, dq_raw);
+      tmem_wait_ld();
+      if (row_ok) {
+        __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + bidx * WO + hh * WL;
 #pragma unroll
-    for (int x = 0; x < WO; ++x) dq[x] = __uint_as_float(dq_raw[x]);
-    if (row_ok) {
-      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.d_q, b, i, h) + bidx * WO;
-#pragma unroll
-      for (int x = 0; x < WO / 8; ++x) {
-        uint4 w;
-        w.x = pack_bf16x2(dq[8 * x + 0] * a.scale, dq[8 * x + 1] * a.scale);
-        w.y = pack_bf16x2(dq[8 * x + 2] * a.scale, dq[8 * x + 3] * a.scale);
-        w.z = pack_bf16x2(dq[8 * x + 4] * a.scale, dq[8 * x + 5] * a.scale);
-        w.w = pack_bf16x2(dq[8 * x + 6] * a.scale, dq[8 * x + 7] * a.scale);
-        *reinterpret_cast<uint4*>(dst + 8 * x) = w;
+        for (int x = 0; x < WL / 8; ++x) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(dq_raw[8 * x + 0]) * a.scale, __uint_as_float(dq_raw[8 * x + 1]) * a.scale);
+          w.y = pack_bf16x2(__uint_as_float(dq_raw[8 * x + 2]) * a.scale, __uint_as_float(dq_raw[8 * x + 3]) * a.scale);
+          w.z = pack_bf16x2(__uint_as_float(dq_raw[8 * x + 4]) * a.scale, __uint_as_float(dq_raw[8 * x + 5]) * a.scale);
+          w.w = pack_bf16x2(__uint_as_float(dq_raw[8 * x + 6]) * a.scale, __uint_as_float(dq_raw[8 * x + 7]) * a.scale);
+          *reinterpret_cast<uint4*>(dst + 8 * x) = w;
+        }
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == WM) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == WM) tmem_dealloc<C::TCOLS>(tmem);
 }
 
 // ============================================================================================
@@ -1421,9 +1465,14 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(uns
 
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         bq::Cfg<false>::SM_ALLOC);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::SM_ALLOC);
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               bq::Cfg<false>::SM_ALLOC);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               bq::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1464,12 +1513,17 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   // with few (long rows: band + G/64) the extra per-tile prologue work does not pay off.
   auto seg_chunks = [](const KeySeg& sg) { return sg.band ? (TM + 2 * sg.radius + TN - 1) / TN : (sg.len + TN - 1) / TN; };
   const int est_chunks = seg_chunks(a.seg[0]) + (a.nseg > 1 ? seg_chunks(a.seg[1]) : 0);
-  static const int force_sets = getenv("MLT_BWD_SETS") ? atoi(getenv("MLT_BWD_SETS")) : 0;
-  const bool two_sets = force_sets ? force_sets == 2 : est_chunks >= 16;
-  if (R <= 32 && two_sets)   // 4 private bin arrays of 32 slots
-    tc_bwd_q_kernel<2><<<grid, bq_threads<2>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  // 1: one warp set, 2: two warp sets on alternate chunks (many chunks: dense global rows),
+  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64)
+  static const int force_cfg = getenv("MLT_BWD_Q_CFG") ? atoi(getenv("MLT_BWD_Q_CFG")) : 0;
+  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
+  if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
+  if (cfg == 3)
+    tc_bwd_q_kernel<1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (cfg == 2)
+    tc_bwd_q_kernel<2, false><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else
-    tc_bwd_q_kernel<1><<<grid, bq_threads<1>(), bq::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<1, false><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 
