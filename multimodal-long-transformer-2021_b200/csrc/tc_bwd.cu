@@ -682,7 +682,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
               for (int jj = 0; jj < W; ++jj)
                 e[jj] = (cp->ce[part * W + jj] == rc.q_e || e[jj] == -INFINITY) ? e[jj] : lpm;
-            } else if (mre) {
+            } else if (mre && __any_sync(0xffffffffu, masked)) {
 #pragma unroll
               for (int jj = 0; jj < W; ++jj) e[jj] = (masked && e[jj] != -INFINITY) ? lpm : e[jj];
             }
