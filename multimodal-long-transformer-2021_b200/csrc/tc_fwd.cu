@@ -358,8 +358,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     if (tid == 0) TRACE(0, 2);
     const float scale2 = a.scale * LOG2E;
     float m = M_INIT;        // maximum the exponentials are taken against (lags the true maximum)
-    float m_true = M_INIT;   // true running maximum
+    float m_true = M_INIT;   // running maximum over the chunks that took the two-pass path
     float l = 0.f;
+    bool seeded = false;     // warp-uniform: every row of the warp has a reference maximum
     int c = 0;   // chunk counter over both segments
 #pragma unroll 1
     for (int sgi = 0; sgi < a.nseg; ++sgi) {
@@ -382,6 +383,66 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int2 pe = make_int2((int)pq.z, (int)pq.w);
         if (tid == 0) TRACE(0, 5 + 3 * c);
         tc_fence_after_sync();
+        // ---- optimistic single pass ----
+        // Once every row of the warp holds a reference maximum m, a chunk whose groups are all FAST
+        // (or dead) is evaluated straight away against m: p = ex2(x * mul + c_row - m * log2e).  Any
+        // consistent reference works for a softmax; it only must not overflow.  A row sum that is not
+        // a finite number below 2^100 (a score outgrew m by 2^100, e.g. the first unmasked score
+        // after masked ones) sends the warp to the exact two-pass path below: nothing has been
+        // written yet, so S is still intact.
+        {
+          const int md0 = (int)(pw.x & 0xffu), md1 = (int)(pw.y & 0xffu);
+          const bool fastable = seeded && (md0 == plan::DEAD || md0 == plan::FAST) && (md1 == plan::DEAD || md1 == plan::FAST);
+          if (fastable) {
+            const float mb = m * LOG2E;
+            uint32_t pk0[16], pk1[16];
+            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+            auto group = [&](int g, uint32_t (&pk)[16]) {
+              const uint32_t w0 = g ? pw.y : pw.x;
+              const bool masked = mre && (rc.q_e != (g ? pe.y : pe.x));   // FAST: mask uniform over the keys
+              bool dead = (w0 & 0xffu) == plan::DEAD;
+              if (!dead && mre && __all_sync(0xffffffffu, masked && m > -1e8f)) dead = true;   // p == 0 exactly
+              if (dead) {
+#pragma unroll
+                for (int x = 0; x < 16; ++x) pk[x] = 0u;
+                return;
+              }
+              const int ccls = (int)((w0 >> 8) & 0xffu);
+              const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+              const float gmul = masked ? 0.f : scale2;
+              const float gsub = fmaf(relc + (masked ? a.neg : 0.f), LOG2E, -mb);
+              uint32_t v[32];
+              tmem_ld32(t_s + 32 * g, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int x = 0; x < 16; x += 2) {
+                const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
+                const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
+                const float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, gsub));
+                const float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, gsub));
+                ls0 += p0;
+                ls1 += p1;
+                ls2 += p2;
+                ls3 += p3;
+                pk[x] = pack_bf16x2(p0, p1);
+                pk[x + 1] = pack_bf16x2(p2, p3);
+              }
+            };
+            group(0, pk0);
+            group(1, pk1);
+            const float lsum = (ls0 + ls1) + (ls2 + ls3);
+            if (!__any_sync(0xffffffffu, !(lsum < 1.2676506e30f))) {   // 2^100; false for inf / NaN too
+              tmem_st16(t_s, pk0);
+              tmem_st16(t_s + 32, pk1);
+              tmem_wait_st();
+              tc_fence_before_sync();
+              mbar_arrive(&bars->p_full[c & 1]);
+              if (tid == 0) TRACE(0, 6 + 3 * c);
+              l += lsum;
+              continue;
+            }
+          }
+        }
         // ---- pass 1: row maximum; FAST groups leave the raw accumulator in place ----
         float mx = -INFINITY;
         uint32_t dead_mask = 0;
@@ -587,6 +648,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_arrive(&bars->p_full[c & 1]);
         if (tid == 0) TRACE(0, 6 + 3 * c);
         l += (ls0 + ls1) + (ls2 + ls3);
+        seeded = __all_sync(0xffffffffu, m != M_INIT);
       }
     }
     // ---- epilogue: O / l ----
