@@ -20,7 +20,9 @@ units = sharding.partition_units(batch=5, heads=3, rank=rank, world=world)
 ms = sharding.max_over_ranks(10.0 + rank)          # slowest rank defines the step time
 total = sharding.sum_over_ranks(float(len(units)))
 dist.barrier()
-print(json.dumps({"rank": rank, "n": len(units), "first": units[0], "ms": ms, "total": total}))
+# one write per rank: the two processes share the launcher's pipe and print() may split line and newline
+sys.stdout.write(json.dumps({"rank": rank, "n": len(units), "first": units[0], "ms": ms, "total": total}) + "\n")
+sys.stdout.flush()
 dist.destroy_process_group()
 '''
 
@@ -38,7 +40,8 @@ def test_two_rank_partition_and_timing_reduction(tmp_path):
       capture_output=True, text=True, env=env, timeout=240)
   assert out.returncode == 0, out.stderr[-2000:]
   import json
-  rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{')]
+  import re
+  rows = [json.loads(m) for m in re.findall(r'\{[^{}]*\}', out.stdout)]   # tolerant of interleaved output
   assert len(rows) == 2
   assert sorted(r['n'] for r in rows) == [7, 8]          # 15 (b, h) units over 2 ranks
   assert all(r['ms'] == 11.0 for r in rows)              # max over ranks
