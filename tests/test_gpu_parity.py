@@ -326,6 +326,35 @@ def test_tc_backward_configurations_agree(env):
   assert r.returncode == 0 and 'ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def _random_tc_case(seed):
+  g = torch.Generator().manual_seed(seed)
+  ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+  dist = ri(1, 14)
+  rv = ri(2 * dist + 4, 40)                      # room for the 1-D ids and the cross ids
+  return (ri(1, 2), ri(40, 700), ri(1, 90), ri(1, 3), ri(3, 150), rv, dist)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_tc_random_shapes_match_simt(seed):
+  """Property test over (B, L, G, H, radius, R, D): the tcgen05 path (planner forms, slim / regular
+  launch configurations, lagging-maximum forward, exponent-form backward) against the SIMT path on
+  identical bf16 inputs, compact side inputs with ragged lengths."""
+  b, l, g, h, r, rv, dist = _random_tc_case(1000 + seed)
+  shape = synthetic.GlobalLocalShape(b, l, g, h, 64, r, rv, dist)
+  x = synthetic.make_inputs(shape, seed=seed, dtype=torch.bfloat16)
+  for n in ('long_emb', 'long_bias', 'global_emb', 'global_bias'):
+    x[n] = (x[n].float() * 10).bfloat16()
+  side = compact_of(x, shape)
+  lo, go, grads = run_cuda_gl(x, shape, side, impl='tc')
+  ls, gs, sgrads = run_cuda_gl(x, shape, side, impl='simt')
+  assert abs_err(lo, ls.double().cpu()) < BF16_ABS, (b, l, g, h, r, rv, dist)
+  assert abs_err(go, gs.double().cpu()) < BF16_ABS, (b, l, g, h, r, rv, dist)
+  for name, got, want in zip(NAMES, grads, sgrads):
+    want = want.double().cpu()
+    scale = max(1.0, want.abs().max().item())
+    assert abs_err(got, want) < 2 * BF16_ABS * scale, (name, b, l, g, h, r, rv, dist)
+
+
 def test_tc_dense_2d_ids():
   b, s, h, d = 2, 230, 2, 64
   gen = torch.Generator().manual_seed(4)
