@@ -60,8 +60,21 @@ class ClockSampler:
 
   def __init__(self, index):
     self.index = index
-    self.rows = []
+    self.rows = []      # (host time the sample was read, fields)
     self.proc = None
+    self.t_begin = self.t_end = None
+
+  def mark_begin(self):
+    self.t_begin = time.perf_counter()
+
+  def mark_end(self):
+    self.t_end = time.perf_counter()
+
+  def in_window(self):
+    if self.t_begin is None:
+      return len(self.rows)
+    t1 = self.t_end if self.t_end is not None else float('inf')
+    return sum(1 for t, _ in self.rows if self.t_begin <= t <= t1)
 
   def start(self):
     q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -78,7 +91,7 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append([c.strip() for c in line.split(',')])
+      self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
   def stop(self):
     if not self.proc:
@@ -91,7 +104,11 @@ class ClockSampler:
       self.proc.kill()
     sm, mx, reasons = [], [], set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for r in self.rows:
+    t0 = self.t_begin if self.t_begin is not None else float('-inf')
+    t1 = self.t_end if self.t_end is not None else float('inf')
+    for t, r in self.rows:
+      if not (t0 <= t <= t1):
+        continue
       if len(r) < 7:
         continue
       try:
@@ -225,16 +242,17 @@ def run_cuda(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local_rank)
+  sampler.start()          # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
   for _ in range(max(args.warmup, 3)):
     step()
   barrier()
 
   # ---- timed region: exactly K steps, device-timed, inputs resident in HBM ----------------
-  sampler = ClockSampler(local_rank)
-  sampler.start()
   launches0 = _lib.launch_count()
   beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
+  sampler.mark_begin()
   wall0 = time.perf_counter()
   beg.record()
   for _ in range(args.steps):
@@ -243,7 +261,19 @@ def run_cuda(args):
   barrier()
   wall = time.perf_counter() - wall0
   launches = _lib.launch_count() - launches0
+  # a short timed region (K x 2 ms) can fall between two nvidia-smi samples: keep the same load
+  # running, untimed, until the sampler has seen it a few times
+  extended = False
+  t_ext = time.perf_counter()
+  while sampler.proc and sampler.in_window() < 5 and time.perf_counter() - t_ext < 0.6:
+    extended = True
+    step()
+    torch.cuda.synchronize()
+  sampler.mark_end()
   clocks = sampler.stop()
+  if extended:
+    clocks['note'] = ('timed region shorter than the sampling period: window extended with '
+                      'identical untimed steps')
   ms = beg.elapsed_time(end)
   t = torch.tensor([ms], device=dev, dtype=torch.float64)
   if world > 1:

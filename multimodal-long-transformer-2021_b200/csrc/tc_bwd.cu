@@ -33,7 +33,7 @@ template <int NP>
 constexpr int nthreads() { return (4 * NP + 2) * 32; }
 
 #ifdef MLT_TC_TRACE
-__device__ unsigned long long g_trace_b[3][256];
+__device__ unsigned long long g_trace_b[6][256];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -291,11 +291,12 @@ __device__ __forceinline__ void eval_generic_q(const SegC& sc, const RowC& rc, i
 // double-buffered by chunk parity, so set s owns buffer s).  The evaluation form of every
 // (quadrant, group) pair comes from the planner warp (tc_plan.cuh).
 constexpr int NPL = 4;   // plan ring slots
-template <int SETS, bool SLIM>
-constexpr int bq_threads() { return (4 * (SLIM ? 1 : 2) * SETS + 3) * 32; }
+// NPS = elementwise threads per row of the SLIM configuration (the others always use two).
+template <int SETS, bool SLIM, int NPS = 1>
+constexpr int bq_threads() { return (4 * (SLIM ? NPS : 2) * SETS + (SLIM && NPS > 1 ? 2 : 3)) * 32; }
 
-template <int SETS, bool SLIM>
-__global__ void __launch_bounds__(bq_threads<SETS, SLIM>(), SLIM ? 2 : 1)
+template <int SETS, bool SLIM, int NPS = 1>
+__global__ void __launch_bounds__(bq_threads<SETS, SLIM, NPS>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
@@ -306,13 +307,22 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 SM_BIN = C::SM_BIN, SM_A = C::SM_A, SM_BS = C::SM_BS, SM_PLAN = C::SM_PLAN, SM_META = C::SM_META,
                 SM_BAR = C::SM_BAR;
   constexpr uint32_t T_S = C::T_S, T_DP = C::T_DP, T_DQ = C::T_DQ, T_REL = C::T_REL, T_DE = C::T_DE;
-  constexpr int NP = SLIM ? 1 : 2;    // elementwise threads per row
+  constexpr int NP = SLIM ? NPS : 2;  // elementwise threads per row
   constexpr int W = 32;               // columns per group
   constexpr int NG = 2 / NP;          // groups of a chunk a thread walks through (slim: both)
   constexpr int NEW = 128 * NP;       // elementwise threads per set
   constexpr int NALL = NEW * SETS;    // all elementwise threads
-  constexpr int NB = NP * SETS;       // private bin arrays per row
-  constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = 4 * NB + 2;   // producer / MMA / planner warp
+  constexpr int NB = NP * SETS;       // elementwise threads per row over all sets (output / id slices)
+  // private bin arrays per row.  SLIM has room for one: with two threads per row they share it --
+  // interior diagonal slots have a single writer by construction, the constant classes are flushed
+  // one thread after the other, and the host never picks this configuration when the generic
+  // (read-modify-write) form can occur.
+  constexpr int NBA = SLIM ? 1 : NB;
+  constexpr bool SHARED_BIN = SLIM && NP > 1;
+  // producer / MMA / planner warp; with two threads per row the slim configuration has no spare
+  // warp (register file: 2 x 320 threads x 96), so its producer doubles as the planner
+  constexpr bool MERGED = SLIM && NP > 1;
+  constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = MERGED ? -1 : 4 * NB + 2;
   constexpr int RB = SLIM ? 32 : 128 / NB;   // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   static_assert(!SLIM || SETS == 1, "the slim configuration has a single S / dP buffer");
@@ -365,29 +375,54 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int pd = a.seg[0].side.max_distance;
   const bool perm = (2 * pd + 1 <= R);
 
+  auto load_tile = [&]() {
+    mbar_arrive_expect_tx(&bars->q_full, 2 * TM * 128 + rpad * 128);
+    tma_load_4d(smem + SM_Q, &map_q, &bars->q_full, 0, i0, h, b);
+    tma_load_4d(smem + SM_DO, &map_do, &bars->q_full, 0, i0, h, b);
+    if (rpad) tma_load_4d(smem + SM_E, &map_e, &bars->q_full, 0, 0, h, 0);
+  };
+  auto load_chunk = [&](int c) {
+    const int st = c % NST;
+    TRACE(4, 2 * c);
+    mbar_wait(&bars->kv_empty[st], ((c / NST) & 1) ^ 1);
+    TRACE(4, 2 * c + 1);
+    const bool first = c < r0.n;
+    const int key0 = first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN;
+    uint8_t* ks = smem + SM_KV + st * (2 * TN * 128);
+    mbar_arrive_expect_tx(&bars->kv_full[st], 2 * TN * 128);
+    tma_load_4d(ks, first ? &map_k0 : &map_k1, &bars->kv_full[st], 0, key0, h, b);
+    tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
+  };
+  auto run_planner = [&](auto pre) {
+    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
+    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    const Side* qs_side = nullptr;
+    if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
+    if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
+    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.kb, r1.kb, b, i0, qs_side ? qs_side->sent : nullptr,
+                                qs_side ? qs_side->sent_len : 0, a.rows.len, plans, bars->pl_full, bars->pl_empty, lane,
+                                pre);
+  };
   if (warp == WP) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(&bars->q_full, 2 * TM * 128 + rpad * 128);
-      tma_load_4d(smem + SM_Q, &map_q, &bars->q_full, 0, i0, h, b);
-      tma_load_4d(smem + SM_DO, &map_do, &bars->q_full, 0, i0, h, b);
-      if (rpad) tma_load_4d(smem + SM_E, &map_e, &bars->q_full, 0, 0, h, 0);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % NST;
-        mbar_wait(&bars->kv_empty[st], ((c / NST) & 1) ^ 1);
-        const bool first = c < r0.n;
-        const int key0 = first ? r0.kb + c * TN : r1.kb + (c - r0.n) * TN;
-        uint8_t* ks = smem + SM_KV + st * (2 * TN * 128);
-        mbar_arrive_expect_tx(&bars->kv_full[st], 2 * TN * 128);
-        tma_load_4d(ks, first ? &map_k0 : &map_k1, &bars->kv_full[st], 0, key0, h, b);
-        tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
-      }
+    if (MERGED) {
+      // producer and planner in one warp: the chunk's loads go out, then the chunk is classified
+      if (lane == 0) load_tile();
+      run_planner([&](int c) {
+        if (lane == 0) load_chunk(c);
+        __syncwarp();
+      });
+    } else if (elect_one()) {
+      load_tile();
+      for (int c = 0; c < nchunks; ++c) load_chunk(c);
     }
   } else if (warp == WM) {
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_dq = make_idesc_bf16(TM, 64, 0, 1);
       const uint32_t q_addr = smem_u32(smem + SM_Q), do_addr = smem_u32(smem + SM_DO);
+      TRACE(3, 0);
       mbar_wait(&bars->q_full, 0);
+      TRACE(3, 1);
       tc_fence_after_sync();
       if (rpad) {
         const uint32_t idesc_r = make_idesc_bf16(TM, rpad, 0, 0);
@@ -401,7 +436,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto issue_sdp = [&](int c) {
         const int st = c % NST;
         mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
+        TRACE(3, 4 + 4 * c);
         mbar_wait(&bars->kv_full[st], (c / NST) & 1);
+        TRACE(3, 5 + 4 * c);
         tc_fence_after_sync();
         const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
         const uint32_t v_addr = k_addr + TN * 128;
@@ -414,10 +451,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_ss(tmem + T_DP + BUF(c) * 64, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
                   make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
         umma_commit(&bars->sdp_full[BUF(c)]);
+        TRACE(3, 6 + 4 * c);
       };
       auto issue_dq = [&](int pc) {
         const int st = pc % NST;
         mbar_wait(&bars->ds_full[BUF(pc)], PH(pc));
+        TRACE(3, 7 + 4 * pc);
         tc_fence_after_sync();
         mbar_arrive(&bars->pl_empty[pc % NPL]);   // every elementwise thread is done with plan pc
         const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
@@ -462,15 +501,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-  } else if (warp == WPL) {
+  } else if (!MERGED && warp == WPL) {
     // ===================== planner =====================
-    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
-    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
-    const Side* qs_side = nullptr;
-    if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
-    if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
-    plan::planner_loop<NPL, TN>(ps0, ps1, r0.n, r1.n, r0.kb, r1.kb, b, i0, qs_side ? qs_side->sent : nullptr,
-                                qs_side ? qs_side->sent_len : 0, a.rows.len, plans, bars->pl_full, bars->pl_empty, lane);
+    run_planner(plan::NoPre());
   } else {
     // ===================== elementwise warps (NP threads per row) =====================
     if (tid == 0) TRACE(1, 0);
@@ -482,8 +515,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-    float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
-    for (int x = lane + 32 * quad; x < RB * TM; x += 128) bin[x] = 0.f;
+    float* bin = bins + (SLIM ? 0 : bidx) * RB * TM;   // slot-ordered, private to (set, part, row) unless SHARED_BIN
+    for (int x = lane + 32 * quad + (SHARED_BIN ? 128 * part0 : 0); x < RB * TM; x += (SHARED_BIN ? 128 * NP : 128)) bin[x] = 0.f;
     if (!SLIM)   // slim: the tile lives in a K/V stage and is written in full by the epilogue
       for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
     const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
@@ -559,7 +592,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tc_fence_after_sync();
 #pragma unroll 1
         for (int pg = 0; pg < NG; ++pg) {
-        const int part = SLIM ? pg : part0;
+        const int part = NG > 1 ? pg : part0;
         const int g0 = kb + (c - c_begin) * TN + part * W;
         const uint32_t t_s = tmem + T_S + BUF(c) * 64 + lane_sel + part * W;
         const uint32_t t_dp = tmem + T_DP + BUF(c) * 64 + lane_sel + part * W;
@@ -757,10 +790,16 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (id >= 0 && id < R) bin[plan::slot_of_id(id, pd, perm) * TM + row] += v;
       };
       const int dd = sc0.D;   // both segments of a row set share max_distance
-      flush(dd, accP);
-      flush(2 * dd, accN);
-      flush(2 * dd + 1, accX);
-      flush(2 * dd + 2, accX1);
+#pragma unroll 1
+      for (int turn = 0; turn < (SHARED_BIN ? NP : 1); ++turn) {
+        if (!SHARED_BIN || turn == part0) {
+          flush(dd, accP);
+          flush(2 * dd, accN);
+          flush(2 * dd + 1, accX);
+          flush(2 * dd + 2, accX1);
+        }
+        if (SHARED_BIN && turn + 1 < NP) named_bar_sync(1, NALL);   // the row's other thread adds next
+      }
     }
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
     if (tid == 0) TRACE(1, 5);
@@ -786,7 +825,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (pid < R) {
             const int sl = plan::slot_of_id(pid, pd, perm);
 #pragma unroll
-            for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
+            for (int pp = 0; pp < NBA; ++pp) w += bins[(pp * RB + sl) * TM + row];
           }
           w8[x] = w;
         }
@@ -1110,7 +1149,9 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   // One query chunk: Q and dO tiles plus the 64-row record block (one elected lane).
   auto load_chunk = [&](int c) {
     const int st = c % NST;
+    TRACE(5, 2 * c);
     mbar_wait(&bars->qd_empty[st], ((c / NST) & 1) ^ 1);
+    TRACE(5, 2 * c + 1);
     const bool first = c < r0.n;
     const TcQuerySource& src = first ? p.src[0] : p.src[1];
     const int q0 = first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN;
@@ -1459,7 +1500,7 @@ static bool g_attr_q = false, g_attr_kv = false;
 
 #ifdef MLT_TC_TRACE
 extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_trace_b, sizeof(unsigned long long) * 3 * 256);
+  return (int)cudaMemcpyFromSymbol(out, g_trace_b, sizeof(unsigned long long) * 6 * 256);
 }
 #endif
 
@@ -1472,6 +1513,9 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
                                bq::Cfg<false>::SM_ALLOC);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               bq::Cfg<true>::SM_ALLOC);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                bq::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
@@ -1514,11 +1558,37 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   auto seg_chunks = [](const KeySeg& sg) { return sg.band ? (TM + 2 * sg.radius + TN - 1) / TN : (sg.len + TN - 1) / TN; };
   const int est_chunks = seg_chunks(a.seg[0]) + (a.nseg > 1 ? seg_chunks(a.seg[1]) : 0);
   // 1: one warp set, 2: two warp sets on alternate chunks (many chunks: dense global rows),
-  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64)
+  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64), one elementwise thread per row,
+  // 4: slim with two elementwise threads per row sharing the row's bin array
   static const int force_cfg = getenv("MLT_BWD_Q_CFG") ? atoi(getenv("MLT_BWD_Q_CFG")) : 0;
+  // Configuration 4 must never meet the generic evaluation form (its bins are read-modify-write):
+  // that form is chosen for explicit side inputs, 2-D ids, a relative table that does not match the
+  // slot order, and for diagonal / sentence groups cut by the sequence end or the band edge.
+  const int pd = a.seg[0].side.max_distance;
+  auto seg_never_generic = [&](const KeySeg& sg) {
+    const Side& sd = sg.side;
+    if (sd.mask_rule == MR_EXPLICIT || sg.len % 32 != 0) return false;
+    if (sg.band && (sg.radius < 64 || sg.radius % 32 != 0)) return false;
+    if (R == 0) return true;
+    const int D = sd.max_distance;
+    switch (sd.id_rule) {
+      case IDR_NONE: return true;
+      case IDR_1D: return 2 * pd + 1 <= R && pd == D;
+      case IDR_CROSS_QSENT:
+      case IDR_CROSS_KSENT: return 2 * D + 2 < R;
+      default: return false;
+    }
+  };
+  const bool slim2_ok = seg_never_generic(a.seg[0]) && (a.nseg < 2 || seg_never_generic(a.seg[1]));
+  // (4 measured slower than 3 on the c3_4096 long rows, 0.75 vs 0.66 ms: the tile is bound by the
+  // MMA <-> elementwise round trip of the single S / dP buffer and by the quadrant imbalance of the
+  // band chunks, not by the elementwise warps' issue rate.  It stays selectable for experiments.)
   int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
+  if (cfg == 4 && !slim2_ok) cfg = 3;
   if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
-  if (cfg == 3)
+  if (cfg == 4)
+    tc_bwd_q_kernel<1, true, 2><<<grid, bq_threads<1, true, 2>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (cfg == 3)
     tc_bwd_q_kernel<1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2)
     tc_bwd_q_kernel<2, false><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);

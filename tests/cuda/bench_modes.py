@@ -1,0 +1,71 @@
+"""Times fwd+bwd of the global-local operator with compact vs explicit side inputs, and the dense
+operator (config-2 shape, S = 512) with explicit 2-D ids vs compact descriptors.  Development probe."""
+import dataclasses
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+import mlt_b200  # noqa: F401
+from mlt_b200 import ops, synthetic
+from mlt_b200.feature_utils import CompactSideInputs
+
+NAMES = ('long_q', 'long_k', 'long_v', 'global_q', 'global_k', 'global_v', 'long_emb', 'long_bias',
+         'global_emb', 'global_bias')
+
+
+def timeit(fn, reps=5):
+  for _ in range(2):
+    fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps
+
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+_, shape = synthetic.CONFIGS['c3_4096']
+shape = dataclasses.replace(shape, batch=batch)
+x = synthetic.make_inputs(shape, seed=1238, dtype=torch.bfloat16)
+dev = [x[n].cuda().requires_grad_() for n in NAMES]
+dlo, dgo = x['d_long_out'].cuda(), x['d_global_out'].cuda()
+compact = CompactSideInputs(x['long_example_ids'].cuda(), x['global_example_ids'].cuda(),
+                            x['sentence_ids'].cuda(), shape.max_distance)
+explicit = ops.build_gl_side_inputs(compact, shape.local_radius)
+
+
+def gl(side):
+  def f():
+    lo, go = ops.global_local_attention(*dev, local_radius=shape.local_radius, side=side)
+    torch.autograd.backward([lo, go], [dlo, dgo])
+  return f
+
+
+print(f'global-local c3_4096 batch {batch}: compact {timeit(gl(compact)):.3f} ms, '
+      f'explicit {timeit(gl(explicit)):.3f} ms')
+
+# dense, config-2 shape: S = 512 (196 patches + text), 2-D ids for the patch block
+B, S, H, D, R = 32, 512, 12, 64, 32
+g = torch.Generator().manual_seed(7)
+q, k, v = [torch.randn(B, S, H, D, generator=g).to(torch.bfloat16).cuda().requires_grad_() for _ in range(3)]
+emb = (0.02 * torch.randn(R, H, D, generator=g)).to(torch.bfloat16).cuda().requires_grad_()
+bias = (0.02 * torch.randn(R, H, generator=g)).to(torch.bfloat16).cuda().requires_grad_()
+do = torch.randn(B, S, H, D, generator=g).to(torch.bfloat16).cuda()
+lengths = torch.randint(S // 2, S + 1, (B,), generator=g)
+eid = (torch.arange(S)[None, :] < lengths[:, None]).to(torch.int32).cuda()
+mask, ids = ops.build_dense_side_inputs(eid, 12)
+
+
+def dense(**kw):
+  def f():
+    o = ops.dense_relative_attention(q, k, v, emb, bias, **kw)
+    o.backward(do)
+  return f
+
+
+print(f'dense B {B} S {S}: explicit 1-D ids {timeit(dense(att_mask=mask, relative_att_ids=ids)):.3f} ms, '
+      f'compact {timeit(dense(compact=ops.DenseCompactSideInputs(eid, max_distance=12))):.3f} ms')

@@ -16,10 +16,10 @@ for _ in range(2):
   torch.autograd.backward([lo, go], [x['d_long_out'].cuda(), x['d_global_out'].cuda()])
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (ctypes.c_ulonglong * (3 * 256))()
+buf = (ctypes.c_ulonglong * (6 * 256))()
 print('rc', lib.mlt_debug_read_trace_b(buf))
-t = np.array(buf[:], dtype=np.int64).reshape(3, 256)
+t = np.array(buf[:], dtype=np.int64).reshape(6, 256)
 t0 = t[t > 0].min()
-for role, name in enumerate(['kv_elementwise', 'bq_elementwise', 'kv_mma']):
+for role, name in enumerate(['kv_elementwise', 'bq_elementwise', 'kv_mma', 'bq_mma', 'bq_producer', 'kv_producer']):
   vals = [(i, int(v - t0)) for i, v in enumerate(t[role]) if v > 0]
   print(name, vals)
