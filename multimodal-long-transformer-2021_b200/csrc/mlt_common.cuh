@@ -44,6 +44,8 @@ struct Side {
   int npr, core;        // 2-D rule: patches per row, core layers
 };
 
+inline bool side_is_explicit(const Side& s) { return s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT; }
+
 struct KeySeg {
   T4 k, v;
   int len;

@@ -209,8 +209,9 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
   return sc;
 }
 
-__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm, bool ex) {
   plan::PSeg s;
+  s.expl_ok = ex;
   s.c_begin = r.kb;
   s.c_end = r.ke;
   s.c_len = sg.len;
@@ -295,7 +296,9 @@ constexpr int NPL = 4;   // plan ring slots
 template <int SETS, bool SLIM, int NPS = 1>
 constexpr int bq_threads() { return (4 * (SLIM ? NPS : 2) * SETS + (SLIM && NPS > 1 ? 2 : 3)) * 32; }
 
-template <int SETS, bool SLIM, int NPS = 1>
+// EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
+// instantiations stay free of its code and register pressure.
+template <int SETS, bool SLIM, int NPS = 1, bool EX = false>
 __global__ void __launch_bounds__(bq_threads<SETS, SLIM, NPS>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
@@ -394,8 +397,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tma_load_4d(ks + TN * 128, first ? &map_v0 : &map_v1, &bars->kv_full[st], 0, key0, h, b);
   };
   auto run_planner = [&](auto pre) {
-    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
-    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm, EX);
+    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm, EX);
     const Side* qs_side = nullptr;
     if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
     if (a.nseg > 1 && ps1.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[1].side;
@@ -704,6 +707,44 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 for (int jj = 0; jj < W; ++jj) e[jj] = fmaf(e[jj], scale2, d0 == jj ? c1 : c0);
                 break;
               }
+              case plan::EXPL: if constexpr (EX) {
+                // explicit int32 tensors: this row's 32 consecutive entries (band: column k = j - i + r)
+                const Side& sd = *sc.sd;
+                const int d0 = g0 - i;
+                int jlo = 0, jhi = min(W, sc.ke - g0);
+                if (sc.band) {
+                  jlo = max(jlo, -sc.radius - d0);
+                  jhi = min(jhi, sc.radius - d0 + 1);
+                }
+                const uint32_t live = plan::span_bits(jlo, jhi);
+                const uint32_t take = row_ok ? live : 0u;
+                const int64_t eoff = (int64_t)b * sd.sb + (int64_t)i * sd.sq + (sc.band ? d0 + sc.radius : g0);
+                const bool vec = !sc.band && ((sd.sb | sd.sq) & 3) == 0 &&
+                                 __all_sync(0xffffffffu, take == 0xffffffffu);
+                if (sc.id_rule == IDR_EXPLICIT) {
+                  int id[W];
+                  plan::load_row32(sd.ids + eoff, vec && (reinterpret_cast<uintptr_t>(sd.ids) & 15) == 0, take, -1, id);
+#pragma unroll
+                  for (int jj = 0; jj < W; ++jj) {
+                    float rel = 0.f;
+                    if ((unsigned)id[jj] < (unsigned)sc.R) rel = rel_s[relmeta[id[jj]].slot_off + row];
+                    e[jj] = fmaf(e[jj], scale2, fmaf(rel, LOG2E, nm2l));
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < W; ++jj) e[jj] = fmaf(e[jj], scale2, nm2l);
+                }
+                if (sc.mask_rule == MR_EXPLICIT) {
+                  int ok[W];
+                  plan::load_row32(sd.mask + eoff, vec && (reinterpret_cast<uintptr_t>(sd.mask) & 15) == 0, take, 1, ok);
+#pragma unroll
+                  for (int jj = 0; jj < W; ++jj) e[jj] = ok[jj] != 0 ? e[jj] : lpm;
+                }
+                if (live != 0xffffffffu) {
+#pragma unroll
+                  for (int jj = 0; jj < W; ++jj) e[jj] = (live >> jj) & 1u ? e[jj] : -INFINITY;
+                }
+              } break;
               default: {   // KS
                 const float c0 = fmaf(rc.relX, LOG2E, nm2l), c1 = fmaf(rc.relX1, LOG2E, nm2l);
 #pragma unroll
@@ -762,6 +803,27 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int x = 0; x < W; ++x) sp += (d0 == x) ? ds[x] : 0.f;
               accX1 += sp;
               accX += tot - sp;
+            } else if (EX && mode == plan::EXPL) {
+              if (sc.id_rule == IDR_EXPLICIT) {
+                // ids re-read (L1 hits) instead of kept live across the exponentials; entries not taken
+                // read back as -1.  Read-modify-write in column order: same association as the generic form.
+                const Side& sd = *sc.sd;
+                const int d0 = g0 - i;
+                int jlo = 0, jhi = min(W, sc.ke - g0);
+                if (sc.band) {
+                  jlo = max(jlo, -sc.radius - d0);
+                  jhi = min(jhi, sc.radius - d0 + 1);
+                }
+                const uint32_t take = row_ok ? plan::span_bits(jlo, jhi) : 0u;
+                const int64_t eoff = (int64_t)b * sd.sb + (int64_t)i * sd.sq + (sc.band ? d0 + sc.radius : g0);
+                const bool vec = !sc.band && ((sd.sb | sd.sq) & 3) == 0 && (reinterpret_cast<uintptr_t>(sd.ids) & 15) == 0 &&
+                                 __all_sync(0xffffffffu, take == 0xffffffffu);
+                int id[W];
+                plan::load_row32(sd.ids + eoff, vec, take, -1, id);
+#pragma unroll
+                for (int x = 0; x < W; ++x)
+                  if ((unsigned)id[x] < (unsigned)sc.R) bin[relmeta[id[x]].slot_off + row] += ds[x];
+              }
             } else {  // KS
               float sp = 0.f;
 #pragma unroll
@@ -1024,8 +1086,9 @@ __device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRan
   return sc;
 }
 
-__device__ __forceinline__ plan::PSeg make_kv_pseg(const TcQuerySource& src, const SrcRange& r) {
+__device__ __forceinline__ plan::PSeg make_kv_pseg(const TcQuerySource& src, const SrcRange& r, bool ex) {
   plan::PSeg s;
+  s.expl_ok = ex;
   const Side& sd = src.q.side;
   s.c_begin = r.ib;
   s.c_end = r.ie;
@@ -1089,7 +1152,7 @@ constexpr int bk_threads() { return (4 * NP * SETS + (SLIM ? 2 : 3)) * 32; }
 // per-query constants arrive exponent-ready in the row records the query-centric pass published
 // (TcBwdQParams::rec_ws), so the common element costs
 //     p = ex2(fma(x, scale*log2e, rec[i][4 + id])),  ds = p * (dp - rec[i][2]).
-template <int NP, int SETS, bool SLIM>
+template <int NP, int SETS, bool SLIM, bool EX = false>
 __global__ void __launch_bounds__(bk_threads<NP, SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
@@ -1165,8 +1228,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     bulk_g2s(smem + SM_REC + st * TN * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
   };
   auto run_planner = [&](auto pre) {
-    const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0);
-    const plan::PSeg ps1 = make_kv_pseg(p.nsrc > 1 ? p.src[1] : p.src[0], r1);
+    const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0, EX);
+    const plan::PSeg ps1 = make_kv_pseg(p.nsrc > 1 ? p.src[1] : p.src[0], r1, EX);
     const Side* ks_side = nullptr;   // row-side (key) sentence ids: rule KSENT
     if (ps0.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[0].q.side;
     if (p.nsrc > 1 && ps1.id_rule == IDR_CROSS_KSENT) ks_side = &p.src[1].q.side;
@@ -1369,6 +1432,29 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
                   const int o = min(max(d0 - x, -sc.D), sc.D);
                   t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * 64 + x]);
                 }
+              } else if (EX && mode == plan::EXPL) {
+                // explicit int32 tensors [B, Lq, W]: entry of (query g0 + x, key j); consecutive keys
+                // (= lanes) are adjacent in memory, so every load is one coalesced line per warp
+                const Side& sd = *sc.sd;
+                int ilo = 0, ihi = min(WS, sc.ie - g0);
+                if (sc.band) {
+                  ilo = max(ilo, d0 - sc.radius);
+                  ihi = min(ihi, d0 + sc.radius + 1);
+                }
+                if (!key_ok) ihi = ilo;
+                const uint32_t live = plan::span_bits(ilo, ihi);
+                const int64_t est = sd.sq - (sc.band ? 1 : 0);   // next query, same key
+                const int64_t eoff = (int64_t)b * sd.sb + (int64_t)g0 * sd.sq + (sc.band ? d0 + sc.radius : j);
+                const bool has_i = sc.id_rule == IDR_EXPLICIT, has_m = sc.mask_rule == MR_EXPLICIT;
+#pragma unroll
+                for (int x = 0; x < WS; ++x) {
+                  const bool lv = (live >> x) & 1u;
+                  int id = -1, ok = 1;
+                  if (lv && has_i) id = __ldg(sd.ids + eoff + x * est);
+                  if (lv && has_m) ok = __ldg(sd.mask + eoff + x * est);
+                  const int f = (unsigned)id < (unsigned)sc.R ? 4 + id : 0;
+                  t[x] = ok != 0 ? fmaf(__uint_as_float(v[x]), scale2, rec[f * 64 + x]) : rec[64 + x];
+                }
               } else {
                 const float* c0 = rec + (5 + 2 * sc.D) * 64;
                 if (mode == plan::QS) {          // row-side sentence: key j belongs to query (k_sent)
@@ -1389,8 +1475,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   #pragma unroll
                 for (int x = 0; x < WS; ++x) t[x] = masked ? lp[x] : t[x];
               }
-              // 3. probabilities; EDGE: dead columns may carry garbage records -> select, not multiply
-              if (mode == plan::EDGE) {
+              // 3. probabilities; EDGE / EXPL: dead columns may carry garbage records -> select, not multiply
+              if (mode == plan::EDGE || (EX && mode == plan::EXPL)) {
                 int ilo = 0, ihi = min(WS, sc.ie - g0);
                 if (sc.band) {
                   ilo = max(ilo, d0 - sc.radius);
@@ -1506,17 +1592,17 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(uns
 
 int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (!g_attr_q) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_q_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         bq::Cfg<false>::SM_ALLOC);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               bq::Cfg<false>::SM_ALLOC);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               bq::Cfg<true>::SM_ALLOC);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_q_kernel<1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               bq::Cfg<true>::SM_ALLOC);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel, int bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set(tc_bwd_q_kernel<2, false>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, false>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, true>, bq::Cfg<true>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, true, 2>, bq::Cfg<true>::SM_ALLOC);
+    set(tc_bwd_q_kernel<2, false, 1, true>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, false, 1, true>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, true, 1, true>, bq::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1586,12 +1672,20 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
   if (cfg == 4 && !slim2_ok) cfg = 3;
   if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
+  // explicit int32 side inputs: the instantiations that carry the EXPL form (never configuration 4)
+  const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
   if (cfg == 4)
     tc_bwd_q_kernel<1, true, 2><<<grid, bq_threads<1, true, 2>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (cfg == 3 && ex)
+    tc_bwd_q_kernel<1, true, 1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 3)
     tc_bwd_q_kernel<1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (cfg == 2 && ex)
+    tc_bwd_q_kernel<2, false, 1, true><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2)
     tc_bwd_q_kernel<2, false><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (ex)
+    tc_bwd_q_kernel<1, false, 1, true><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else
     tc_bwd_q_kernel<1, false><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
@@ -1599,14 +1693,16 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   if (!g_attr_kv) {
-    cudaError_t e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         bk::Cfg<false>::SM_ALLOC);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               bk::Cfg<false>::SM_ALLOC);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_bwd_kv_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               bk::Cfg<true>::SM_ALLOC);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel, int bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set(tc_bwd_kv_kernel<2, 2, false>, bk::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_kv_kernel<4, 1, false>, bk::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_kv_kernel<2, 1, true>, bk::Cfg<true>::SM_ALLOC);
+    set(tc_bwd_kv_kernel<2, 2, false, true>, bk::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_kv_kernel<4, 1, false, true>, bk::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_kv_kernel<2, 1, true, true>, bk::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_kv = true;
   }
@@ -1641,10 +1737,17 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   static const int force_kv = getenv("MLT_KV_CFG") ? atoi(getenv("MLT_KV_CFG")) : 0;   // 1: <4,1>  2: <2,2>  3: slim
   const bool slim_ok = p.src[0].rw <= 32 && p.src[1].rw <= 32;
   const int cfg = force_kv ? force_kv : (est_chunks >= 16 ? 2 : (slim_ok ? 3 : 1));
-  if (cfg == 3 && slim_ok)
+  const bool ex = side_is_explicit(a.src[0].side) || (a.nsrc > 1 && side_is_explicit(a.src[1].side));
+  if (cfg == 3 && slim_ok && ex)
+    tc_bwd_kv_kernel<2, 1, true, true><<<grid, bk_threads<2, 1, true>(), bk::Cfg<true>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  else if (cfg == 3 && slim_ok)
     tc_bwd_kv_kernel<2, 1, true><<<grid, bk_threads<2, 1, true>(), bk::Cfg<true>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  else if (cfg == 2 && ex)
+    tc_bwd_kv_kernel<2, 2, false, true><<<grid, bk_threads<2, 2, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   else if (cfg == 2)
     tc_bwd_kv_kernel<2, 2, false><<<grid, bk_threads<2, 2, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  else if (ex)
+    tc_bwd_kv_kernel<4, 1, false, true><<<grid, bk_threads<4, 1, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   else
     tc_bwd_kv_kernel<4, 1, false><<<grid, bk_threads<4, 1, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
   return (int)cudaGetLastError();

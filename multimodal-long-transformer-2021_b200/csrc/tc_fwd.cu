@@ -102,8 +102,9 @@ __device__ __forceinline__ SegRange seg_range(const KeySeg& sg, int i0) {
   return r;
 }
 
-__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
+__device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm, bool ex) {
   plan::PSeg s;
+  s.expl_ok = ex;
   s.c_begin = r.kb;
   s.c_end = r.ke;
   s.c_len = sg.len;
@@ -201,6 +202,9 @@ __device__ __forceinline__ float score_generic(float x, const SegC& sc, const Ro
   return v;
 }
 
+// EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
+// instantiation stays free of its code and register pressure.
+template <bool EX>
 __global__ void __launch_bounds__(NTHREADS, 2)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k0,
               const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_k1,
@@ -321,8 +325,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp == 6) {
     // ===================== planner =====================
-    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm);
-    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm);
+    const plan::PSeg ps0 = make_pseg(a.seg[0], r0, R, pd, perm, EX);
+    const plan::PSeg ps1 = make_pseg(a.nseg > 1 ? a.seg[1] : a.seg[0], r1, R, pd, perm, EX);
     // row-side sentence ranges (only the QSENT rule needs them; both segments share the array)
     const Side* qs_side = nullptr;
     if (ps0.id_rule == IDR_CROSS_QSENT) qs_side = &a.seg[0].side;
@@ -550,6 +554,44 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 for (int jj = 0; jj < 32; ++jj) t[jj] = fmaf(t[jj], a.scale, cp->cs[32 * g + jj] == i ? c1 : c0);
                 break;
               }
+              case plan::EXPL: if constexpr (EX) {
+                // explicit int32 tensors: this row's 32 consecutive entries (band: column k = j - i + r)
+                const Side& sd = *sc.sd;
+                const int d0 = g0 - i;
+                int jlo = 0, jhi = min(32, sc.ke - g0);
+                if (sc.band) {
+                  jlo = max(jlo, -sc.radius - d0);
+                  jhi = min(jhi, sc.radius - d0 + 1);
+                }
+                const uint32_t live = plan::span_bits(jlo, jhi);
+                const uint32_t take = row_ok ? live : 0u;   // rows beyond the end: no loads (unmasked, no id)
+                const int64_t eoff = (int64_t)b * sd.sb + (int64_t)i * sd.sq + (sc.band ? d0 + sc.radius : g0);
+                const bool vec = !sc.band && ((sd.sb | sd.sq) & 3) == 0 &&
+                                 __all_sync(0xffffffffu, take == 0xffffffffu);
+                if (sc.id_rule == IDR_EXPLICIT) {
+                  int id[32];
+                  plan::load_row32(sd.ids + eoff, vec && (reinterpret_cast<uintptr_t>(sd.ids) & 15) == 0, take, -1, id);
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj) {
+                    float rel = 0.f;
+                    if ((unsigned)id[jj] < (unsigned)sc.R) rel = rel_s[relmeta[id[jj]].slot_off + row];
+                    t[jj] = fmaf(t[jj], a.scale, rel);
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj) t[jj] *= a.scale;
+                }
+                if (sc.mask_rule == MR_EXPLICIT) {
+                  int ok[32];
+                  plan::load_row32(sd.mask + eoff, vec && (reinterpret_cast<uintptr_t>(sd.mask) & 15) == 0, take, 1, ok);
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj) t[jj] += ok[jj] != 0 ? 0.f : a.neg;
+                }
+                if (live != 0xffffffffu) {
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj) t[jj] = (live >> jj) & 1u ? t[jj] : -INFINITY;
+                }
+              } break;
               default:
                 break;  // GEN: evaluated above
             }
@@ -717,7 +759,9 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   // experiment knob: extra dynamic shared memory forces one CTA per SM
   static const int extra_smem = getenv("MLT_FWD_ONE_CTA") ? 100 * 1024 : 0;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -740,7 +784,10 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
-  tc_fwd_kernel<<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
+  if (side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side)))
+    tc_fwd_kernel<true><<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
+  else
+    tc_fwd_kernel<false><<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 

@@ -12,7 +12,9 @@
 //   DIAG  1-D rule near the diagonal: gather from the slot-ordered row table
 //   QS    cross block that contains the sentence column of some row      (+ select)
 //   KS    cross block that contains columns belonging to some row's sentence (+ select)
-//   GEN   anything else (explicit int32 side inputs, 2-D ids, ...)
+//   EXPL  explicit int32 mask / id tensors (the reference's own call signature): the row's 32
+//         consecutive entries are loaded with 128-bit accesses where the layout allows
+//   GEN   anything else (2-D ids, mixed rules, ...)
 // "Row" = the index the thread owns (TMEM lane), "column" = the index that varies inside a chunk.
 // In the forward and the query-centric backward rows are queries and columns are keys; in the
 // key-centric backward rows are keys and columns are queries (the planner is told which).
@@ -26,7 +28,7 @@
 namespace mlt {
 namespace plan {
 
-enum Mode : int { DEAD = 0, FAST, EDGE, DIAG, QS, KS, GEN };
+enum Mode : int { DEAD = 0, FAST, EDGE, DIAG, QS, KS, GEN, EXPL };
 // constant relative classes of a group (which per-row constant applies)
 enum CCls : int { C_NONE = 0, C_POS = 1, C_NEG = 2, C_CROSS = 3 };
 
@@ -62,6 +64,7 @@ struct PSeg {
   const int32_t* c_sent; // per-column sentence ids [B, c_len] (or null)
   int64_t c_eid_stride, c_sent_stride;
   bool col_sent;         // sentence ids live on the column side (KS form); else on the row side (QS)
+  bool expl_ok;          // the kernel instantiation carries the EXPL form (else explicit tensors take GEN)
 };
 
 // Per-tile row-side sentence ranges (QS form): [rs_min[w], rs_max[w]] of quadrant w.
@@ -123,8 +126,14 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
     }
     uint32_t mode, ccls = C_NONE, flags = 0;
     const bool dead = g0 >= s.c_end || (s.band && (o_min > s.radius || o_max < -s.radius));
+    // explicit tensors only (each of mask / ids either explicit or absent)
+    const bool expl = s.expl_ok && (s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT) &&
+                      (s.mask_rule == MR_EXPLICIT || s.mask_rule == MR_NONE) &&
+                      (s.id_rule == IDR_EXPLICIT || s.id_rule == IDR_NONE);
     if (dead) {
       mode = DEAD;
+    } else if (expl) {
+      mode = EXPL;
     } else {
       const bool all_live = (g0 + 31 < s.c_end) && (!s.band || (o_min >= -s.radius && o_max <= s.radius));
       bool gen = false;
@@ -176,6 +185,32 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
     out->q[w][g] = mode | (ccls << 8) | flags;
     out->q[w][2 + g] = (uint32_t)(g ? f1 : f0);
   }
+}
+
+// ---- explicit side inputs -----------------------------------------------------------------------
+// 32 consecutive int32 entries of one row of an explicit mask / id tensor, entry x taken only where
+// bit x of `take` is set (others = fill).  `vec` (warp-uniform; implies take == all) = the 32 entries
+// of every lane are 16-byte aligned: eight 128-bit loads.
+__device__ __forceinline__ void load_row32(const int32_t* p, bool vec, uint32_t take, int fill, int (&out)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(p) + x);
+      out[4 * x] = v.x;
+      out[4 * x + 1] = v.y;
+      out[4 * x + 2] = v.z;
+      out[4 * x + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int x = 0; x < 32; ++x) out[x] = (take >> x) & 1u ? __ldg(p + x) : fill;
+  }
+}
+// bit x set <=> lo <= x < hi  (0 <= lo, hi <= 32)
+__device__ __forceinline__ uint32_t span_bits(int lo, int hi) {
+  if (hi <= lo) return 0u;
+  const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  return upto_hi & ~((1u << lo) - 1u);
 }
 
 // ---- per-row relative table ---------------------------------------------------------------------

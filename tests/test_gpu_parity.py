@@ -315,11 +315,13 @@ def test_tc_backward_configurations_agree(env):
       x = synthetic.make_inputs(shape, seed=21, dtype=torch.bfloat16)
       side = t.oracle_side(x, shape)
       rl, rg, rgrads = t.run_oracle_gl(x, shape, side)
-      lo, go, grads = t.run_cuda_gl(x, shape, t.compact_of(x, shape), impl='tc')
-      assert t.abs_err(lo, rl) < t.BF16_ABS and t.abs_err(go, rg) < t.BF16_ABS
-      for name, got, want in zip(t.NAMES, grads, rgrads):
-        scale = max(1.0, want.abs().max().item())
-        assert t.abs_err(got, want) < t.BF16_ABS * scale, name
+      # compact descriptors (planner forms) and the explicit int32 tensors (EXPL form)
+      for cuda_side in (t.compact_of(x, shape), {k: v.cuda() for k, v in side.items()}):
+        lo, go, grads = t.run_cuda_gl(x, shape, cuda_side, impl='tc')
+        assert t.abs_err(lo, rl) < t.BF16_ABS and t.abs_err(go, rg) < t.BF16_ABS
+        for name, got, want in zip(t.NAMES, grads, rgrads):
+          scale = max(1.0, want.abs().max().item())
+          assert t.abs_err(got, want) < t.BF16_ABS * scale, name
       print('ok')
   ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
   r = subprocess.run([sys.executable, '-c', code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
