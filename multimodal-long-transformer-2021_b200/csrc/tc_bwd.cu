@@ -47,6 +47,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(role, idx) do {} while (0)
 #endif
 constexpr float LOG2E = 1.4426950408889634f;
+// Row records (TcBwdQParams::rec_ws): field stride inside a 64-row block, in floats.  65, not 64: the
+// key-centric pass reads field (4 + id) of ONE query from 32 lanes with different ids -- with a
+// stride of 64 all of them hit the same shared-memory bank (up to 25-way conflict on every gather of
+// the diagonal groups); 65 spreads consecutive fields over consecutive banks.
+constexpr int RSF = 65;
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -171,7 +176,7 @@ struct TcBwdQParams {
   float4* rowstat;    // ws [B, H, lp] = (m * log2e, 1 / l, delta, 0)     (tc_bwd_prep_kernel)
   // ws [B, H, lp / 64, rw + 4, 64]: the per-row records the key-centric pass consumes, exponent-ready,
   // stored field-major per block of 64 rows (one contiguous bulk copy per query chunk; in shared
-  // memory field f of query x sits at f * 64 + x: immediate offsets, warp-broadcast reads):
+  // memory field f of query x sits at f * RSF + x: immediate offsets, warp-broadcast reads):
   //   field 0      -(m*log2e + log2 l)               exponent term of an element without relative score
   //   field 1      log2 of p for a MASKED element    log2(1/l) on fully-masked rows, -inf otherwise
   //   field 2      delta = sum_c dO*O      field 3: 0
@@ -544,12 +549,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     const int rs_stride = p.rw + 4;
     // field 0 of this row: block (i / 64), lane (i % 64); consecutive fields are 64 floats apart
-    float* rec_row = p.rec_ws + (((int64_t)(b * a.H + h) * (p.lp >> 6) + (i >> 6)) * rs_stride) * 64 + (i & 63);
+    float* rec_row = p.rec_ws + (((int64_t)(b * a.H + h) * (p.lp >> 6) + (i >> 6)) * rs_stride) * RSF + (i & 63);
     if (bidx == 0 && row_ok) {
       rec_row[0] = nm2l;
-      rec_row[64] = lpm;
-      rec_row[128] = delta;
-      rec_row[192] = 0.f;
+      rec_row[RSF] = lpm;
+      rec_row[2 * RSF] = delta;
+      rec_row[3 * RSF] = 0.f;
     }
     if (rpad && tid < 64)
       plan::rel_meta_init(relmeta, tid, reinterpret_cast<const __nv_bfloat16*>(a.rows.bias), a.H, h, R, pd, perm,
@@ -560,14 +565,14 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait_warp(&bars->rel_full, 0);
       if (tid == 0) TRACE(1, 2);
       tc_fence_after_sync();
-      float* ws_row = rec_row + 4 * 64;
+      float* ws_row = rec_row + 4 * RSF;
       const int rw = p.rw;
       plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale,
                             [&](int c0, const float (&val)[16]) {
                               if (row_ok) {   // one coalesced 128-byte store per id and warp
 #pragma unroll
                                 for (int x = 0; x < 16; ++x)
-                                  if (c0 + x < rw) ws_row[(c0 + x) * 64] = fmaf(val[x], LOG2E, nm2l);
+                                  if (c0 + x < rw) ws_row[(c0 + x) * RSF] = fmaf(val[x], LOG2E, nm2l);
                               }
                             });
     }
@@ -1010,7 +1015,7 @@ struct Cfg {
   static constexpr int SM_V = SM_K + TM * 128;           // 16 KB
   static constexpr int SM_QD = SM_V + TM * 128;          // NST x (Q 8 KB + dO 8 KB)
   static constexpr int SM_REC = SM_QD + NST * 2 * TN * 128;      // NST x [64] row records (see TcBwdQParams::rec_ws)
-  static constexpr int SM_PLAN = SM_REC + NST * TN * RSMAX * 4;  // NPL x ChunkPlan
+  static constexpr int SM_PLAN = SM_REC + NST * RSF * RSMAX * 4;  // NPL x ChunkPlan
   static constexpr int SM_BAR = SM_PLAN + NPL * (int)sizeof(plan::ChunkPlan);
   static constexpr int SM_ALLOC = SM_BAR + 256 + 1024;
   static constexpr uint32_t TCOLS = SLIM ? 256 : 512;
@@ -1220,12 +1225,12 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     const int q0 = first ? r0.ib + c * TN : r1.ib + (c - r0.n) * TN;
     const int rs = src.rw + 4;
     uint8_t* qs = smem + SM_QD + st * (2 * TN * 128);
-    const int64_t prow = ((int64_t)(b * p.H + h) * (src.lp >> 6) + (q0 >> 6)) * 64;   // record block of q0
-    const uint32_t rec_bytes = TN * rs * 4;
+    const int64_t prow = ((int64_t)(b * p.H + h) * (src.lp >> 6) + (q0 >> 6)) * RSF;   // record block of q0
+    const uint32_t rec_bytes = RSF * rs * 4;
     mbar_arrive_expect_tx(&bars->qd_full[st], 2 * TN * 128 + rec_bytes);
     tma_load_4d(qs, first ? &map_q0 : &map_q1, &bars->qd_full[st], 0, q0, h, b);
     tma_load_4d(qs + TN * 128, first ? &map_do0 : &map_do1, &bars->qd_full[st], 0, q0, h, b);
-    bulk_g2s(smem + SM_REC + st * TN * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
+    bulk_g2s(smem + SM_REC + st * RSF * RSMAX * 4, src.rec_ws + prow * rs, rec_bytes, &bars->qd_full[st]);
   };
   auto run_planner = [&](auto pre) {
     const plan::PSeg ps0 = make_kv_pseg(p.src[0], r0, EX);
@@ -1344,8 +1349,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         mbar_wait_warp(&bars->sdp_full[BUF(c)], PH(c));
         if (tid == 0) TRACE(0, 4 * c + 1);
         tc_fence_after_sync();
-        // record fields of this thread's query slice: field f of query x at rec[f * 64 + x]
-        const float* recw = reinterpret_cast<const float*>(smem + SM_REC + st * TN * RSMAX * 4) + part * W;
+        // record fields of this thread's query slice: field f of query x at rec[f * RSF + x]
+        const float* recw = reinterpret_cast<const float*>(smem + SM_REC + st * RSF * RSMAX * 4) + part * W;
         const int32_t* cew = cp->ce + part * W;
         const int32_t* csw = cp->cs + part * W;
         const uint32_t w0 = cp->q[quad][grp];
@@ -1384,8 +1389,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               float pv = 0.f, ds = 0.f;
               if (live) {
                 const float* r = rec + ii;
-                pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * 64]) : r[64]);
-                ds = pv * (__uint_as_float(dpr) - r[128]);
+                pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * RSF]) : r[RSF]);
+                ds = pv * (__uint_as_float(dpr) - r[2 * RSF]);
               }
               __syncwarp();   // the generic evaluation diverges per row; tcgen05.st needs the converged warp
               tmem_st1(t_s + ii, __float_as_uint(pv));
@@ -1407,10 +1412,10 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
             tmem_ldN(t_dp, w);
             tmem_wait_ld();
             // unmasked: exponent = x * scale2 + field(4 + id); masked: the per-query constant field 1
-            const float* dl = rec + 2 * 64;
+            const float* dl = rec + 2 * RSF;
             if (mode == plan::FAST) {
               const float gmul = masked ? 0.f : scale2;
-              const float* cc = rec + (masked ? 1 : coff) * 64;
+              const float* cc = rec + (masked ? 1 : coff) * RSF;
   #pragma unroll
               for (int x = 0; x < WS / 2; ++x) {
                 const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, cc[2 * x]));
@@ -1423,14 +1428,14 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               float t[WS];
               const int d0 = j - g0;   // offset(key - query) = d0 - x
               if (mode == plan::EDGE) {
-                const float* cc = rec + coff * 64;
+                const float* cc = rec + coff * RSF;
   #pragma unroll
                 for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, cc[x]);
               } else if (mode == plan::DIAG) {
   #pragma unroll
                 for (int x = 0; x < WS; ++x) {
                   const int o = min(max(d0 - x, -sc.D), sc.D);
-                  t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * 64 + x]);
+                  t[x] = fmaf(__uint_as_float(v[x]), scale2, rec[(4 + (o >= 0 ? o : sc.D - o)) * RSF + x]);
                 }
               } else if (EX && mode == plan::EXPL) {
                 // explicit int32 tensors [B, Lq, W]: entry of (query g0 + x, key j); consecutive keys
@@ -1453,21 +1458,21 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
                   if (lv && has_i) id = __ldg(sd.ids + eoff + x * est);
                   if (lv && has_m) ok = __ldg(sd.mask + eoff + x * est);
                   const int f = (unsigned)id < (unsigned)sc.R ? 4 + id : 0;
-                  t[x] = ok != 0 ? fmaf(__uint_as_float(v[x]), scale2, rec[f * 64 + x]) : rec[64 + x];
+                  t[x] = ok != 0 ? fmaf(__uint_as_float(v[x]), scale2, rec[f * RSF + x]) : rec[RSF + x];
                 }
               } else {
-                const float* c0 = rec + (5 + 2 * sc.D) * 64;
+                const float* c0 = rec + (5 + 2 * sc.D) * RSF;
                 if (mode == plan::QS) {          // row-side sentence: key j belongs to query (k_sent)
                   const int sp = kc.k_sent - g0;
   #pragma unroll
-                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(sp == x ? 64 : 0) + x]);
+                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(sp == x ? RSF : 0) + x]);
                 } else {                         // KS: column-side sentence: query x's sentence is key j
   #pragma unroll
-                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(cs[x] == j ? 64 : 0) + x]);
+                  for (int x = 0; x < WS; ++x) t[x] = fmaf(__uint_as_float(v[x]), scale2, c0[(cs[x] == j ? RSF : 0) + x]);
                 }
               }
               // 2. masked elements take the per-query constant (field 1)
-              const float* lp = rec + 64;
+              const float* lp = rec + RSF;
               if (mask_pe) {
   #pragma unroll
                 for (int x = 0; x < WS; ++x) t[x] = (ce[x] != kc.k_e) ? lp[x] : t[x];
@@ -1566,7 +1571,8 @@ inline int pad4(int r) { return (r + 3) / 4 * 4; }
 // Workspace of one row set for the tcgen05 backward (rowstat + row records), bytes.
 size_t tc_bwd_rows_ws_bytes(int B, int H, int len, int R) {
   const size_t rows = (size_t)B * H * pad_rows(len);
-  return align256(rows * sizeof(float4)) + align256(rows * (pad4(R > 0 ? R : 0) + 4) * sizeof(float) + 256);
+  // rowstat [rows] float4 + row records [rows / 64][R4 + 4][RSF] floats
+  return align256(rows * sizeof(float4)) + align256(rows / 64 * RSF * (pad4(R > 0 ? R : 0) + 4) * sizeof(float) + 256);
 }
 
 bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d) {
