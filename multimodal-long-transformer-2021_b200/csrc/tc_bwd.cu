@@ -47,11 +47,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TRACE(role, idx) do {} while (0)
 #endif
 constexpr float LOG2E = 1.4426950408889634f;
-// Row records (TcBwdQParams::rec_ws): field stride inside a 64-row block, in floats.  65, not 64: the
+// Row records (TcBwdQParams::rec_ws): field stride inside a 64-row block, in floats.  68, not 64: the
 // key-centric pass reads field (4 + id) of ONE query from 32 lanes with different ids -- with a
 // stride of 64 all of them hit the same shared-memory bank (up to 25-way conflict on every gather of
-// the diagonal groups); 65 spreads consecutive fields over consecutive banks.
-constexpr int RSF = 65;
+// the diagonal groups).  68 spreads eight consecutive fields over eight banks (at most 4-way) and
+// keeps every field row 16-byte aligned, so the warp-uniform reads of the FAST form stay LDS.128
+// (a stride of 65 is conflict-free but turns those into scalar loads: measured slower overall).
+constexpr int RSF = 68;
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(
