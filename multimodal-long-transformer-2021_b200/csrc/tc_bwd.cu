@@ -82,17 +82,20 @@ __device__ __forceinline__ void side_ok_id(const Side& sd, int b, int i, int j, 
 // ============================================================================================
 __global__ void __launch_bounds__(256) tc_bwd_prep_kernel(const T4 out, const T4 d_out, const float* stats,
                                                           float4* rowstat, int B, int H, int len, int lp) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t r = t >> 3;   // row index over (b, i, h): h fastest (matches the tensor layout)
+  // 32-bit index arithmetic (the host guarantees B * len * H * 8 < 2^32): 64-bit divisions made this
+  // kernel issue-bound at half the HBM rate
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t r = t >> 3;   // row index over (b, i, h): h fastest (matches the tensor layout)
   const int sub8 = (int)(t & 7);
-  const int64_t total = (int64_t)B * len * H;
+  const uint32_t total = (uint32_t)B * (uint32_t)len * (uint32_t)H;
   float acc = 0.f;
   int b = 0, i = 0, h = 0;
   const bool ok = r < total;
   if (ok) {
-    h = (int)(r % H);
-    i = (int)((r / H) % len);
-    b = (int)(r / ((int64_t)H * len));
+    const uint32_t bi = r / (uint32_t)H;
+    h = (int)(r - bi * (uint32_t)H);
+    b = (int)(bi / (uint32_t)len);
+    i = (int)(bi - (uint32_t)b * (uint32_t)len);
     const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(d_out, b, i, h)) + sub8);
     const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(row_ptr<__nv_bfloat16>(out, b, i, h)) + sub8);
     const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
@@ -151,6 +154,7 @@ struct Bars {
   uint64_t kv_full[4], kv_empty[4];
   uint64_t sdp_full[2], ds_full[2], dq_full, dar_full;
   uint64_t pl_full[4], pl_empty[4];
+  uint64_t dp_full, rel_done;   // slim: dP of a chunk ready; allrel extracted (its columns become S buffer 1)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -366,6 +370,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dar_full, NALL);
+    mbar_init(&bars->dp_full, 1);
+    mbar_init(&bars->rel_done, 128);
     for (int s = 0; s < NPL; ++s) {
       mbar_init(&bars->pl_full[s], 1);
       mbar_init(&bars->pl_empty[s], 1);
@@ -443,6 +449,35 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                   make_smem_desc_sw128(e_addr + kk * 32, 16, 1024), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
       }
+      // ---- slim: S runs one chunk ahead ------------------------------------------------------
+      // S is double-buffered (buffer 1 = the allrel columns, idle between the table build and the
+      // epilogue), dP is not: S_{c+1} is issued as soon as its K tile is there, so that when the
+      // elementwise warps hand over dS_c they find S_{c+1} waiting and evaluate its probabilities
+      // while dQ_c and dP_{c+1} execute.
+      auto issue_s = [&](int c) {
+        const int st = c % NST;
+        mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
+        TRACE(3, 4 + 4 * c);
+        mbar_wait(&bars->kv_full[st], (c / NST) & 1);
+        TRACE(3, 5 + 4 * c);
+        if (c == 1 && rpad) mbar_wait(&bars->rel_done, 0);   // allrel has been read out of buffer 1
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + ((c & 1) ? T_REL : T_S), make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&bars->sdp_full[c & 1]);
+      };
+      auto issue_dp = [&](int c) {   // kv_full(c) has been waited for by issue_s(c)
+        const uint32_t v_addr = smem_u32(smem + SM_KV + (c % NST) * (2 * TN * 128)) + TN * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + T_DP, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
+                  make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&bars->dp_full);
+        TRACE(3, 6 + 4 * c);
+      };
       auto issue_sdp = [&](int c) {
         const int st = c % NST;
         mbar_wait(&bars->pl_full[c % NPL], (c / NPL) & 1);   // relayed to the elementwise warps by sdp_full
@@ -501,11 +536,18 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       };
       // double-buffered: S/dP of chunk c run ahead of dQ of chunk c-1; single buffer (SLIM): the dQ
       // MMAs that read dS are issued first (MMAs of one thread execute in issue order)
-      for (int c = 0; c <= nchunks; ++c) {
-        if (SLIM) {
-          if (c >= 1) issue_dq(c - 1);
-          if (c < nchunks) issue_sdp(c);
-        } else {
+      if (SLIM) {
+        if (nchunks > 0) {
+          issue_s(0);
+          issue_dp(0);
+        }
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks) issue_s(c + 1);
+          issue_dq(c);                       // waits for dS_c; MMAs execute in issue order
+          if (c + 1 < nchunks) issue_dp(c + 1);
+        }
+      } else {
+        for (int c = 0; c <= nchunks; ++c) {
           if (c < nchunks) issue_sdp(c);
           if (c >= 1) issue_dq(c - 1);
         }
@@ -577,6 +619,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                   if (c0 + x < rw) ws_row[(c0 + x) * RSF] = fmaf(val[x], LOG2E, nm2l);
                               }
                             });
+      if (SLIM) {   // the allrel columns may now be overwritten (S buffer 1)
+        tc_fence_before_sync();
+        mbar_arrive(&bars->rel_done);
+      }
     }
     if (tid == 0) TRACE(1, 3);
     named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
@@ -596,15 +642,25 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (; c < c_end; c += SETS) {
         const plan::ChunkPlan* cp = plans + (c % NPL);
         if (tid == 0) TRACE(1, 8 + 3 * c);
-        // the MMA warp issued S_c / dP_c only after plan c had been published
-        mbar_wait_warp(&bars->sdp_full[BUF(c)], PH(c));
+        // the MMA warp issued S_c / dP_c only after plan c had been published.  Slim: this barrier
+        // covers S_c alone (buffer c & 1); dP_c follows behind dp_full (wait_dp below).
+        if (SLIM) mbar_wait_warp(&bars->sdp_full[c & 1], (c >> 1) & 1);
+        else mbar_wait_warp(&bars->sdp_full[BUF(c)], PH(c));
         if (tid == 0) TRACE(1, 9 + 3 * c);
         tc_fence_after_sync();
+        bool dp_ready = !SLIM;
+        auto wait_dp = [&]() {   // before the first access (read or write) to the chunk's dP columns
+          if (!dp_ready) {
+            mbar_wait_warp(&bars->dp_full, c & 1);
+            tc_fence_after_sync();
+            dp_ready = true;
+          }
+        };
 #pragma unroll 1
         for (int pg = 0; pg < NG; ++pg) {
         const int part = NG > 1 ? pg : part0;
         const int g0 = kb + (c - c_begin) * TN + part * W;
-        const uint32_t t_s = tmem + T_S + BUF(c) * 64 + lane_sel + part * W;
+        const uint32_t t_s = tmem + (SLIM ? ((c & 1) ? T_REL : T_S) : T_S + BUF(c) * 64) + lane_sel + part * W;
         const uint32_t t_dp = tmem + T_DP + BUF(c) * 64 + lane_sel + part * W;
         const uint32_t w0 = cp->q[quad][part];
         const int ce0 = (int)cp->q[quad][2 + part];
@@ -623,15 +679,22 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         } else if (mode == plan::FAST) {
           uint32_t v[W], w[W];
           tmem_ld32(t_s, v);
-          tmem_ld32(t_dp, w);
+          if (!SLIM) tmem_ld32(t_dp, w);
           tmem_wait_ld();
           const float gmul = masked ? 0.f : scale2;
           const float gsub = masked ? lpm : fmaf(relc, LOG2E, nm2l);
           float t0 = 0.f, t1 = 0.f;
+          if (SLIM) {   // probabilities first: dP of the chunk may still be executing
+#pragma unroll
+            for (int x = 0; x < W; ++x) v[x] = __float_as_uint(ex2(fmaf(__uint_as_float(v[x]), gmul, gsub)));
+            wait_dp();
+            tmem_ld32(t_dp, w);
+            tmem_wait_ld();
+          }
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
-            const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
+            const float p0 = SLIM ? __uint_as_float(v[2 * x]) : ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
+            const float p1 = SLIM ? __uint_as_float(v[2 * x + 1]) : ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
             const float d0 = p0 * (__uint_as_float(w[2 * x]) - delta);
             const float d1 = p1 * (__uint_as_float(w[2 * x + 1]) - delta);
             t0 += d0;
@@ -646,6 +709,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           float ds[W];
           if (mode == plan::GEN) {
             // real loop, TMEM as dynamically indexed scratch: one copy of the generic code
+            wait_dp();
 #pragma unroll 1
             for (int jj = 0; jj < W; ++jj) {
               const uint32_t raw = tmem_ld1(t_s + jj);
@@ -675,7 +739,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             {
               uint32_t v[W];
               tmem_ld32(t_s, v);
-              tmem_ld32(t_dp, w);
+              if (!SLIM) tmem_ld32(t_dp, w);
               tmem_wait_ld();
 #pragma unroll
               for (int x = 0; x < W; ++x) e[x] = __uint_as_float(v[x]);
@@ -768,10 +832,17 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int jj = 0; jj < W; ++jj) e[jj] = (masked && e[jj] != -INFINITY) ? lpm : e[jj];
             }
             float t0 = 0.f, t1 = 0.f;
+            if (SLIM) {   // probabilities first: dP of the chunk may still be executing
+#pragma unroll
+              for (int x = 0; x < W; ++x) e[x] = ex2(e[x]);
+              wait_dp();
+              tmem_ld32(t_dp, w);
+              tmem_wait_ld();
+            }
 #pragma unroll
             for (int x = 0; x < W; x += 2) {
-              const float p0 = ex2(e[x]);
-              const float p1 = ex2(e[x + 1]);
+              const float p0 = SLIM ? e[x] : ex2(e[x]);
+              const float p1 = SLIM ? e[x + 1] : ex2(e[x + 1]);
               ds[x] = p0 * (__uint_as_float(w[x]) - delta);
               ds[x + 1] = p1 * (__uint_as_float(w[x + 1]) - delta);
               t0 += ds[x];
@@ -843,6 +914,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = pack_bf16x2(ds[2 * x], ds[2 * x + 1]);
         }
         // each group packs into its OWN column range (the other group's inputs are still unread)
+        wait_dp();   // (dead groups reach this point without having touched dP)
         tmem_st16(t_dp, ds_pk);
         }
         tmem_wait_st();
@@ -851,6 +923,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (tid == 0) TRACE(1, 10 + 3 * c);
       }
     };
+    // (one inlined copy per segment measured faster than a single copy behind a segment loop here:
+    // 0.227 vs 0.240 ms on the global rows, no difference on the long rows)
     run_chunks(sc0, rc0, 0, r0.n, r0.kb);
     if (a.nseg > 1) run_chunks(sc1, rc1, r0.n, nchunks, r1.kb);
     // flush the constant-class accumulators into this part's bins
@@ -1520,7 +1594,18 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         if (tid == 0) TRACE(0, 4 * c + 3);
       }
     };
-    {
+    if constexpr (SLIM) {
+      // ONE copy of the chunk loop, source context built once per source outside it: the smaller code
+      // wins on the few-chunk tiles (long keys 0.522 -> 0.498 ms) ...
+#pragma unroll 1
+      for (int si = 0; si < p.nsrc; ++si) {
+        KeyC kc;
+        const SrcC sc = make_srcc(p.src[si], si ? r1 : r0);
+        key_loads(kc, sc, b, j, key_ok);
+        run_chunks(sc, kc, si ? r0.n : 0, si ? nchunks : r0.n, si ? r1.ib : r0.ib);
+      }
+    } else {
+      // ... and loses on the 68-chunk tiles of the global keys (0.232 -> 0.255 ms): one inlined copy per source
       KeyC kc;
       const SrcC sc0 = make_srcc(p.src[0], r0);
       key_loads(kc, sc0, b, j, key_ok);
@@ -1641,6 +1726,7 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   if (e) return MLT_ERR_UNSUPPORTED;
   {
     const int64_t threads = (int64_t)a.B * a.rows.len * a.H * 8;
+    if (threads >= (int64_t)1 << 32) return MLT_ERR_UNSUPPORTED;   // 32-bit row index in the kernel
     tc_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.out, a.d_out, a.stats, p.rowstat, a.B, a.H,
                                                                        a.rows.len, p.lp);
     cudaError_t pe = cudaGetLastError();
@@ -1677,7 +1763,8 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   // (4 measured slower than 3 on the c3_4096 long rows, 0.75 vs 0.66 ms: the tile is bound by the
   // MMA <-> elementwise round trip of the single S / dP buffer and by the quadrant imbalance of the
   // band chunks, not by the elementwise warps' issue rate.  It stays selectable for experiments.)
-  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
+  static const bool prefer_slim2 = getenv("MLT_BWD_Q_SLIM2") != nullptr;   // experiment knob: 4 wherever 3 would run
+  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : (prefer_slim2 ? 4 : 3));
   if (cfg == 4 && !slim2_ok) cfg = 3;
   if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
   // explicit int32 side inputs: the instantiations that carry the EXPL form (never configuration 4)
