@@ -418,7 +418,11 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--workload', default='c3_4096', choices=['c3_2048', 'c3_4096', 'c3_8192'],
+                  help='long-input sweep point (BASELINE.json configs[2]); the default is the one the '
+                       'metric is quoted on, the others hold B*L = 65 536 tokens per GPU as well')
   args = ap.parse_args()
+  globals()['WORKLOAD'] = args.workload
   if args.impl == 'reference':
     run_reference(args)
   else:

@@ -303,14 +303,13 @@ __device__ __forceinline__ void eval_generic_q(const SegC& sc, const RowC& rc, i
 // double-buffered by chunk parity, so set s owns buffer s).  The evaluation form of every
 // (quadrant, group) pair comes from the planner warp (tc_plan.cuh).
 constexpr int NPL = 4;   // plan ring slots
-// NPS = elementwise threads per row of the SLIM configuration (the others always use two).
-template <int SETS, bool SLIM, int NPS = 1>
-constexpr int bq_threads() { return (4 * (SLIM ? NPS : 2) * SETS + (SLIM && NPS > 1 ? 2 : 3)) * 32; }
+template <int SETS, bool SLIM>
+constexpr int bq_threads() { return (4 * (SLIM ? 1 : 2) * SETS + 3) * 32; }
 
 // EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
 // instantiations stay free of its code and register pressure.
-template <int SETS, bool SLIM, int NPS = 1, bool EX = false>
-__global__ void __launch_bounds__(bq_threads<SETS, SLIM, NPS>(), SLIM ? 2 : 1)
+template <int SETS, bool SLIM, bool EX = false>
+__global__ void __launch_bounds__(bq_threads<SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
                 const __grid_constant__ CUtensorMap map_k1, const __grid_constant__ CUtensorMap map_v1,
@@ -321,22 +320,13 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 SM_BIN = C::SM_BIN, SM_A = C::SM_A, SM_BS = C::SM_BS, SM_PLAN = C::SM_PLAN, SM_META = C::SM_META,
                 SM_BAR = C::SM_BAR;
   constexpr uint32_t T_S = C::T_S, T_DP = C::T_DP, T_DQ = C::T_DQ, T_REL = C::T_REL, T_DE = C::T_DE;
-  constexpr int NP = SLIM ? NPS : 2;  // elementwise threads per row
+  constexpr int NP = SLIM ? 1 : 2;    // elementwise threads per row
   constexpr int W = 32;               // columns per group
   constexpr int NG = 2 / NP;          // groups of a chunk a thread walks through (slim: both)
   constexpr int NEW = 128 * NP;       // elementwise threads per set
   constexpr int NALL = NEW * SETS;    // all elementwise threads
   constexpr int NB = NP * SETS;       // elementwise threads per row over all sets (output / id slices)
-  // private bin arrays per row.  SLIM has room for one: with two threads per row they share it --
-  // interior diagonal slots have a single writer by construction, the constant classes are flushed
-  // one thread after the other, and the host never picks this configuration when the generic
-  // (read-modify-write) form can occur.
-  constexpr int NBA = SLIM ? 1 : NB;
-  constexpr bool SHARED_BIN = SLIM && NP > 1;
-  // producer / MMA / planner warp; with two threads per row the slim configuration has no spare
-  // warp (register file: 2 x 320 threads x 96), so its producer doubles as the planner
-  constexpr bool MERGED = SLIM && NP > 1;
-  constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = MERGED ? -1 : 4 * NB + 2;
+  constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = 4 * NB + 2;   // producer / MMA / planner warp
   constexpr int RB = SLIM ? 32 : 128 / NB;   // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
   static_assert(!SLIM || SETS == 1, "the slim configuration has a single S / dP buffer");
@@ -420,14 +410,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                 pre);
   };
   if (warp == WP) {
-    if (MERGED) {
-      // producer and planner in one warp: the chunk's loads go out, then the chunk is classified
-      if (lane == 0) load_tile();
-      run_planner([&](int c) {
-        if (lane == 0) load_chunk(c);
-        __syncwarp();
-      });
-    } else if (elect_one()) {
+    if (elect_one()) {
       load_tile();
       for (int c = 0; c < nchunks; ++c) load_chunk(c);
     }
@@ -553,7 +536,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-  } else if (!MERGED && warp == WPL) {
+  } else if (warp == WPL) {
     // ===================== planner =====================
     run_planner(plan::NoPre());
   } else {
@@ -567,8 +550,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int i = i0 + row;
     const bool row_ok = i < a.rows.len;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-    float* bin = bins + (SLIM ? 0 : bidx) * RB * TM;   // slot-ordered, private to (set, part, row) unless SHARED_BIN
-    for (int x = lane + 32 * quad + (SHARED_BIN ? 128 * part0 : 0); x < RB * TM; x += (SHARED_BIN ? 128 * NP : 128)) bin[x] = 0.f;
+    float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
+    for (int x = lane + 32 * quad; x < RB * TM; x += 128) bin[x] = 0.f;
     if (!SLIM)   // slim: the tile lives in a K/V stage and is written in full by the epilogue
       for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
     const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
@@ -933,16 +916,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (id >= 0 && id < R) bin[plan::slot_of_id(id, pd, perm) * TM + row] += v;
       };
       const int dd = sc0.D;   // both segments of a row set share max_distance
-#pragma unroll 1
-      for (int turn = 0; turn < (SHARED_BIN ? NP : 1); ++turn) {
-        if (!SHARED_BIN || turn == part0) {
-          flush(dd, accP);
-          flush(2 * dd, accN);
-          flush(2 * dd + 1, accX);
-          flush(2 * dd + 2, accX1);
-        }
-        if (SHARED_BIN && turn + 1 < NP) named_bar_sync(1, NALL);   // the row's other thread adds next
-      }
+      flush(dd, accP);
+      flush(2 * dd, accN);
+      flush(2 * dd + 1, accX);
+      flush(2 * dd + 2, accX1);
     }
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
     if (tid == 0) TRACE(1, 5);
@@ -968,7 +945,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (pid < R) {
             const int sl = plan::slot_of_id(pid, pd, perm);
 #pragma unroll
-            for (int pp = 0; pp < NBA; ++pp) w += bins[(pp * RB + sl) * TM + row];
+            for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
           }
           w8[x] = w;
         }
@@ -1692,10 +1669,9 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
     set(tc_bwd_q_kernel<2, false>, bq::Cfg<false>::SM_ALLOC);
     set(tc_bwd_q_kernel<1, false>, bq::Cfg<false>::SM_ALLOC);
     set(tc_bwd_q_kernel<1, true>, bq::Cfg<true>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, true, 2>, bq::Cfg<true>::SM_ALLOC);
-    set(tc_bwd_q_kernel<2, false, 1, true>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, false, 1, true>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, true, 1, true>, bq::Cfg<true>::SM_ALLOC);
+    set(tc_bwd_q_kernel<2, false, true>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, false, true>, bq::Cfg<false>::SM_ALLOC);
+    set(tc_bwd_q_kernel<1, true, true>, bq::Cfg<true>::SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     g_attr_q = true;
   }
@@ -1738,49 +1714,25 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   auto seg_chunks = [](const KeySeg& sg) { return sg.band ? (TM + 2 * sg.radius + TN - 1) / TN : (sg.len + TN - 1) / TN; };
   const int est_chunks = seg_chunks(a.seg[0]) + (a.nseg > 1 ? seg_chunks(a.seg[1]) : 0);
   // 1: one warp set, 2: two warp sets on alternate chunks (many chunks: dense global rows),
-  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64), one elementwise thread per row,
-  // 4: slim with two elementwise threads per row sharing the row's bin array
+  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64).  (A slim variant with two
+  // elementwise threads per row was measured slower, 0.75 vs 0.66 ms on the c3_4096 long rows, and
+  // removed: the tile is bound by the quadrant imbalance of the band chunks and by the per-warp
+  // latency chains, not by the number of elementwise warps.)
   static const int force_cfg = getenv("MLT_BWD_Q_CFG") ? atoi(getenv("MLT_BWD_Q_CFG")) : 0;
-  // Configuration 4 must never meet the generic evaluation form (its bins are read-modify-write):
-  // that form is chosen for explicit side inputs, 2-D ids, a relative table that does not match the
-  // slot order, and for diagonal / sentence groups cut by the sequence end or the band edge.
-  const int pd = a.seg[0].side.max_distance;
-  auto seg_never_generic = [&](const KeySeg& sg) {
-    const Side& sd = sg.side;
-    if (sd.mask_rule == MR_EXPLICIT || sg.len % 32 != 0) return false;
-    if (sg.band && (sg.radius < 64 || sg.radius % 32 != 0)) return false;
-    if (R == 0) return true;
-    const int D = sd.max_distance;
-    switch (sd.id_rule) {
-      case IDR_NONE: return true;
-      case IDR_1D: return 2 * pd + 1 <= R && pd == D;
-      case IDR_CROSS_QSENT:
-      case IDR_CROSS_KSENT: return 2 * D + 2 < R;
-      default: return false;
-    }
-  };
-  const bool slim2_ok = seg_never_generic(a.seg[0]) && (a.nseg < 2 || seg_never_generic(a.seg[1]));
-  // (4 measured slower than 3 on the c3_4096 long rows, 0.75 vs 0.66 ms: the tile is bound by the
-  // MMA <-> elementwise round trip of the single S / dP buffer and by the quadrant imbalance of the
-  // band chunks, not by the elementwise warps' issue rate.  It stays selectable for experiments.)
-  static const bool prefer_slim2 = getenv("MLT_BWD_Q_SLIM2") != nullptr;   // experiment knob: 4 wherever 3 would run
-  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : (prefer_slim2 ? 4 : 3));
-  if (cfg == 4 && !slim2_ok) cfg = 3;
+  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
   if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
-  // explicit int32 side inputs: the instantiations that carry the EXPL form (never configuration 4)
+  // explicit int32 side inputs: the instantiations that carry the EXPL form
   const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
-  if (cfg == 4)
-    tc_bwd_q_kernel<1, true, 2><<<grid, bq_threads<1, true, 2>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else if (cfg == 3 && ex)
-    tc_bwd_q_kernel<1, true, 1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  if (cfg == 3 && ex)
+    tc_bwd_q_kernel<1, true, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 3)
     tc_bwd_q_kernel<1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2 && ex)
-    tc_bwd_q_kernel<2, false, 1, true><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<2, false, true><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2)
     tc_bwd_q_kernel<2, false><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (ex)
-    tc_bwd_q_kernel<1, false, 1, true><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    tc_bwd_q_kernel<1, false, true><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else
     tc_bwd_q_kernel<1, false><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();

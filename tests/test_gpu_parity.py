@@ -395,3 +395,43 @@ def test_tc_dense_backward_matches_oracle():
     for name, got, want in zip('q k v emb bias'.split(), dev, ref):
       scale = max(1.0, want.grad.abs().max().item())
       assert abs_err(got.grad, want.grad) < BF16_ABS * scale, name
+
+
+# ------------------------------------------------------------------------------------------
+# Full sweep lengths (BASELINE.json configs[2]): the fp64 oracle is too slow there, so the checks
+# are properties that hold at any size, plus the two independent CUDA formulations against each other.
+
+@pytest.mark.parametrize('name', ['c3_2048', 'c3_4096', 'c3_8192'])
+def test_full_length_properties(name):
+  """At L = 2048 / 4096 / 8192 (G = L / 16, r = 64, 12 heads; batch cut to 1 -- units are independent):
+    * rows of the joint softmax sum to one: with V = 1 every output element is 1;
+    * gradient mass is conserved: sum_j dV_j (long + global keys) = sum_i dO_i (long + global rows), per
+      head and channel, because every softmax row sums to one;
+    * the tcgen05 kernels agree with the SIMT kernels (different tiling, different arithmetic order)
+      on the outputs and on every gradient."""
+  import dataclasses
+  seed_off, shape = synthetic.CONFIGS[name]
+  shape = dataclasses.replace(shape, batch=1)
+  x = synthetic.make_inputs(shape, seed=1234 + seed_off, dtype=torch.bfloat16)
+  side = compact_of(x, shape)
+
+  lo, go, grads = run_cuda_gl(x, shape, side, impl='tc')
+  ls, gs, sgrads = run_cuda_gl(x, shape, side, impl='simt')
+  assert abs_err(lo, ls.double().cpu()) < BF16_ABS and abs_err(go, gs.double().cpu()) < BF16_ABS
+  for n, got, want in zip(NAMES, grads, sgrads):
+    want = want.double().cpu()
+    scale = max(1.0, want.abs().max().item())
+    assert abs_err(got, want) < 2 * BF16_ABS * scale, n
+
+  # gradient mass: sum over keys of dV == sum over rows of dO  (fp32 sums of bf16 tensors)
+  d_v = grads[2].float().sum(1) + grads[5].float().sum(1)                       # [B, H, d]
+  d_o = x['d_long_out'].float().sum(1) + x['d_global_out'].float().sum(1)
+  tol = 2e-2 * d_o.abs().max().item() + 0.5     # bf16 rounding of ~L summands per element
+  assert (d_v.cpu() - d_o).abs().max().item() < tol
+
+  # V = 1  ->  out = 1
+  ones = dict(x)
+  ones['long_v'] = torch.ones_like(x['long_v'])
+  ones['global_v'] = torch.ones_like(x['global_v'])
+  lo1, go1, _ = run_cuda_gl(ones, shape, side, impl='tc')
+  assert (lo1.float() - 1).abs().max().item() < 1e-2 and (go1.float() - 1).abs().max().item() < 1e-2
