@@ -538,7 +538,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else if (warp == WPL) {
     // ===================== planner =====================
+#ifdef MLT_TC_TRACE
+    if (lane == 0) TRACE(4, 30);
+    run_planner([&](int c) { if (lane == 0) TRACE(4, 32 + c); });
+#else
     run_planner(plan::NoPre());
+#endif
   } else {
     // ===================== elementwise warps (NP threads per row) =====================
     if (tid == 0) TRACE(1, 0);
