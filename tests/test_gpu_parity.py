@@ -435,3 +435,26 @@ def test_full_length_properties(name):
   ones['global_v'] = torch.ones_like(x['global_v'])
   lo1, go1, _ = run_cuda_gl(ones, shape, side, impl='tc')
   assert (lo1.float() - 1).abs().max().item() < 1e-2 and (go1.float() - 1).abs().max().item() < 1e-2
+
+
+def test_tc_partial_explicit_side_inputs():
+  """tcgen05 EXPL form with some of the eight explicit tensors missing: a missing mask is all ones, missing
+  ids contribute no relative term (per block, as in the reference's optional arguments); fwd + bwd vs the
+  SIMT kernels on identical bf16 inputs, for an aligned shape (128-bit loads) and a ragged one."""
+  for dims in ((2, 256, 32, 2, 64, 32, 12), (1, 210, 9, 2, 64, 32, 12)):
+    b, l, g, h, r, rv, dist = dims
+    shape = synthetic.GlobalLocalShape(b, l, g, h, 64, r, rv, dist)
+    x = synthetic.make_inputs(shape, seed=l, dtype=torch.bfloat16)
+    for n in ('long_emb', 'long_bias', 'global_emb', 'global_bias'):
+      x[n] = (x[n].float() * 10).bfloat16()
+    full = {k: v.cuda() for k, v in oracle_side(x, shape).items()}
+    for drop in (('l2g_att_mask', 'g2g_relative_att_ids'), ('l2l_relative_att_ids', 'g2l_att_mask'),
+                 ('l2l_att_mask', 'l2g_relative_att_ids', 'g2g_att_mask', 'g2l_relative_att_ids')):
+      side = {k: v for k, v in full.items() if k not in drop}
+      lo, go, grads = run_cuda_gl(x, shape, side, impl='tc')
+      ls, gs, sgrads = run_cuda_gl(x, shape, side, impl='simt')
+      assert abs_err(lo, ls.double().cpu()) < BF16_ABS and abs_err(go, gs.double().cpu()) < BF16_ABS, drop
+      for name, got, want in zip(NAMES, grads, sgrads):
+        want = want.double().cpu()
+        scale = max(1.0, want.abs().max().item())
+        assert abs_err(got, want) < 2 * BF16_ABS * scale, (name, drop)
