@@ -286,10 +286,38 @@ class ForkScope {
   bool joined_ = false;
 };
 
-FwdArgs dense_fwd_args(const mlt_dense_params* p) {
+// Compact 2-D descriptors on the tcgen05 path: the ids depend on the two positions only, not on the
+// batch element, so the library materialises ONE [Lq, Lk] int32 plane in the caller's workspace
+// (side-input constructor kernel, ~1 MB at S = 512) and the kernels read it through the EXPL form
+// with batch stride 0; the mask stays the example-id rule.  (The closed 2-D rule needs two integer
+// divisions per element and otherwise runs through the generic per-element loop: 12x slower.)
+size_t dense_ids_plane_bytes(const mlt_dense_params* p) {
+  const bool plane = p->side_mode == MLT_SIDE_COMPACT && p->id_layout.num_patch_per_row > 0 && p->R > 0 &&
+                     p->Lq == p->Lk;
+  return plane ? align_up(sizeof(int32_t) * (size_t)p->Lq * p->Lk) : 0;
+}
+// The plane sits at the end of the workspace (mlt_dense_workspace_bytes); null when not applicable.
+int32_t* dense_ids_plane(const mlt_dense_params* p, int bwd) {
+  const size_t n = dense_ids_plane_bytes(p);
+  const size_t total = mlt_dense_workspace_bytes(p, bwd);
+  if (n == 0 || !p->workspace || p->workspace_bytes < total) return nullptr;
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
+  return reinterpret_cast<int32_t*>(base + (total - kAlign - n));
+}
+Side with_ids_plane(Side s, const int32_t* plane, int lk) {
+  if (plane) {
+    s.id_rule = IDR_EXPLICIT;
+    s.ids = plane;
+    s.sb = 0;      // every batch element reads the same plane
+    s.sq = lk;
+  }
+  return s;
+}
+
+FwdArgs dense_fwd_args(const mlt_dense_params* p, const int32_t* ids_plane = nullptr) {
   FwdArgs a{};
   a.rows = dense_rows(p);
-  a.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, dense_side(p));
+  a.seg[0] = make_seg(p->k, p->v, p->Lk, 0, 0, with_ids_plane(dense_side(p), ids_plane, p->Lk));
   a.nseg = 1;
   a.out = to_t4(p->out);
   a.stats = p->stats;
@@ -411,6 +439,7 @@ size_t mlt_dense_workspace_bytes(const mlt_dense_params* p, int bwd) {
   if (!p) return 0;
   size_t n = kAlign;
   if (bwd) n += row_ws_bytes(p->B, p->H, p->Lq, p->R, p->d) + tc_bwd_rows_ws_bytes(p->B, p->H, p->Lq, p->R);
+  n += dense_ids_plane_bytes(p);
   return n;
 }
 
@@ -429,7 +458,14 @@ int mlt_dense_rel_attn_fwd(const mlt_dense_params* p, void* cuda_stream) {
   const bool tc = dense_fwd_on_tc(p);
   if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
-  return launch_fwd(dense_fwd_args(p), tc, p->dtype, p->d, "fwd_dense",
+  const int32_t* plane = nullptr;
+  if (tc && dense_ids_plane_bytes(p)) {
+    int32_t* w = dense_ids_plane(p, 0);
+    if (!w) return MLT_ERR_WORKSPACE;
+    MLT_TRY(mlt_build_dense_side_inputs(nullptr, 1, p->Lq, p->id_layout, nullptr, w, cuda_stream));
+    plane = w;
+  }
+  return launch_fwd(dense_fwd_args(p, plane), tc, p->dtype, p->d, "fwd_dense",
                     fwd_flops(bh, pairs, p->d, p->R, p->Lq),
                     qkv_bytes(bh, 2.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st);
 }
@@ -447,7 +483,7 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p->workspace)));
   RowWs ws = carve_row_ws(wp, p->B, p->H, p->Lq, p->R, p->d);
   void* tcw[2] = {wp, wp};
-  const Side side = dense_side(p);
+  Side side = dense_side(p);
 
   BwdQArgs q{};
   q.rows = dense_rows(p);
@@ -471,6 +507,14 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(q, p->dtype, p->d) && bwd_kv_on_tc(kv);
   if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
+  if (tc && dense_ids_plane_bytes(p)) {   // compact 2-D ids: one [Lq, Lk] plane, read through the EXPL form
+    int32_t* w = dense_ids_plane(p, 1);
+    if (!w) return MLT_ERR_WORKSPACE;
+    MLT_TRY(mlt_build_dense_side_inputs(nullptr, 1, p->Lq, p->id_layout, nullptr, w, cuda_stream));
+    side = with_ids_plane(side, w, p->Lk);
+    q.seg[0].side = side;
+    kv.src[0].side = side;
+  }
   MLT_TRY(launch_bwd_q(q, tc, tcw[0], p->dtype, p->d, "bwd_q_dense",
                        bh * (4.0 * p->d * pairs + 2.0 * p->d * p->R * p->Lq),
                        qkv_bytes(bh, 4.0 * p->Lq + 2.0 * p->Lk, p->d, p->dtype, 1), st));

@@ -575,11 +575,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                   for (int jj = 0; jj < 32; ++jj) {
                     float rel = 0.f;
                     if ((unsigned)id[jj] < (unsigned)sc.R) rel = rel_s[relmeta[id[jj]].slot_off + row];
-                    t[jj] = fmaf(t[jj], a.scale, rel);
+                    t[jj] = fmaf(t[jj], a.scale, rel + mterm);   // mterm: example-id mask uniform over the group
                   }
                 } else {
 #pragma unroll
-                  for (int jj = 0; jj < 32; ++jj) t[jj] *= a.scale;
+                  for (int jj = 0; jj < 32; ++jj) t[jj] = fmaf(t[jj], a.scale, mterm);
                 }
                 if (sc.mask_rule == MR_EXPLICIT) {
                   int ok[32];

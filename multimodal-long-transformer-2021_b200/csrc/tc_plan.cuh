@@ -126,14 +126,15 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
     }
     uint32_t mode, ccls = C_NONE, flags = 0;
     const bool dead = g0 >= s.c_end || (s.band && (o_min > s.radius || o_max < -s.radius));
-    // explicit tensors only (each of mask / ids either explicit or absent)
+    // explicit tensors (ids explicit or absent; the mask explicit, absent, or the example-id rule --
+    // the latter with an explicit id plane is how compact 2-D ids are served)
     const bool expl = s.expl_ok && (s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT) &&
-                      (s.mask_rule == MR_EXPLICIT || s.mask_rule == MR_NONE) &&
                       (s.id_rule == IDR_EXPLICIT || s.id_rule == IDR_NONE);
     if (dead) {
       mode = DEAD;
     } else if (expl) {
       mode = EXPL;
+      if (s.mask_rule == MR_EXAMPLE_ID && !(g ? uni1 : uni0)) flags |= F_MASK_PE;
     } else {
       const bool all_live = (g0 + 31 < s.c_end) && (!s.band || (o_min >= -s.radius && o_max <= s.radius));
       bool gen = false;

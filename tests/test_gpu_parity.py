@@ -458,3 +458,29 @@ def test_tc_partial_explicit_side_inputs():
         want = want.double().cpu()
         scale = max(1.0, want.abs().max().item())
         assert abs_err(got, want) < 2 * BF16_ABS * scale, (name, drop)
+
+
+def test_tc_dense_2d_compact_backward_matches_simt_and_explicit():
+  """Compact 2-D descriptors on the tcgen05 path (id plane materialised in the workspace, read through the
+  EXPL form with the example-id mask) against the SIMT kernels (closed 2-D rule) and against the same ids
+  fed explicitly; fwd + bwd, ragged example lengths so that the mask changes inside 32-column groups."""
+  b, s, h, d, rv = 2, 300, 2, 64, 49
+  gen = torch.Generator().manual_seed(11)
+  q, k, v, do = (torch.randn(b, s, h, d, generator=gen).bfloat16() for _ in range(4))
+  emb = (torch.randn(rv, h, d, generator=gen) * 0.2).bfloat16()
+  bias = (torch.randn(rv, h, generator=gen) * 0.2).bfloat16()
+  e = (torch.arange(s)[None] < torch.tensor([[300], [217]])).int().cuda()
+  compact = ops.DenseCompactSideInputs(e, max_distance=12, num_patch_per_row=14, num_core_layers=2)
+  mask, ids = ops.build_dense_side_inputs(e, 12, num_patch_per_row=14, num_core_layers=2)
+  results = []
+  for impl, kwargs in (('tc', dict(compact=compact)), ('simt', dict(compact=compact)),
+                       ('tc', dict(att_mask=mask, relative_att_ids=ids))):
+    dev = [t.cuda().requires_grad_() for t in (q, k, v, emb, bias)]
+    out = ops.dense_relative_attention(*dev, impl=impl, **kwargs)
+    (out.float() * do.cuda().float()).sum().backward()
+    results.append([out.detach()] + [t.grad for t in dev])
+  for other in results[1:]:
+    for name, got, want in zip('out q k v emb bias'.split(), results[0], other):
+      want = want.double().cpu()
+      scale = max(1.0, want.abs().max().item())
+      assert abs_err(got, want) < 2 * BF16_ABS * scale, name
