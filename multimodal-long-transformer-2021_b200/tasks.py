@@ -141,17 +141,34 @@ def pretraining_losses(labels: Dict[str, torch.Tensor], model_outputs: Dict[str,
 
 
 class PretrainingStep:
-  """One optimizer step: micro-batch accumulation (reference :242-270) then ONE flat gradient
-  all-reduce over NCCL (what `apply_gradients` does implicitly under the TF strategy, :273)."""
+  """One optimizer step: micro-batch accumulation (reference :242-270) then ONE gradient all-reduce
+  over NCCL (what `apply_gradients` does implicitly under the TF strategy, :273).
+
+  The gradients of all parameters live in one flat buffer per dtype (every `p.grad` is a view into
+  it, as in DDP's bucket views), so the accumulation of the micro-batches writes straight into the
+  buffer the collective runs on: no concatenation, no copy back, the all-reduce moves the gradients
+  in their own dtype."""
 
   def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, micro_batch_size: int):
     self.model, self.optimizer, self.micro = model, optimizer, micro_batch_size
     self.params = [p for p in model.parameters() if p.requires_grad]
+    self.flat = {}
+    by_dtype = {}
+    for p in self.params:
+      by_dtype.setdefault((p.dtype, p.device), []).append(p)
+    for key, ps in by_dtype.items():
+      flat = torch.zeros(sum(p.numel() for p in ps), dtype=key[0], device=key[1])
+      off = 0
+      for p in ps:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+      self.flat[key] = flat
 
   def __call__(self, inputs: Dict[str, torch.Tensor], labels: Dict[str, torch.Tensor], **model_kwargs):
     n = inputs['word_ids'].shape[0]
     steps = max(1, n // self.micro)
-    self.optimizer.zero_grad(set_to_none=True)
+    for flat in self.flat.values():     # zero in place: the parameters keep their views
+      flat.zero_()
     total = torch.zeros((), device=inputs['word_ids'].device)
     for s in range(steps):
       sl = slice(s * self.micro, (s + 1) * self.micro)
@@ -161,14 +178,13 @@ class PretrainingStep:
       loss.backward()
       total = total + loss.detach()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-      grads = [p.grad for p in self.params if p.grad is not None]
-      flat = torch.cat([g.reshape(-1).float() for g in grads])
-      dist.all_reduce(flat, op=dist.ReduceOp.SUM)   # NCCL (NVLS on NVSwitch) in production, gloo in tests
-      flat /= dist.get_world_size()
-      off = 0
-      for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+      world = dist.get_world_size()
+      works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)   # NCCL (NVLS on NVSwitch) in
+               for flat in self.flat.values()]                              # production, gloo in tests
+      for w in works:
+        w.wait()
+      for flat in self.flat.values():
+        flat /= world
     self.optimizer.step()
     return total
 

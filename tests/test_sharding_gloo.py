@@ -30,14 +30,17 @@ dist.destroy_process_group()
 def test_two_rank_partition_and_timing_reduction(tmp_path):
   script = tmp_path / 'worker.py'
   script.write_text(WORKER)
-  with socket.socket() as s:
-    s.bind(('127.0.0.1', 0))
-    port = s.getsockname()[1]
   env = dict(os.environ, MLT_ROOT=ROOT)
-  out = subprocess.run(
-      [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
-       '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
-      capture_output=True, text=True, env=env, timeout=240)
+  for attempt in range(2):      # the probed port can be taken between the probe and the rendezvous: one retry
+    with socket.socket() as s:
+      s.bind(('127.0.0.1', 0))
+      port = s.getsockname()[1]
+    out = subprocess.run(
+        [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+         '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
+        capture_output=True, text=True, env=env, timeout=240)
+    if out.returncode == 0:
+      break
   assert out.returncode == 0, out.stderr[-2000:]
   import json
   import re
