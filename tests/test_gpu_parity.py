@@ -484,3 +484,32 @@ def test_tc_dense_2d_compact_backward_matches_simt_and_explicit():
       want = want.double().cpu()
       scale = max(1.0, want.abs().max().item())
       assert abs_err(got, want) < 2 * BF16_ABS * scale, name
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_tc_random_shapes_explicit_match_simt(seed):
+  """Property test of the EXPL form over (B, L, G, H, radius, R, D): explicit int32 side inputs built by the
+  device-side constructor, with random out-of-vocabulary ids and random extra masking sprinkled in, tcgen05
+  against SIMT on identical bf16 inputs (fwd + bwd)."""
+  b, l, g, h, r, rv, dist = _random_tc_case(2000 + seed)
+  shape = synthetic.GlobalLocalShape(b, l, g, h, 64, r, rv, dist)
+  x = synthetic.make_inputs(shape, seed=50 + seed, dtype=torch.bfloat16)
+  for n in ('long_emb', 'long_bias', 'global_emb', 'global_bias'):
+    x[n] = (x[n].float() * 10).bfloat16()
+  side = ops.build_gl_side_inputs(compact_of(x, shape), shape.local_radius)
+  gen = torch.Generator(device='cuda').manual_seed(seed)
+  for k, t in side.items():
+    noise = torch.rand(t.shape, generator=gen, device='cuda')
+    if k.endswith('relative_att_ids'):
+      t[noise < 0.02] = rv + 3            # out-of-vocabulary: contributes 0
+      t[(noise >= 0.02) & (noise < 0.03)] = -2
+    else:
+      t[noise < 0.05] = 0                 # extra masked pairs
+  lo, go, grads = run_cuda_gl(x, shape, side, impl='tc')
+  ls, gs, sgrads = run_cuda_gl(x, shape, side, impl='simt')
+  assert abs_err(lo, ls.double().cpu()) < BF16_ABS, (b, l, g, h, r, rv, dist)
+  assert abs_err(go, gs.double().cpu()) < BF16_ABS, (b, l, g, h, r, rv, dist)
+  for name, got, want in zip(NAMES, grads, sgrads):
+    want = want.double().cpu()
+    scale = max(1.0, want.abs().max().item())
+    assert abs_err(got, want) < 2 * BF16_ABS * scale, (name, b, l, g, h, r, rv, dist)
