@@ -238,7 +238,9 @@ MLT_API int mlt_gl_uses_tensor_cores(const mlt_gl_params* p);
 MLT_API int mlt_dense_uses_tensor_cores(const mlt_dense_params* p);
 
 /* Workspace sizes (bytes) for forward (bwd == 0) or backward (bwd != 0); pointer fields of *p
- * are ignored. */
+ * are ignored.  The forward needs a workspace too: with MLT_SIDE_COMPACT and a 2-D id layout
+ * (num_patch_per_row > 0) the dense entry points materialise one [Lq, Lk] int32 id plane in it
+ * (the ids do not depend on the batch element), which the kernels then read like explicit ids. */
 MLT_API size_t mlt_dense_workspace_bytes(const mlt_dense_params* p, int bwd);
 MLT_API size_t mlt_gl_workspace_bytes(const mlt_gl_params* p, int bwd);
 
