@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(256) tc_bwd_prep_kernel(const T4 out, const T4
 // ============================================================================================
 namespace bq {
 // SLIM: a 256-column / ~105 KB configuration that lets TWO CTAs share an SM (relative vocabulary
-// <= 32, one elementwise thread per row, S / dP single-buffered, two K/V stages, the dallrel^T
-// tile reuses a drained K/V stage).  Used for the long-row tiles, which have few chunks: prologue
+// <= 32, one elementwise thread per row, dP single-buffered, S double-buffered through the allrel
+// columns that are idle during the chunk loop, two K/V stages, the dallrel^T tile reuses a drained
+// K/V stage).  Used for the long-row tiles, which have few chunks: prologue
 // (table build), epilogue (dallrel assembly) and the MMA round trips of one CTA are covered by
 // the other.
 template <bool SLIM>
@@ -329,7 +330,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr int WP = 4 * NB, WM = 4 * NB + 1, WPL = 4 * NB + 2;   // producer / MMA / planner warp
   constexpr int RB = SLIM ? 32 : 128 / NB;   // bin slots per array (host guarantees R <= RB)
   static_assert(SETS == 1 || SETS == 2, "chunk buffers are double-buffered");
-  static_assert(!SLIM || SETS == 1, "the slim configuration has a single S / dP buffer");
+  static_assert(!SLIM || SETS == 1, "the slim configuration has a single dP buffer");
   // chunk c uses buffer BUF(c) in its PH(c)-th use
   auto BUF = [](int c) { return SLIM ? 0 : (c & 1); };
   auto PH = [](int c) { return SLIM ? (c & 1) : ((c >> 1) & 1); };
@@ -517,8 +518,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_commit(&bars->dq_full);
         }
       };
-      // double-buffered: S/dP of chunk c run ahead of dQ of chunk c-1; single buffer (SLIM): the dQ
-      // MMAs that read dS are issued first (MMAs of one thread execute in issue order)
+      // double-buffered: S/dP of chunk c run ahead of dQ of chunk c-1.  SLIM (single dP buffer): S runs
+      // one chunk ahead in its own buffer; the dQ MMAs that read dS are issued before the dP MMAs that
+      // overwrite it (MMAs of one thread execute in issue order)
       if (SLIM) {
         if (nchunks > 0) {
           issue_s(0);
