@@ -249,9 +249,12 @@ __device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i
   if (row_ok && sc.mask_rule == MR_EXAMPLE_ID) rc.q_e = __ldg(sc.sd->q_eid + (int64_t)b * sc.sd->q_len + i);
   if (row_ok && sc.id_rule == IDR_CROSS_QSENT) rc.q_sent = __ldg(sc.sd->sent + (int64_t)b * sc.sd->sent_len + i);
 }
-__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, int row) {
+// `meta` = the id -> slot table of the tile (plan::rel_meta_init): one warp-broadcast LDS instead of the
+// branchy id -> slot rule in this once-per-tile (cold) code
+__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, const plan::RelMeta* meta,
+                                           int row) {
   auto rel_at = [&](int id) -> float {
-    return (id >= 0 && id < sc.R) ? rel_s[plan::slot_of_id(id, sc.pd, sc.perm) * TM + row] : 0.f;
+    return (id >= 0 && id < sc.R) ? rel_s[meta[id].slot_off + row] : 0.f;
   };
   const bool on = sc.id_rule != IDR_NONE;
   rc.relP = on ? rel_at(sc.D) : 0.f;
@@ -617,8 +620,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (tid == 0) TRACE(1, 3);
     named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
     if (tid == 0) TRACE(1, 4);
-    row_consts(rc0, sc0, rel_s, row);
-    row_consts(rc1, sc1, rel_s, row);
+    row_consts(rc0, sc0, rel_s, relmeta, row);
+    row_consts(rc1, sc1, rel_s, relmeta, row);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
     float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
     const float scale2 = a.scale * LOG2E;
@@ -920,7 +923,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // flush the constant-class accumulators into this part's bins
     if (R > 0) {
       auto flush = [&](int id, float v) {
-        if (id >= 0 && id < R) bin[plan::slot_of_id(id, pd, perm) * TM + row] += v;
+        if (id >= 0 && id < R) bin[relmeta[id].slot_off + row] += v;
       };
       const int dd = sc0.D;   // both segments of a row set share max_distance
       flush(dd, accP);
@@ -950,9 +953,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int pid = c0 + x;
           float w = 0.f;
           if (pid < R) {
-            const int sl = plan::slot_of_id(pid, pd, perm);
+            const int so = relmeta[pid].slot_off;   // slot * TM (warp-broadcast LDS instead of the branchy id -> slot rule)
 #pragma unroll
-            for (int pp = 0; pp < NB; ++pp) w += bins[(pp * RB + sl) * TM + row];
+            for (int pp = 0; pp < NB; ++pp) w += bins[pp * RB * TM + so + row];
           }
           w8[x] = w;
         }

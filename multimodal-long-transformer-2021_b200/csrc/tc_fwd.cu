@@ -160,9 +160,12 @@ __device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i
   if (row_ok && sc.mask_rule == MR_EXAMPLE_ID) rc.q_e = __ldg(sc.sd->q_eid + (int64_t)b * sc.sd->q_len + i);
   if (row_ok && sc.id_rule == IDR_CROSS_QSENT) rc.q_sent = __ldg(sc.sd->sent + (int64_t)b * sc.sd->sent_len + i);
 }
-__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, int row) {
+// `meta` = the id -> slot table of the tile (plan::rel_meta_init): one warp-broadcast LDS instead of the
+// branchy id -> slot rule in this once-per-tile (cold) code
+__device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, const plan::RelMeta* meta,
+                                           int row) {
   auto rel_at = [&](int id) -> float {
-    return (id >= 0 && id < sc.R) ? rel_s[plan::slot_of_id(id, sc.pd, sc.perm) * TM + row] : 0.f;
+    return (id >= 0 && id < sc.R) ? rel_s[meta[id].slot_off + row] : 0.f;
   };
   const bool on = sc.id_rule != IDR_NONE;
   rc.relP = on ? rel_at(sc.D) : 0.f;
@@ -356,8 +359,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tc_fence_after_sync();
       plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale, [](int, const float (&)[16]) {});
     }
-    row_consts(rc0, sc0, rel_s, row);   // a thread only reads its own column of rel_s: no barrier
-    row_consts(rc1, sc1, rel_s, row);
+    row_consts(rc0, sc0, rel_s, relmeta, row);   // a thread only reads its own column of rel_s: no barrier
+    row_consts(rc1, sc1, rel_s, relmeta, row);
 
     if (tid == 0) TRACE(0, 2);
     const float scale2 = a.scale * LOG2E;
