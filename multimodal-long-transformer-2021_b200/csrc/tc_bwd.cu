@@ -432,8 +432,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t e_addr = smem_u32(smem + SM_E);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_REL, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(e_addr + kk * 32, 16, 1024), idesc_r, kk > 0);
+          umma_ss(tmem + T_REL, sdesc(q_addr).at(kk * 32),
+                  sdesc(e_addr).at(kk * 32), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
       }
       // ---- slim: S runs one chunk ahead ------------------------------------------------------
@@ -452,16 +452,16 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + ((c & 1) ? T_REL : T_S), make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + ((c & 1) ? T_REL : T_S), sdesc(q_addr).at(kk * 32),
+                  sdesc(k_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->sdp_full[c & 1]);
       };
       auto issue_dp = [&](int c) {   // kv_full(c) has been waited for by issue_s(c)
         const uint32_t v_addr = smem_u32(smem + SM_KV + (c % NST) * (2 * TN * 128)) + TN * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_DP, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + T_DP, sdesc(do_addr).at(kk * 32),
+                  sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->dp_full);
         TRACE(3, 6 + 4 * c);
       };
@@ -476,12 +476,12 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t v_addr = k_addr + TN * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_S + BUF(c) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + T_S + BUF(c) * 64, sdesc(q_addr).at(kk * 32),
+                  sdesc(k_addr).at(kk * 32), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_DP + BUF(c) * 64, make_smem_desc_sw128(do_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(v_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + T_DP + BUF(c) * 64, sdesc(do_addr).at(kk * 32),
+                  sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->sdp_full[BUF(c)]);
         TRACE(3, 6 + 4 * c);
       };
@@ -495,7 +495,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_ts(tmem + T_DQ, tmem + T_DP + BUF(pc) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                  make_smem_desc_sw128(k_addr + kk * 2048, 16, 1024), idesc_dq, (pc > 0 || kk > 0));
+                  sdesc(k_addr).at(kk * 2048), idesc_dq, (pc > 0 || kk > 0));
         umma_commit(&bars->kv_empty[st]);
         if (pc == nchunks - 1) {
           if (rpad) {
@@ -505,7 +505,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_after_sync();
             const uint32_t e_addr = smem_u32(smem + SM_E);
             for (int kk = 0; kk < rpad / 16; ++kk)
-              umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, make_smem_desc_sw128(e_addr + kk * 2048, 16, 1024),
+              umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, sdesc(e_addr).at(kk * 2048),
                       idesc_dq, 1u);
             if (a.tg_partial) {
               // table-gradient partial of this tile: dE[64 ids x 64] = dallrel^T . Q  (M = 64, both
@@ -514,8 +514,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               const uint32_t a_addr = smem_u32(smem + SM_A + (SLIM ? (nchunks % NST) * (2 * TN * 128) : 0));
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
-                umma_ss(tmem + T_DE, make_smem_desc_sw128(a_addr + kk * 2048, 16, 1024),
-                        make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_de, kk > 0);
+                umma_ss(tmem + T_DE, sdesc(a_addr).at(kk * 2048),
+                        sdesc(q_addr).at(kk * 2048), idesc_de, kk > 0);
             }
           }
           umma_commit(&bars->dq_full);
@@ -1338,12 +1338,12 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         const uint32_t do_addr = q_addr + TN * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)   // S^T = K . Q_c^T
-          umma_ss(tmem + T_S + BUF(c) * 64, make_smem_desc_sw128(k_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(q_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + T_S + BUF(c) * 64, sdesc(k_addr).at(kk * 32),
+                  sdesc(q_addr).at(kk * 32), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)   // dP^T = V . dO_c^T
-          umma_ss(tmem + T_DP + BUF(c) * 64, make_smem_desc_sw128(v_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(do_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_ss(tmem + T_DP + BUF(c) * 64, sdesc(v_addr).at(kk * 32),
+                  sdesc(do_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->sdp_full[BUF(c)]);
         TRACE(2, 4 * c + 1);
       };
@@ -1358,11 +1358,11 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)   // dV += P^T . dO_c
           umma_ts(tmem + T_DV, tmem + T_S + BUF(pc) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
-                  make_smem_desc_sw128(do_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
+                  sdesc(do_addr).at(kk * 2048), idesc_acc, (pc > 0 || kk > 0));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)   // dK += dS^T . Q_c
           umma_ts(tmem + T_DK, tmem + T_DP + BUF(pc) * 64 + ((16 * kk) / W) * W + ((16 * kk) % W) / 2,
-                  make_smem_desc_sw128(q_addr + kk * 2048, 16, 1024), idesc_acc, (pc > 0 || kk > 0));
+                  sdesc(q_addr).at(kk * 2048), idesc_acc, (pc > 0 || kk > 0));
         umma_commit(&bars->qd_empty[st]);
         TRACE(2, 4 * pc + 3);
         if (pc == nchunks - 1) umma_commit(&bars->acc_full);

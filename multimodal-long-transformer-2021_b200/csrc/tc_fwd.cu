@@ -292,8 +292,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const uint32_t e_addr = smem_u32(smem + SM_E);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_REL, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                  make_smem_desc_sw128(e_addr + kk * 32, 16, 1024), idesc_r, kk > 0);
+          umma_ss(tmem + T_REL, sdesc(q_addr).at(kk * 32),
+                  sdesc(e_addr).at(kk * 32), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
       }
       for (int c = 0; c <= nchunks; ++c) {
@@ -305,8 +305,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TN * 128));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + (c & 1) * 64, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+            umma_ss(tmem + (c & 1) * 64, sdesc(q_addr).at(kk * 32),
+                    sdesc(k_addr).at(kk * 32), idesc_s, kk > 0);
           umma_commit(&bars->s_full[c & 1]);
           TRACE(2, 2 + 2 * c);
         }
@@ -319,7 +319,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ts(tmem + T_O, tmem + (pc & 1) * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                    make_smem_desc_sw128(v_addr + kk * 2048, 16, 1024), idesc_o, (pc > 0 || kk > 0));
+                    sdesc(v_addr).at(kk * 2048), idesc_o, (pc > 0 || kk > 0));
           umma_commit(&bars->o_full[pc & 1]);
           umma_commit(&bars->kv_empty[st]);
           TRACE(2, 3 + 2 * pc);

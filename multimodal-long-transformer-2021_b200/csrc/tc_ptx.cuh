@@ -136,6 +136,22 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor split into its two words, with the start address advanced by a byte offset
+// through ONE integer add: the MMA-issuing thread forms two descriptors per instruction, 12-16
+// instructions per chunk, on the critical path between the elementwise warps' hand-over and their
+// next accumulator (the compiler does not fold `((addr + off) & 0x3FFFF) >> 4` into base + constant).
+// Valid while base + offset stays inside the 256 KB window (always true for shared memory) and both
+// are multiples of 16 bytes.
+struct SmemDescSw128 {
+  uint32_t lo, hi;
+  __device__ __forceinline__ uint64_t at(uint32_t byte_off) const {
+    return ((uint64_t)hi << 32) | (uint64_t)(lo + (byte_off >> 4));
+  }
+};
+__device__ __forceinline__ SmemDescSw128 sdesc(uint32_t smem_addr) {   // LBO 16 B, SBO 1024 B
+  const uint64_t d = make_smem_desc_sw128(smem_addr, 16, 1024);
+  return SmemDescSw128{(uint32_t)d, (uint32_t)(d >> 32)};
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor):
 // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, a_major @15, b_major @16
 // (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
