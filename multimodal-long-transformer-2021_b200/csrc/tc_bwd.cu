@@ -561,7 +561,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool row_ok = i < a.rows.len;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float* bin = bins + bidx * RB * TM;   // slot-ordered, private to (set, part, row)
-    for (int x = lane + 32 * quad; x < RB * TM; x += 128) bin[x] = 0.f;
+    for (int x = 4 * (lane + 32 * quad); x < RB * TM; x += 512)   // 128-bit stores: this is once-per-tile code
+      *reinterpret_cast<float4*>(bin + x) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!SLIM)   // slim: the tile lives in a K/V stage and is written in full by the epilogue
       for (int x = tid; x < TM * 128 / 16; x += NALL) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
     const SegC sc0 = make_segc(a.seg[0], r0, R, pd, perm);
