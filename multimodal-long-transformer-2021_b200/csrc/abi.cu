@@ -91,6 +91,20 @@ RowWs carve_row_ws(char*& p, int B, int H, int len, int R, int d) {
   return w;
 }
 
+// dropout_p in [0, 1); thr = floor(p * 2^32) (0 = off)
+int check_dropout(float p) { return (p >= 0.f && p < 1.f) ? MLT_OK : MLT_ERR_DROPOUT; }
+Dropout make_dropout(float p, uint64_t seed, uint32_t rowset) {
+  Dropout d{};
+  double t = (double)p * 4294967296.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  d.thr = p > 0.f ? (uint32_t)t : 0u;
+  d.inv_keep = 1.f / (1.f - p);
+  d.seed_lo = (uint32_t)seed;
+  d.seed_hi = (uint32_t)(seed >> 32);
+  d.rowset = rowset;
+  return d;
+}
+
 Side explicit_side(const int32_t* mask, const int32_t* ids, int lq, int width) {
   Side s{};
   s.mask_rule = mask ? MR_EXPLICIT : MR_NONE;
@@ -111,7 +125,7 @@ int validate_dense(const mlt_dense_params* p) {
   if (p->B <= 0 || p->Lq <= 0 || p->Lk <= 0 || p->H <= 0 || p->d <= 0 || p->R < 0) return MLT_ERR_SHAPE;
   if (p->R > 64) return MLT_ERR_UNSUPPORTED;
   if (!simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
-  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  MLT_TRY(check_dropout(p->dropout_p));
   MLT_TRY(check_t4(p->q, p->dtype, p->d));
   MLT_TRY(check_t4(p->k, p->dtype, p->d));
   MLT_TRY(check_t4(p->v, p->dtype, p->d));
@@ -162,7 +176,7 @@ int validate_gl(const mlt_gl_params* p) {
     return MLT_ERR_SHAPE;
   if (p->R > 64) return MLT_ERR_UNSUPPORTED;
   if (!simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
-  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  MLT_TRY(check_dropout(p->dropout_p));
   const mlt_tensor4* ts[] = {&p->long_q, &p->long_k, &p->long_v, &p->global_q, &p->global_k,
                              &p->global_v, &p->long_out, &p->global_out};
   for (const mlt_tensor4* t : ts) MLT_TRY(check_t4(*t, p->dtype, p->d));
@@ -215,7 +229,7 @@ Side gl_side(const mlt_gl_params* p, GlBlock blk) {
 }
 
 KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, int radius,
-                const Side& side) {
+                const Side& side, int col_base = 0) {
   KeySeg s{};
   s.k = to_t4(k);
   s.v = to_t4(v);
@@ -223,7 +237,23 @@ KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, i
   s.band = band;
   s.radius = radius;
   s.side = side;
+  s.col_base = col_base;
   return s;
+}
+QuerySource make_src(const RowSet& rows, const mlt_tensor4& d_out, const float* stats, const RowWs& ws, int band,
+                     int radius, const Side& side, int col_base, const Dropout& drop) {
+  QuerySource q{};
+  q.rows = rows;
+  q.d_out = to_t4(d_out);
+  q.stats = stats;
+  q.delta = ws.delta;
+  q.allrel = ws.allrel;
+  q.band = band;
+  q.radius = radius;
+  q.side = side;
+  q.col_base = col_base;
+  q.drop = drop;
+  return q;
 }
 
 // ---- fork / join helper: runs independent kernels of one call on a second, library-owned
@@ -233,34 +263,41 @@ KeySeg make_seg(const mlt_tensor4& k, const mlt_tensor4& v, int len, int band, i
 struct ForkCtx {
   cudaStream_t s2 = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
+  bool ok = false, tried = false;
+  std::mutex mu;   // held by the one call that is using this context (try_lock only: never blocks)
 };
-constexpr int kMaxDevices = 64;
-ForkCtx g_fork[kMaxDevices];
-std::once_flag g_fork_once[kMaxDevices];
-std::mutex g_fork_mu;
+// A small pool of side-stream contexts per device.  A call takes any free context with try_lock; when
+// all are busy (many host threads enqueueing on one device at once) it simply runs unforked on the
+// caller's stream -- no call ever waits for another one.
+constexpr int kMaxDevices = 64, kForkPool = 4;
+ForkCtx g_fork[kMaxDevices][kForkPool];
 
-ForkCtx* get_fork() {
+ForkCtx* acquire_fork() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
-  std::call_once(g_fork_once[dev], [dev] {
-    ForkCtx& f = g_fork[dev];
-    f.ok = cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) == cudaSuccess;
-  });
-  return g_fork[dev].ok ? &g_fork[dev] : nullptr;
+  for (int i = 0; i < kForkPool; ++i) {
+    ForkCtx& f = g_fork[dev][i];
+    if (!f.mu.try_lock()) continue;
+    if (!f.tried) {
+      f.tried = true;
+      f.ok = cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (f.ok) return &f;   // locked
+    f.mu.unlock();
+  }
+  return nullptr;
 }
 
 // RAII: between construction and join() the side stream is ordered after everything enqueued on
-// `st` so far; join() orders `st` after the side stream.  Holds a mutex for the enqueue window.
+// `st` so far; join() orders `st` after the side stream.  Owns one pool context for the enqueue window.
 class ForkScope {
  public:
-  explicit ForkScope(cudaStream_t st) : st_(st), f_(profile_enabled() ? nullptr : get_fork()) {
+  explicit ForkScope(cudaStream_t st) : st_(st), f_(profile_enabled() ? nullptr : acquire_fork()) {
     if (f_) {
-      g_fork_mu.lock();
       if (cudaEventRecord(f_->fork, st_) != cudaSuccess || cudaStreamWaitEvent(f_->s2, f_->fork, 0) != cudaSuccess) {
-        g_fork_mu.unlock();
+        f_->mu.unlock();
         f_ = nullptr;
       }
     }
@@ -276,7 +313,7 @@ class ForkScope {
   ~ForkScope() {
     if (f_) {
       join();
-      g_fork_mu.unlock();
+      f_->mu.unlock();
     }
   }
 
@@ -325,6 +362,7 @@ FwdArgs dense_fwd_args(const mlt_dense_params* p, const int32_t* ids_plane = nul
   a.H = p->H;
   a.scale = p->scale;
   a.neg = p->neg;
+  a.drop = make_dropout(p->dropout_p, p->dropout_seed, 0);
   return a;
 }
 
@@ -333,11 +371,12 @@ FwdArgs gl_long_fwd_args(const mlt_gl_params* p) {
   FwdArgs a{};
   a.rows = RowSet{to_t4(p->long_q), p->L, p->long_tables.emb, p->long_tables.bias, p->R};
   a.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, gl_side(p, L2L));
-  a.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, L2G));
+  a.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, L2G), p->L);
   a.nseg = 2;
   a.out = to_t4(p->long_out);
   a.stats = p->long_stats;
   a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  a.drop = make_dropout(p->dropout_p, p->dropout_seed, 0);
   return a;
 }
 
@@ -346,11 +385,12 @@ FwdArgs gl_global_fwd_args(const mlt_gl_params* p) {
   FwdArgs g{};
   g.rows = RowSet{to_t4(p->global_q), p->G, p->global_tables.emb, p->global_tables.bias, p->R};
   g.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, gl_side(p, G2G));
-  g.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, gl_side(p, G2L));
+  g.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, gl_side(p, G2L), p->G);
   g.nseg = 2;
   g.out = to_t4(p->global_out);
   g.stats = p->global_stats;
   g.B = p->B; g.H = p->H; g.scale = p->scale; g.neg = p->neg;
+  g.drop = make_dropout(p->dropout_p, p->dropout_seed, 1);
   return g;
 }
 
@@ -374,13 +414,11 @@ int launch_fwd(const FwdArgs& a, bool tc, int dtype, int d, const char* name, do
   return MLT_OK;
 }
 
-bool t4_tc_ok(const T4& t) {
-  return t.ptr && t.sb % 8 == 0 && t.sl % 8 == 0 && t.sh % 8 == 0 && reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0;
-}
 bool bwd_kv_on_tc(const BwdKVArgs& kv) {
-  if (!t4_tc_ok(kv.k) || !t4_tc_ok(kv.v) || !t4_tc_ok(kv.d_k) || !t4_tc_ok(kv.d_v)) return false;
+  auto ok = [&](const T4& t, int len) { return tc_t4_ok(t, kv.B, len, kv.H); };
+  if (!ok(kv.k, kv.len) || !ok(kv.v, kv.len) || !ok(kv.d_k, kv.len) || !ok(kv.d_v, kv.len)) return false;
   for (int s = 0; s < kv.nsrc; ++s)
-    if (!t4_tc_ok(kv.src[s].rows.q) || !t4_tc_ok(kv.src[s].d_out)) return false;
+    if (!ok(kv.src[s].rows.q, kv.src[s].rows.len) || !ok(kv.src[s].d_out, kv.src[s].rows.len)) return false;
   return true;
 }
 
@@ -419,7 +457,7 @@ const char* mlt_strerror(int code) {
     case MLT_ERR_STRIDE: return "mlt: stride/alignment requirement violated (4 elements, 16 bytes)";
     case MLT_ERR_WORKSPACE: return "mlt: workspace missing or too small";
     case MLT_ERR_DTYPE: return "mlt: unknown dtype";
-    case MLT_ERR_DROPOUT: return "mlt: attention-probability dropout is not implemented (dropout_p must be 0)";
+    case MLT_ERR_DROPOUT: return "mlt: dropout_p must lie in [0, 1)";
     default:
       if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
       return "mlt: unknown error";
@@ -497,10 +535,11 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   q.allrel = ws.allrel;
   q.dallrel = ws.dallrel;
   q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
+  q.drop = make_dropout(p->dropout_p, p->dropout_seed, 0);
   BwdKVArgs kv{};
   kv.k = to_t4(p->k); kv.v = to_t4(p->v); kv.d_k = to_t4(g->d_k); kv.d_v = to_t4(g->d_v);
   kv.len = p->Lk;
-  kv.src[0] = QuerySource{dense_rows(p), to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, side};
+  kv.src[0] = make_src(dense_rows(p), g->d_out, p->stats, ws, 0, 0, side, 0, q.drop);
   kv.nsrc = 1;
   kv.B = p->B; kv.H = p->H; kv.scale = p->scale; kv.neg = p->neg;
 
@@ -573,8 +612,9 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   BwdQArgs ql{};
   ql.rows = long_rows;
   ql.seg[0] = make_seg(p->long_k, p->long_v, p->L, 1, p->local_radius, s_l2l);
-  ql.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_l2g);
+  ql.seg[1] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_l2g, p->L);
   ql.nseg = 2;
+  ql.drop = make_dropout(p->dropout_p, p->dropout_seed, 0);
   ql.out = to_t4(p->long_out); ql.d_out = to_t4(g->d_long_out); ql.d_q = to_t4(g->d_long_q);
   ql.stats = p->long_stats; ql.delta = wl.delta; ql.allrel = wl.allrel; ql.dallrel = wl.dallrel;
   ql.B = p->B; ql.H = p->H; ql.scale = p->scale; ql.neg = p->neg;
@@ -582,8 +622,9 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   BwdQArgs qg{};
   qg.rows = glob_rows;
   qg.seg[0] = make_seg(p->global_k, p->global_v, p->G, 0, 0, s_g2g);
-  qg.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, s_g2l);
+  qg.seg[1] = make_seg(p->long_k, p->long_v, p->L, 0, 0, s_g2l, p->G);
   qg.nseg = 2;
+  qg.drop = make_dropout(p->dropout_p, p->dropout_seed, 1);
   qg.out = to_t4(p->global_out); qg.d_out = to_t4(g->d_global_out); qg.d_q = to_t4(g->d_global_q);
   qg.stats = p->global_stats; qg.delta = wg.delta; qg.allrel = wg.allrel; qg.dallrel = wg.dallrel;
   qg.B = p->B; qg.H = p->H; qg.scale = p->scale; qg.neg = p->neg;
@@ -592,18 +633,16 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
   BwdKVArgs kl{};
   kl.k = to_t4(p->long_k); kl.v = to_t4(p->long_v); kl.d_k = to_t4(g->d_long_k); kl.d_v = to_t4(g->d_long_v);
   kl.len = p->L;
-  kl.src[0] = QuerySource{long_rows, to_t4(g->d_long_out), p->long_stats, wl.delta, wl.allrel, 1,
-                          p->local_radius, s_l2l};
-  kl.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0,
-                          s_g2l};
+  kl.src[0] = make_src(long_rows, g->d_long_out, p->long_stats, wl, 1, p->local_radius, s_l2l, 0, ql.drop);
+  kl.src[1] = make_src(glob_rows, g->d_global_out, p->global_stats, wg, 0, 0, s_g2l, p->G, qg.drop);
   kl.nsrc = 2;
   kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
   // global keys: from long queries (dense, l2g) and global queries (dense, g2g)
   BwdKVArgs kg{};
   kg.k = to_t4(p->global_k); kg.v = to_t4(p->global_v); kg.d_k = to_t4(g->d_global_k); kg.d_v = to_t4(g->d_global_v);
   kg.len = p->G;
-  kg.src[0] = QuerySource{long_rows, to_t4(g->d_long_out), p->long_stats, wl.delta, wl.allrel, 0, 0, s_l2g};
-  kg.src[1] = QuerySource{glob_rows, to_t4(g->d_global_out), p->global_stats, wg.delta, wg.allrel, 0, 0, s_g2g};
+  kg.src[0] = make_src(long_rows, g->d_long_out, p->long_stats, wl, 0, 0, s_l2g, p->L, ql.drop);
+  kg.src[1] = make_src(glob_rows, g->d_global_out, p->global_stats, wg, 0, 0, s_g2g, 0, qg.drop);
   kg.nsrc = 2;
   kg.B = p->B; kg.H = p->H; kg.scale = p->scale; kg.neg = p->neg;
 
@@ -664,7 +703,7 @@ int validate_local(const mlt_local_params* p) {
   if (p->B <= 0 || p->L <= 0 || p->G < 0 || p->H <= 0 || p->d <= 0 || p->R < 0 || p->local_radius < 1)
     return MLT_ERR_SHAPE;
   if (p->R > 64 || !simt_supports_head_dim(p->d)) return MLT_ERR_UNSUPPORTED;
-  if (p->dropout_p != 0.f) return MLT_ERR_DROPOUT;
+  MLT_TRY(check_dropout(p->dropout_p));
   MLT_TRY(check_t4(p->q, p->dtype, p->d));
   MLT_TRY(check_t4(p->k, p->dtype, p->d));
   MLT_TRY(check_t4(p->v, p->dtype, p->d));
@@ -707,12 +746,13 @@ FwdArgs local_fwd_args(const mlt_local_params* p) {
   a.seg[0] = make_seg(p->k, p->v, p->L, 1, p->local_radius, gl_side(&g, L2L));
   a.nseg = 1;
   if (p->G > 0) {
-    a.seg[1] = make_seg(p->side_k, p->side_v, p->G, 0, 0, gl_side(&g, L2G));
+    a.seg[1] = make_seg(p->side_k, p->side_v, p->G, 0, 0, gl_side(&g, L2G), p->L);
     a.nseg = 2;
   }
   a.out = to_t4(p->out);
   a.stats = p->stats;
   a.B = p->B; a.H = p->H; a.scale = p->scale; a.neg = p->neg;
+  a.drop = make_dropout(p->dropout_p, p->dropout_seed, 0);
   return a;
 }
 }  // namespace
@@ -762,17 +802,18 @@ int mlt_local_rel_attn_bwd(const mlt_local_params* p, const mlt_local_grads* g, 
   q.out = to_t4(p->out); q.d_out = to_t4(g->d_out); q.d_q = to_t4(g->d_q);
   q.stats = p->stats; q.delta = ws.delta; q.allrel = ws.allrel; q.dallrel = ws.dallrel;
   q.B = p->B; q.H = p->H; q.scale = p->scale; q.neg = p->neg;
+  q.drop = f.drop;
   BwdKVArgs kl{};
   kl.k = to_t4(p->k); kl.v = to_t4(p->v); kl.d_k = to_t4(g->d_k); kl.d_v = to_t4(g->d_v);
   kl.len = p->L;
-  kl.src[0] = QuerySource{f.rows, to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 1, p->local_radius, f.seg[0].side};
+  kl.src[0] = make_src(f.rows, g->d_out, p->stats, ws, 1, p->local_radius, f.seg[0].side, 0, f.drop);
   kl.nsrc = 1;
   kl.B = p->B; kl.H = p->H; kl.scale = p->scale; kl.neg = p->neg;
   BwdKVArgs ks{};
   if (p->G > 0) {
     ks.k = to_t4(p->side_k); ks.v = to_t4(p->side_v); ks.d_k = to_t4(g->d_side_k); ks.d_v = to_t4(g->d_side_v);
     ks.len = p->G;
-    ks.src[0] = QuerySource{f.rows, to_t4(g->d_out), p->stats, ws.delta, ws.allrel, 0, 0, f.seg[1].side};
+    ks.src[0] = make_src(f.rows, g->d_out, p->stats, ws, 0, 0, f.seg[1].side, p->L, f.drop);
     ks.nsrc = 1;
     ks.B = p->B; ks.H = p->H; ks.scale = p->scale; ks.neg = p->neg;
   }

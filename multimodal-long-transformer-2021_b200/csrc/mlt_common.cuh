@@ -52,7 +52,42 @@ struct KeySeg {
   int band;    // 1 = band segment (keys are the query sequence), 0 = dense
   int radius;
   Side side;
+  int col_base;  // position of key 0 on the row set's concatenated key axis (dropout counter)
 };
+
+// ---- attention-probability dropout ----------------------------------------------------------
+// keep(i, col) is a pure function of (seed, batch, head, row set, query row i, column col), where
+// col indexes the row's concatenated key axis (segment 0 first).  Forward, both backward passes, the
+// SIMT and the tcgen05 kernels and the numpy restatement in tests/ all evaluate the same function, so
+// the mask is never stored.  The hash is the 32-bit finaliser "lowbias32" (two multiplies, three
+// xor-shifts) over a per-(batch, head, row set) salted linear counter; keep iff hash >= thr with
+// thr = floor(p * 2^32): the rate is exact to 2^-32.
+struct Dropout {
+  uint32_t thr;        // 0: dropout off
+  float inv_keep;      // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi;
+  uint32_t rowset;     // 0: dense / long rows, 1: global rows
+};
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+// salt of one (batch * H + head, row set) unit
+__host__ __device__ __forceinline__ uint32_t dropout_salt(const Dropout& d, uint32_t bh) {
+  return mix32(d.seed_lo ^ mix32(d.seed_hi + 0x9e3779b9U * (2u * bh + d.rowset + 1u)));
+}
+// per-row base: salt + i * 0x10001 (rows 65537 counters apart; columns add their index)
+__host__ __device__ __forceinline__ uint32_t dropout_row_base(uint32_t salt, int i) {
+  return salt + (uint32_t)i * 0x00010001U;
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t row_base, int col, uint32_t thr) {
+  return mix32(row_base + (uint32_t)col) >= thr;
+}
 
 struct RowSet {  // query rows + the tables of their attention core
   T4 q;
@@ -70,6 +105,7 @@ struct FwdArgs {
   float* stats;  // [B, H, Lq, 2]
   int B, H;
   float scale, neg;
+  Dropout drop;
 };
 
 // Backward, query-centric pass: dq + per-row dallrel bins; also publishes delta / allrel.
@@ -88,6 +124,7 @@ struct BwdQArgs {
   float* tg_partial_bias;
   int B, H;
   float scale, neg;
+  Dropout drop;
 };
 
 // One query source as seen from a key set (key-centric pass).
@@ -99,6 +136,8 @@ struct QuerySource {
   const float* allrel;
   int band, radius;
   Side side;  // row = query index, col = key index (band: j - i + r)
+  int col_base;   // position of this key set on the source rows' concatenated key axis (dropout counter)
+  Dropout drop;   // of the source's row set
 };
 
 struct BwdKVArgs {

@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const FwdArgs a) {
   for (int c = 0; c < DH; ++c) o[c] = 0.f;
 
   const int wrow0 = i0 + (tid >> 5) * 16;  // first row of this warp
+  const uint32_t dthr = a.drop.thr;
+  const uint32_t drow = dropout_row_base(dropout_salt(a.drop, (uint32_t)(b * a.H + h)), i);
   for (int sgi = 0; sgi < a.nseg; ++sgi) {
     const KeySeg& sg = a.seg[sgi];
     const Side& sd = sg.side;
@@ -190,14 +192,15 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const FwdArgs a) {
             m = s;
           }
           const float p = __expf(s - m);
-          l += p;
-          axpy_half<DH>(o, p, vs + jj * D + half * DH);
+          l += p;   // the softmax normaliser is taken BEFORE dropout
+          const bool keep = dthr == 0 || dropout_keep(drow, sg.col_base + j, dthr);
+          axpy_half<DH>(o, keep ? p : 0.f, vs + jj * D + half * DH);
         }
       }
     }
   }
   if (row_ok) {
-    store_half<T, DH>(row_ptr_mut<T>(a.out, b, i, h) + half * DH, o, 1.f / l);
+    store_half<T, DH>(row_ptr_mut<T>(a.out, b, i, h) + half * DH, o, (dthr ? a.drop.inv_keep : 1.f) / l);
     if (half == 0) {
       float2* st = reinterpret_cast<float2*>(a.stats) + ((int64_t)(b * a.H + h) * a.rows.len + i);
       *st = make_float2(m, l);
@@ -254,6 +257,8 @@ __global__ void __launch_bounds__(NT) bwd_q_kernel(const BwdQArgs a) {
   __syncthreads();
 
   const int wrow0 = i0 + (tid >> 5) * 16;
+  const uint32_t dthr = a.drop.thr;
+  const uint32_t drow = dropout_row_base(dropout_salt(a.drop, (uint32_t)(b * a.H + h)), i);
   for (int sgi = 0; sgi < a.nseg; ++sgi) {
     const KeySeg& sg = a.seg[sgi];
     const Side& sd = sg.side;
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(NT) bwd_q_kernel(const BwdQArgs a) {
           float s = (acc + rel) * a.scale;
           if (!ok) s += a.neg;
           const float p = __expf(s - m) * linv;
+          if (dthr) dp = dropout_keep(drow, sg.col_base + j, dthr) ? dp * a.drop.inv_keep : 0.f;
           const float ds = p * (dp - delta);
           axpy_half<DH>(dq, ds, ks + jj * D + half * DH);
           if (idv && half == 0) drel_s[id * ROWS + rl] += ds;
@@ -357,6 +363,8 @@ __global__ void __launch_bounds__(NT) bwd_kv_kernel(const BwdKVArgs a) {
       ib = max(0, j0 - qs_src.radius);
       ie = min(lq, j0 + ROWS + qs_src.radius);
     }
+    const uint32_t dthr = qs_src.drop.thr;
+    const uint32_t dsalt = dropout_salt(qs_src.drop, (uint32_t)(b * a.H + h));
     int k_e = 0, k_sent = -1;
     if (key_ok && sd.mask_rule == MR_EXAMPLE_ID) k_e = __ldg(sd.k_eid + (int64_t)b * sd.k_len + j);
     if (key_ok && sd.id_rule == IDR_CROSS_KSENT) k_sent = __ldg(sd.sent + (int64_t)b * sd.sent_len + j);
@@ -401,8 +409,14 @@ __global__ void __launch_bounds__(NT) bwd_kv_kernel(const BwdKVArgs a) {
           float s = (acc + rel) * a.scale;
           if (!ok) s += a.neg;
           const float p = __expf(s - m_s[ii]) * linv_s[ii];
+          float pd = p;   // dropped-out probability (what multiplied V in the forward)
+          if (dthr) {
+            const bool keep = dropout_keep(dropout_row_base(dsalt, i), qs_src.col_base + j, dthr);
+            pd = keep ? p * qs_src.drop.inv_keep : 0.f;
+            dp = keep ? dp * qs_src.drop.inv_keep : 0.f;
+          }
           const float ds = p * (dp - delta_s[ii]);
-          axpy_half<DH>(dv, p, gos + ii * D + half * DH);
+          axpy_half<DH>(dv, pd, gos + ii * D + half * DH);
           axpy_half<DH>(dk, ds, qs + ii * D + half * DH);
         }
       }

@@ -7,7 +7,35 @@
 #include "../../include/mlt_attn.h"
 #include "mlt_common.cuh"
 
+#include <mutex>
+
 namespace mlt {
+
+// Runs `fn` (returning 0 on success) once per CUDA device, thread-safe: kernel function attributes
+// are per device, and the library is entered from arbitrary threads (TF's inter-op pool).  A failed
+// attempt is retried by the next caller.
+class PerDeviceOnce {
+ public:
+  template <typename F>
+  int run(F&& fn) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMax) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu_);
+    if (done_[dev]) return 0;
+    const int e = fn();
+    if (e == 0) done_[dev] = true;
+    return e;
+  }
+
+ private:
+  static constexpr int kMax = 64;
+  std::mutex mu_;
+  bool done_[kMax] = {};
+};
+
+// [B, len, H, 64] bf16 view addressable by the TMA path (16-byte base / strides, broadcast strides
+// only over extents of 1).
+bool tc_t4_ok(const T4& t, int B, int len, int H);
 
 // True when the tcgen05 forward kernel can run this problem (bf16, d == 64, R <= 64, 16-byte
 // aligned strides, TMA encode entry point available).

@@ -13,8 +13,6 @@
 // backward needs no row reductions) + TMA warp + MMA warp, 512 TMEM columns.
 #include "tc_api.cuh"
 
-#include <cstdlib>
-
 #include "mlt_common.cuh"
 #include "tc_plan.cuh"
 #include "tc_ptx.cuh"
@@ -200,6 +198,7 @@ struct SegC {          // warp-uniform
   int mask_rule, id_rule;
   int D, R, pd;
   bool perm;
+  int col_base;        // dropout counter offset of key 0
 };
 struct RowC {          // per thread and segment
   int q_e, q_sent;
@@ -218,6 +217,7 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
   sc.R = R;
   sc.pd = pd;
   sc.perm = perm;
+  sc.col_base = sg.col_base;
   return sc;
 }
 
@@ -312,7 +312,7 @@ constexpr int bq_threads() { return (4 * (SLIM ? 1 : 2) * SETS + 3) * 32; }
 
 // EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
 // instantiations stay free of its code and register pressure.
-template <int SETS, bool SLIM, bool EX = false>
+template <int SETS, bool SLIM, bool EX = false, bool DROP = false>
 __global__ void __launch_bounds__(bq_threads<SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
@@ -571,6 +571,23 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     row_loads(rc0, sc0, b, i, row_ok);
     row_loads(rc1, sc1, b, i, row_ok);
     // row constants (written by tc_bwd_prep_kernel)
+    // The ABI's `neg` is honoured literally (see tc_fwd.cu): |neg| > 1e5 -> a masked score is the
+    // additive constant itself (per-row constant lpm below); |neg| <= 1e5 ("literal" mode) -> a masked
+    // element evaluates like an unmasked one with neg * log2e added to its exponent, and FAST groups
+    // with masked rows take the per-element EDGE form.
+    const bool lit = fabsf(a.neg) <= 1e5f;
+    const bool skip_ok = a.neg < -200.f;
+    const float negl2 = a.neg * LOG2E;
+    const float real_thr2 = 0.5f * a.neg * LOG2E;
+    const uint32_t drow = DROP ? dropout_row_base(dropout_salt(a.drop, (uint32_t)(b * a.H + h)), i0 + (warp & 3) * 32 + lane) : 0u;
+    const uint32_t dthr = a.drop.thr;
+    const float dinv = a.drop.inv_keep;
+    // dP of the element at dropout column `col`: the gradient reaches P only where it was kept
+    auto dpv = [&](uint32_t wraw, int col) -> float {
+      const float w = __uint_as_float(wraw);
+      if constexpr (DROP) return dropout_keep(drow, col, dthr) ? w * dinv : 0.f;
+      else return w;
+    };
     float nm2l = -INFINITY;   // -(m*log2e + log2 l): rows beyond the end evaluate to p = 0
     float lpm = -INFINITY;    // log2 of p of a masked element
     float delta = 0.f;
@@ -581,7 +598,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float4 rs4 = __ldg(p.rowstat + prow);
       const float ll = __log2f(rs4.y);   // log2(1/l)
       nm2l = ll - rs4.x;
-      real_max = rs4.x > -1e8f;
+      real_max = rs4.x > real_thr2;
       lpm = real_max ? -INFINITY : ll;
       delta = rs4.z;
     }
@@ -658,15 +675,17 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t t_dp = tmem + T_DP + BUF(c) * 64 + lane_sel + part * W;
         const uint32_t w0 = cp->q[quad][part];
         const int ce0 = (int)cp->q[quad][2 + part];
-        const int mode = (int)(w0 & 0xffu);
+        int mode = (int)(w0 & 0xffu);
         const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
         const bool masked = mre && !mask_pe && (rc.q_e != ce0);
         const int ccls = (int)((w0 >> 8) & 0xffu);
         const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+        const int dcol = sc.col_base + g0;   // dropout counter of the group's first key
         uint32_t ds_pk[W / 2];
         bool zero = (mode == plan::DEAD);
         // every row of the warp masked for the whole group while holding a real maximum: p == 0 exactly
-        if (!zero && mode == plan::FAST && mre && __all_sync(0xffffffffu, masked && real_max)) zero = true;
+        if (!zero && mode == plan::FAST && mre && skip_ok && __all_sync(0xffffffffu, masked && real_max)) zero = true;
+        if (lit && !zero && mode == plan::FAST && __any_sync(0xffffffffu, masked)) mode = plan::EDGE;
         if (zero) {
 #pragma unroll
           for (int x = 0; x < W / 2; ++x) ds_pk[x] = 0u;
@@ -689,8 +708,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int x = 0; x < W / 2; ++x) {
             const float p0 = SLIM ? __uint_as_float(v[2 * x]) : ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
             const float p1 = SLIM ? __uint_as_float(v[2 * x + 1]) : ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
-            const float d0 = p0 * (__uint_as_float(w[2 * x]) - delta);
-            const float d1 = p1 * (__uint_as_float(w[2 * x + 1]) - delta);
+            const float d0 = p0 * (dpv(w[2 * x], dcol + 2 * x) - delta);
+            const float d1 = p1 * (dpv(w[2 * x + 1], dcol + 2 * x + 1) - delta);
             t0 += d0;
             t1 += d1;
             ds_pk[x] = pack_bf16x2(d0, d1);
@@ -714,8 +733,9 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               float rel;
               eval_generic_q(sc, rc, b, i, row, row_ok, g0 + jj, cp->ce[part * W + jj], cp->cs[part * W + jj], rel_s,
                              live, ok, rel, slot);
-              const float pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, fmaf(rel, LOG2E, nm2l)) : lpm);
-              const float dsv = live ? pv * (__uint_as_float(dpr) - delta) : 0.f;
+              const float eu = fmaf(__uint_as_float(raw), scale2, fmaf(rel, LOG2E, nm2l));
+              const float pv = ex2(ok ? eu : (lit ? eu + negl2 : lpm));
+              const float dsv = live ? pv * (dpv(dpr, dcol + jj) - delta) : 0.f;
               if (live && slot >= 0) bin[slot * TM + row] += dsv;
               __syncwarp();   // score_generic diverges per row; tcgen05.st needs the converged warp
               tmem_st1(t_s + jj, __float_as_uint(dsv));
@@ -803,7 +823,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                   int ok[W];
                   plan::load_row32(sd.mask + eoff, vec && (reinterpret_cast<uintptr_t>(sd.mask) & 15) == 0, take, 1, ok);
 #pragma unroll
-                  for (int jj = 0; jj < W; ++jj) e[jj] = ok[jj] != 0 ? e[jj] : lpm;
+                  for (int jj = 0; jj < W; ++jj) e[jj] = ok[jj] != 0 ? e[jj] : (lit ? e[jj] + negl2 : lpm);
                 }
                 if (live != 0xffffffffu) {
 #pragma unroll
@@ -820,10 +840,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (mask_pe) {
 #pragma unroll
               for (int jj = 0; jj < W; ++jj)
-                e[jj] = (cp->ce[part * W + jj] == rc.q_e || e[jj] == -INFINITY) ? e[jj] : lpm;
+                e[jj] = (cp->ce[part * W + jj] == rc.q_e || e[jj] == -INFINITY) ? e[jj] : (lit ? e[jj] + negl2 : lpm);
             } else if (mre && __any_sync(0xffffffffu, masked)) {
 #pragma unroll
-              for (int jj = 0; jj < W; ++jj) e[jj] = (masked && e[jj] != -INFINITY) ? lpm : e[jj];
+              for (int jj = 0; jj < W; ++jj) e[jj] = (masked && e[jj] != -INFINITY) ? (lit ? e[jj] + negl2 : lpm) : e[jj];
             }
             float t0 = 0.f, t1 = 0.f;
             if (SLIM) {   // probabilities first: dP of the chunk may still be executing
@@ -837,8 +857,8 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int x = 0; x < W; x += 2) {
               const float p0 = SLIM ? e[x] : ex2(e[x]);
               const float p1 = SLIM ? e[x + 1] : ex2(e[x + 1]);
-              ds[x] = p0 * (__uint_as_float(w[x]) - delta);
-              ds[x + 1] = p1 * (__uint_as_float(w[x + 1]) - delta);
+              ds[x] = p0 * (dpv(w[x], dcol + x) - delta);
+              ds[x + 1] = p1 * (dpv(w[x + 1], dcol + x + 1) - delta);
               t0 += ds[x];
               t1 += ds[x + 1];
             }
@@ -1136,6 +1156,8 @@ struct SrcC {            // warp-uniform, one per query source
   bool band;
   int radius;
   int mask_rule, id_rule;
+  int col_base;          // dropout: position of this key set on the source rows' key axis
+  Dropout drop;          // dropout descriptor of the source's row set
 };
 struct KeyC {            // per thread and source
   int k_e, k_sent;
@@ -1152,6 +1174,8 @@ __device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRan
   sc.radius = src.q.radius;
   sc.mask_rule = src.q.side.mask_rule;
   sc.id_rule = sc.R > 0 ? src.q.side.id_rule : IDR_NONE;
+  sc.col_base = src.q.col_base;
+  sc.drop = src.q.drop;
   return sc;
 }
 
@@ -1221,7 +1245,7 @@ constexpr int bk_threads() { return (4 * NP * SETS + (SLIM ? 2 : 3)) * 32; }
 // per-query constants arrive exponent-ready in the row records the query-centric pass published
 // (TcBwdQParams::rec_ws), so the common element costs
 //     p = ex2(fma(x, scale*log2e, rec[i][4 + id])),  ds = p * (dp - rec[i][2]).
-template <int NP, int SETS, bool SLIM, bool EX = false>
+template <int NP, int SETS, bool SLIM, bool EX = false, bool DROP = false>
 __global__ void __launch_bounds__(bk_threads<NP, SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
@@ -1395,11 +1419,20 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     const bool key_ok = j < p.len;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     const float scale2 = p.scale * LOG2E;
+    // `neg` honoured literally (see tc_fwd.cu / the query-centric pass): in literal mode a masked element
+    // evaluates like an unmasked one with neg * log2e added to its exponent.
+    const bool lit = fabsf(p.neg) <= 1e5f;
+    const float negl2 = p.neg * LOG2E;
     // One call per query source (inlined twice: no per-field selects inside the chunk loop).
     // Chunks [c_begin, c_end) belong to this source; this warp set handles those with c % SETS == set.
     auto run_chunks = [&](const SrcC sc, const KeyC kc, int c_begin, int c_end, int ib) {
       int c = c_begin + ((set - c_begin) % SETS + SETS) % SETS;
       const bool mre = sc.mask_rule == MR_EXAMPLE_ID;
+      // dropout: keep(query i, this key) = hash(salt + i * 0x10001 + col); per thread the key is fixed
+      const uint32_t dthr = sc.drop.thr;
+      const float dinv = sc.drop.inv_keep;
+      const uint32_t dkey = DROP ? dropout_salt(sc.drop, (uint32_t)(b * p.H + h)) + (uint32_t)(sc.col_base + j) : 0u;
+      auto keep_at = [&](int i) -> bool { return mix32(dkey + (uint32_t)i * 0x00010001U) >= dthr; };
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
         const int st = c % NST;
@@ -1419,9 +1452,10 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         const int32_t* csw = cp->cs + part * W;
         const uint32_t w0 = cp->q[quad][grp];
         const int ce0 = (int)cp->q[quad][2 + grp];
-        const int mode = (int)(w0 & 0xffu);
+        int mode = (int)(w0 & 0xffu);
         const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
         const bool masked = mre && !mask_pe && (kc.k_e != ce0);
+        if (lit && mode == plan::FAST && __any_sync(0xffffffffu, masked)) mode = plan::EDGE;
         const int ccls = (int)((w0 >> 8) & 0xffu);
         // record field of the group's constant class
         const int coff = ccls == plan::C_POS ? 4 + sc.D : (ccls == plan::C_NEG ? 4 + 2 * sc.D : (ccls == plan::C_CROSS ? 5 + 2 * sc.D : 0));
@@ -1453,8 +1487,17 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               float pv = 0.f, ds = 0.f;
               if (live) {
                 const float* r = rec + ii;
-                pv = ex2(ok ? fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * RSF]) : r[RSF]);
-                ds = pv * (__uint_as_float(dpr) - r[2 * RSF]);
+                const float eu = fmaf(__uint_as_float(raw), scale2, r[(id >= 0 ? 4 + id : 0) * RSF]);
+                pv = ex2(ok ? eu : (lit ? eu + negl2 : r[RSF]));
+                float dpx = __uint_as_float(dpr);
+                if constexpr (DROP) {
+                  const bool kp = keep_at(g0 + ii);
+                  dpx = kp ? dpx * dinv : 0.f;
+                  ds = pv * (dpx - r[2 * RSF]);
+                  pv = kp ? pv : 0.f;    // dV takes the dropped-out probabilities (1 / (1 - p) joins the epilogue)
+                } else {
+                  ds = pv * (dpx - r[2 * RSF]);
+                }
               }
               __syncwarp();   // the generic evaluation diverges per row; tcgen05.st needs the converged warp
               tmem_st1(t_s + ii, __float_as_uint(pv));
@@ -1484,8 +1527,15 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               for (int x = 0; x < WS / 2; ++x) {
                 const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, cc[2 * x]));
                 const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, cc[2 * x + 1]));
+                if constexpr (DROP) {
+                  const bool k0 = keep_at(g0 + 2 * x), k1 = keep_at(g0 + 2 * x + 1);
+                  p_pk[x] = pack_bf16x2(k0 ? p0 : 0.f, k1 ? p1 : 0.f);
+                  ds_pk[x] = pack_bf16x2(p0 * ((k0 ? __uint_as_float(w[2 * x]) * dinv : 0.f) - dl[2 * x]),
+                                         p1 * ((k1 ? __uint_as_float(w[2 * x + 1]) * dinv : 0.f) - dl[2 * x + 1]));
+                } else {
                 p_pk[x] = pack_bf16x2(p0, p1);
                 ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
+                }
               }
             } else {
               // 1. exponent per element, in place (one code copy per form: `mode` is warp-uniform)
@@ -1522,7 +1572,8 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
                   if (lv && has_i) id = __ldg(sd.ids + eoff + x * est);
                   if (lv && has_m) ok = __ldg(sd.mask + eoff + x * est);
                   const int f = (unsigned)id < (unsigned)sc.R ? 4 + id : 0;
-                  t[x] = ok != 0 ? fmaf(__uint_as_float(v[x]), scale2, rec[f * RSF + x]) : rec[RSF + x];
+                  const float eu = fmaf(__uint_as_float(v[x]), scale2, rec[f * RSF + x]);
+                  t[x] = ok != 0 ? eu : (lit ? eu + negl2 : rec[RSF + x]);
                 }
               } else {
                 const float* c0 = rec + (5 + 2 * sc.D) * RSF;
@@ -1539,10 +1590,10 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               const float* lp = rec + RSF;
               if (mask_pe) {
   #pragma unroll
-                for (int x = 0; x < WS; ++x) t[x] = (ce[x] != kc.k_e) ? lp[x] : t[x];
+                for (int x = 0; x < WS; ++x) t[x] = (ce[x] != kc.k_e) ? (lit ? t[x] + negl2 : lp[x]) : t[x];
               } else if (mre && __any_sync(0xffffffffu, masked)) {
   #pragma unroll
-                for (int x = 0; x < WS; ++x) t[x] = masked ? lp[x] : t[x];
+                for (int x = 0; x < WS; ++x) t[x] = masked ? (lit ? t[x] + negl2 : lp[x]) : t[x];
               }
               // 3. probabilities; EDGE / EXPL: dead columns may carry garbage records -> select, not multiply
               if (mode == plan::EDGE || (EX && mode == plan::EXPL)) {
@@ -1556,18 +1607,33 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   #pragma unroll
                 for (int x = 0; x < WS / 2; ++x) {
                   const bool l0 = (unsigned)(2 * x - ilo) < span, l1 = (unsigned)(2 * x + 1 - ilo) < span;
-                  const float p0 = l0 ? ex2(t[2 * x]) : 0.f, p1 = l1 ? ex2(t[2 * x + 1]) : 0.f;
-                  const float e0 = l0 ? p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]) : 0.f;
-                  const float e1 = l1 ? p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]) : 0.f;
-                  p_pk[x] = pack_bf16x2(p0, p1);
+                  float p0 = l0 ? ex2(t[2 * x]) : 0.f, p1 = l1 ? ex2(t[2 * x + 1]) : 0.f;
+                  float w0f = __uint_as_float(w[2 * x]), w1f = __uint_as_float(w[2 * x + 1]);
+                  bool k0 = true, k1 = true;
+                  if constexpr (DROP) {
+                    k0 = keep_at(g0 + 2 * x);
+                    k1 = keep_at(g0 + 2 * x + 1);
+                    w0f = k0 ? w0f * dinv : 0.f;
+                    w1f = k1 ? w1f * dinv : 0.f;
+                  }
+                  const float e0 = l0 ? p0 * (w0f - dl[2 * x]) : 0.f;
+                  const float e1 = l1 ? p1 * (w1f - dl[2 * x + 1]) : 0.f;
+                  p_pk[x] = pack_bf16x2(k0 ? p0 : 0.f, k1 ? p1 : 0.f);
                   ds_pk[x] = pack_bf16x2(e0, e1);
                 }
               } else {
   #pragma unroll
                 for (int x = 0; x < WS / 2; ++x) {
                   const float p0 = ex2(t[2 * x]), p1 = ex2(t[2 * x + 1]);
+                  if constexpr (DROP) {
+                    const bool k0 = keep_at(g0 + 2 * x), k1 = keep_at(g0 + 2 * x + 1);
+                    p_pk[x] = pack_bf16x2(k0 ? p0 : 0.f, k1 ? p1 : 0.f);
+                    ds_pk[x] = pack_bf16x2(p0 * ((k0 ? __uint_as_float(w[2 * x]) * dinv : 0.f) - dl[2 * x]),
+                                           p1 * ((k1 ? __uint_as_float(w[2 * x + 1]) * dinv : 0.f) - dl[2 * x + 1]));
+                  } else {
                   p_pk[x] = pack_bf16x2(p0, p1);
                   ds_pk[x] = pack_bf16x2(p0 * (__uint_as_float(w[2 * x]) - dl[2 * x]), p1 * (__uint_as_float(w[2 * x + 1]) - dl[2 * x + 1]));
+                  }
                 }
               }
             }
@@ -1618,10 +1684,11 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
 #pragma unroll
       for (int x = 0; x < WO / 8; ++x) {
         uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 0]), __uint_as_float(dv_raw[8 * x + 1]));
-        w.y = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 2]), __uint_as_float(dv_raw[8 * x + 3]));
-        w.z = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 4]), __uint_as_float(dv_raw[8 * x + 5]));
-        w.w = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 6]), __uint_as_float(dv_raw[8 * x + 7]));
+        const float vs = DROP ? p.src[0].q.drop.inv_keep : 1.f;   // every source shares the dropout rate
+        w.x = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 0]) * vs, __uint_as_float(dv_raw[8 * x + 1]) * vs);
+        w.y = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 2]) * vs, __uint_as_float(dv_raw[8 * x + 3]) * vs);
+        w.z = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 4]) * vs, __uint_as_float(dv_raw[8 * x + 5]) * vs);
+        w.w = pack_bf16x2(__uint_as_float(dv_raw[8 * x + 6]) * vs, __uint_as_float(dv_raw[8 * x + 7]) * vs);
         *reinterpret_cast<uint4*>(dv + 8 * x) = w;
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(dk_raw[8 * x + 0]) * p.scale, __uint_as_float(dk_raw[8 * x + 1]) * p.scale);
@@ -1657,13 +1724,11 @@ bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d) {
   f.seg[1] = a.seg[1];
   f.nseg = a.nseg;
   f.out = a.out;
-  auto ok = [](const T4& t) {
-    return t.ptr && t.sb % 8 == 0 && t.sl % 8 == 0 && t.sh % 8 == 0 && reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0;
-  };
-  return tc_fwd_args_supported(f, dtype, d) && ok(a.d_out) && ok(a.d_q);
+  f.B = a.B;
+  f.H = a.H;
+  return tc_fwd_args_supported(f, dtype, d) && tc_t4_ok(a.d_out, a.B, a.rows.len, a.H) &&
+         tc_t4_ok(a.d_q, a.B, a.rows.len, a.H);
 }
-
-static bool g_attr_q = false, g_attr_kv = false;
 
 #ifdef MLT_TC_TRACE
 extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(unsigned long long* out) {
@@ -1671,21 +1736,77 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_b(uns
 }
 #endif
 
-int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
-  if (!g_attr_q) {
-    cudaError_t e = cudaSuccess;
-    auto set = [&](auto kernel, int bytes) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    };
-    set(tc_bwd_q_kernel<2, false>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, false>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, true>, bq::Cfg<true>::SM_ALLOC);
-    set(tc_bwd_q_kernel<2, false, true>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, false, true>, bq::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_q_kernel<1, true, true>, bq::Cfg<true>::SM_ALLOC);
-    if (e != cudaSuccess) return (int)e;
-    g_attr_q = true;
+namespace {
+// launch configuration -> kernel instantiation (EX: explicit int32 side inputs, DROP: dropout on)
+template <int SETS, bool SLIM>
+struct BqLaunch {
+  template <bool EX, bool DROP>
+  static void go(dim3 grid, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdo, const CUtensorMap& mk0,
+                 const CUtensorMap& mv0, const CUtensorMap& mk1, const CUtensorMap& mv1, const CUtensorMap& me,
+                 const TcBwdQParams& p) {
+    tc_bwd_q_kernel<SETS, SLIM, EX, DROP><<<grid, bq_threads<SETS, SLIM>(), bq::Cfg<SLIM>::SM_ALLOC, st>>>(
+        mq, mdo, mk0, mv0, mk1, mv1, me, p);
   }
+  static void run(bool ex, bool dr, dim3 grid, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdo,
+                  const CUtensorMap& mk0, const CUtensorMap& mv0, const CUtensorMap& mk1, const CUtensorMap& mv1,
+                  const CUtensorMap& me, const TcBwdQParams& p) {
+    if (ex && dr) go<true, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    else if (ex) go<true, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    else if (dr) go<false, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    else go<false, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  }
+  static cudaError_t attrs() {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel) {
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::Cfg<SLIM>::SM_ALLOC);
+    };
+    set(tc_bwd_q_kernel<SETS, SLIM, false, false>);
+    set(tc_bwd_q_kernel<SETS, SLIM, true, false>);
+    set(tc_bwd_q_kernel<SETS, SLIM, false, true>);
+    set(tc_bwd_q_kernel<SETS, SLIM, true, true>);
+    return e;
+  }
+};
+template <int NP, int SETS, bool SLIM>
+struct BkLaunch {
+  template <bool EX, bool DROP>
+  static void go(dim3 grid, cudaStream_t st, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap* mq,
+                 const CUtensorMap* mdo, const TcBwdKVParams& p) {
+    tc_bwd_kv_kernel<NP, SETS, SLIM, EX, DROP><<<grid, bk_threads<NP, SETS, SLIM>(), bk::Cfg<SLIM>::SM_ALLOC, st>>>(
+        mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  }
+  static void run(bool ex, bool dr, dim3 grid, cudaStream_t st, const CUtensorMap& mk, const CUtensorMap& mv,
+                  const CUtensorMap* mq, const CUtensorMap* mdo, const TcBwdKVParams& p) {
+    if (ex && dr) go<true, true>(grid, st, mk, mv, mq, mdo, p);
+    else if (ex) go<true, false>(grid, st, mk, mv, mq, mdo, p);
+    else if (dr) go<false, true>(grid, st, mk, mv, mq, mdo, p);
+    else go<false, false>(grid, st, mk, mv, mq, mdo, p);
+  }
+  static cudaError_t attrs() {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel) {
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::Cfg<SLIM>::SM_ALLOC);
+    };
+    set(tc_bwd_kv_kernel<NP, SETS, SLIM, false, false>);
+    set(tc_bwd_kv_kernel<NP, SETS, SLIM, true, false>);
+    set(tc_bwd_kv_kernel<NP, SETS, SLIM, false, true>);
+    set(tc_bwd_kv_kernel<NP, SETS, SLIM, true, true>);
+    return e;
+  }
+};
+}  // namespace
+
+int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
+  static PerDeviceOnce once;
+  const int ae = once.run([] {
+    cudaError_t e = BqLaunch<2, false>::attrs();
+    if (e == cudaSuccess) e = BqLaunch<1, false>::attrs();
+    if (e == cudaSuccess) e = BqLaunch<1, true>::attrs();
+    return (int)e;
+  });
+  if (ae) return ae;
   TcBwdQParams p;
   p.a = a;
   const int R = a.rows.R;
@@ -1724,46 +1845,31 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
   // with few (long rows: band + G/64) the extra per-tile prologue work does not pay off.
   auto seg_chunks = [](const KeySeg& sg) { return sg.band ? (TM + 2 * sg.radius + TN - 1) / TN : (sg.len + TN - 1) / TN; };
   const int est_chunks = seg_chunks(a.seg[0]) + (a.nseg > 1 ? seg_chunks(a.seg[1]) : 0);
-  // 1: one warp set, 2: two warp sets on alternate chunks (many chunks: dense global rows),
-  // 3: slim, two CTAs per SM (few chunks: long rows = band + G/64).  (A slim variant with two
-  // elementwise threads per row was measured slower, 0.75 vs 0.66 ms on the c3_4096 long rows, and
-  // removed: the tile is bound by the quadrant imbalance of the band chunks and by the per-warp
-  // latency chains, not by the number of elementwise warps.)
-  static const int force_cfg = getenv("MLT_BWD_Q_CFG") ? atoi(getenv("MLT_BWD_Q_CFG")) : 0;
-  int cfg = force_cfg ? force_cfg : (est_chunks >= 16 ? 2 : 3);
-  if (R > 32 && cfg != 1) cfg = 1;   // slim and two-set bins hold 32 slots
+  // 1: one warp set (relative vocabulary > 32), 2: two warp sets on alternate chunks (many chunks:
+  // dense global rows), 3: slim, two CTAs per SM (few chunks: long rows = band + G/64).  (A slim
+  // variant with two elementwise threads per row was measured slower, 0.75 vs 0.66 ms on the c3_4096
+  // long rows, and removed: the tile is bound by the quadrant imbalance of the band chunks and by the
+  // per-warp latency chains, not by the number of elementwise warps.)
+  int cfg = est_chunks >= 16 ? 2 : 3;
+  if (R > 32) cfg = 1;   // slim and two-set bins hold 32 slots
   // explicit int32 side inputs: the instantiations that carry the EXPL form
   const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
-  if (cfg == 3 && ex)
-    tc_bwd_q_kernel<1, true, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else if (cfg == 3)
-    tc_bwd_q_kernel<1, true><<<grid, bq_threads<1, true>(), bq::Cfg<true>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else if (cfg == 2 && ex)
-    tc_bwd_q_kernel<2, false, true><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else if (cfg == 2)
-    tc_bwd_q_kernel<2, false><<<grid, bq_threads<2, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else if (ex)
-    tc_bwd_q_kernel<1, false, true><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
-  else
-    tc_bwd_q_kernel<1, false><<<grid, bq_threads<1, false>(), bq::Cfg<false>::SM_ALLOC, st>>>(mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  const bool dr = a.drop.thr != 0;
+  if (cfg == 3) BqLaunch<1, true>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else if (cfg == 2) BqLaunch<2, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+  else BqLaunch<1, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   return (int)cudaGetLastError();
 }
 
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
-  if (!g_attr_kv) {
-    cudaError_t e = cudaSuccess;
-    auto set = [&](auto kernel, int bytes) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    };
-    set(tc_bwd_kv_kernel<2, 2, false>, bk::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_kv_kernel<4, 1, false>, bk::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_kv_kernel<2, 1, true>, bk::Cfg<true>::SM_ALLOC);
-    set(tc_bwd_kv_kernel<2, 2, false, true>, bk::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_kv_kernel<4, 1, false, true>, bk::Cfg<false>::SM_ALLOC);
-    set(tc_bwd_kv_kernel<2, 1, true, true>, bk::Cfg<true>::SM_ALLOC);
-    if (e != cudaSuccess) return (int)e;
-    g_attr_kv = true;
-  }
+  static PerDeviceOnce once;
+  const int ae = once.run([] {
+    cudaError_t e = BkLaunch<2, 2, false>::attrs();
+    if (e == cudaSuccess) e = BkLaunch<4, 1, false>::attrs();
+    if (e == cudaSuccess) e = BkLaunch<2, 1, true>::attrs();
+    return (int)e;
+  });
+  if (ae) return ae;
   TcBwdKVParams p{};
   p.k = a.k; p.v = a.v; p.d_k = a.d_k; p.d_v = a.d_v;
   p.len = a.len;
@@ -1791,23 +1897,15 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   auto src_chunks = [](const QuerySource& q) { return q.band ? (TM + 2 * q.radius + TN - 1) / TN : (q.rows.len + TN - 1) / TN; };
   const int est_chunks = src_chunks(a.src[0]) + (a.nsrc > 1 ? src_chunks(a.src[1]) : 0);
   // Few chunks per tile (long keys: band + G/64): start-up and drain dominate -> the slim
-  // configuration with two CTAs per SM.  Many chunks (global keys): two warp sets on alternate chunks.
-  static const int force_kv = getenv("MLT_KV_CFG") ? atoi(getenv("MLT_KV_CFG")) : 0;   // 1: <4,1>  2: <2,2>  3: slim
+  // configuration with two CTAs per SM (3).  Many chunks (global keys): two warp sets on alternate
+  // chunks (2).  Relative vocabulary > 32 with few chunks: one warp set, four threads per row (1).
   const bool slim_ok = p.src[0].rw <= 32 && p.src[1].rw <= 32;
-  const int cfg = force_kv ? force_kv : (est_chunks >= 16 ? 2 : (slim_ok ? 3 : 1));
+  const int cfg = est_chunks >= 16 ? 2 : (slim_ok ? 3 : 1);
   const bool ex = side_is_explicit(a.src[0].side) || (a.nsrc > 1 && side_is_explicit(a.src[1].side));
-  if (cfg == 3 && slim_ok && ex)
-    tc_bwd_kv_kernel<2, 1, true, true><<<grid, bk_threads<2, 1, true>(), bk::Cfg<true>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
-  else if (cfg == 3 && slim_ok)
-    tc_bwd_kv_kernel<2, 1, true><<<grid, bk_threads<2, 1, true>(), bk::Cfg<true>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
-  else if (cfg == 2 && ex)
-    tc_bwd_kv_kernel<2, 2, false, true><<<grid, bk_threads<2, 2, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
-  else if (cfg == 2)
-    tc_bwd_kv_kernel<2, 2, false><<<grid, bk_threads<2, 2, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
-  else if (ex)
-    tc_bwd_kv_kernel<4, 1, false, true><<<grid, bk_threads<4, 1, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
-  else
-    tc_bwd_kv_kernel<4, 1, false><<<grid, bk_threads<4, 1, false>(), bk::Cfg<false>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
+  const bool dr = a.src[0].drop.thr != 0;
+  if (cfg == 3) BkLaunch<2, 1, true>::run(ex, dr, grid, st, mk, mv, mq, mdo, p);
+  else if (cfg == 2) BkLaunch<2, 2, false>::run(ex, dr, grid, st, mk, mv, mq, mdo, p);
+  else BkLaunch<4, 1, false>::run(ex, dr, grid, st, mk, mv, mq, mdo, p);
   return (int)cudaGetLastError();
 }
 

@@ -23,8 +23,6 @@
 // TMEM map (columns): [0,64) S0/P0, [64,128) S1/P1, [128,192) O, [192,256) allrel.
 #include "tc_api.cuh"
 
-#include <cstdlib>
-
 #include "mlt_common.cuh"
 #include "profile.cuh"
 #include "tc_plan.cuh"
@@ -133,6 +131,7 @@ struct SegC {          // warp-uniform
   int mask_rule, id_rule;
   int D, R, pd;
   bool perm;
+  int col_base;        // dropout counter offset of key 0
 };
 struct RowC {          // per thread and segment
   int q_e, q_sent;
@@ -151,6 +150,7 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
   sc.R = R;
   sc.pd = pd;
   sc.perm = perm;
+  sc.col_base = sg.col_base;
   return sc;
 }
 
@@ -207,7 +207,7 @@ __device__ __forceinline__ float score_generic(float x, const SegC& sc, const Ro
 
 // EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
 // instantiation stays free of its code and register pressure.
-template <bool EX>
+template <bool EX, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 2)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k0,
               const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_k1,
@@ -364,6 +364,16 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     if (tid == 0) TRACE(0, 2);
     const float scale2 = a.scale * LOG2E;
+    // The ABI's `neg` is honoured literally.  |neg| > 1e5 (the reference's -1e9): a masked score is
+    // the additive constant itself in fp32, which the FAST form folds into a per-row constant.
+    // |neg| <= 1e5 ("literal" mode): a masked score still carries x * scale + rel, so FAST groups with
+    // masked rows take the per-element EDGE form.  Masked groups are skipped (p == 0 exactly) only when
+    // neg is negative enough for exp(neg + 64) to flush to zero, against a real (unmasked) maximum.
+    const bool lit = fabsf(a.neg) <= 1e5f;
+    const bool skip_ok = a.neg < -200.f;
+    const float real_thr = 0.5f * a.neg;
+    const uint32_t drow = DROP ? dropout_row_base(dropout_salt(a.drop, (uint32_t)(b * a.H + h)), i) : 0u;
+    const uint32_t dthr = a.drop.thr;
     float m = M_INIT;        // maximum the exponentials are taken against (lags the true maximum)
     float m_true = M_INIT;   // running maximum over the chunks that took the two-pass path
     float l = 0.f;
@@ -406,7 +416,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           auto single_pass_ok = [&](int md, uint32_t w0) {
             return md == plan::DEAD || md == plan::FAST || (md == plan::KS && !(w0 & plan::F_MASK_PE));
           };
-          const bool fastable = seeded && single_pass_ok(md0, pw.x) && single_pass_ok(md1, pw.y);
+          const bool litblock = lit && mre &&
+              __any_sync(0xffffffffu, (md0 != plan::DEAD && rc.q_e != pe.x) || (md1 != plan::DEAD && rc.q_e != pe.y));
+          const bool fastable = seeded && single_pass_ok(md0, pw.x) && single_pass_ok(md1, pw.y) && !litblock;
           if (fastable) {
             const float mb = m * LOG2E;
             uint32_t pk0[16], pk1[16];
@@ -415,7 +427,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               const uint32_t w0 = g ? pw.y : pw.x;
               const bool masked = mre && (rc.q_e != (g ? pe.y : pe.x));   // FAST: mask uniform over the keys
               bool dead = (w0 & 0xffu) == plan::DEAD;
-              if (!dead && mre && __all_sync(0xffffffffu, masked && m > -1e8f)) dead = true;   // p == 0 exactly
+              if (!dead && mre && skip_ok && __all_sync(0xffffffffu, masked && m > real_thr)) dead = true;   // p == 0 exactly
               if (dead) {
 #pragma unroll
                 for (int x = 0; x < 16; ++x) pk[x] = 0u;
@@ -429,17 +441,24 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               uint32_t v[32];
               tmem_ld32(t_s + 32 * g, v);
               tmem_wait_ld();
+              const int dcol = sc.col_base + key0 + 32 * g;   // dropout counter of the group's first key
               auto body = [&](auto subf) {
 #pragma unroll
                 for (int x = 0; x < 16; x += 2) {
-                  const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, subf(2 * x)));
-                  const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, subf(2 * x + 1)));
-                  const float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, subf(2 * x + 2)));
-                  const float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, subf(2 * x + 3)));
+                  float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, subf(2 * x)));
+                  float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, subf(2 * x + 1)));
+                  float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, subf(2 * x + 2)));
+                  float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, subf(2 * x + 3)));
                   ls0 += p0;
                   ls1 += p1;
                   ls2 += p2;
                   ls3 += p3;
+                  if constexpr (DROP) {   // the normaliser is taken before dropout; 1 / (1 - p) joins 1 / l
+                    p0 = dropout_keep(drow, dcol + 2 * x, dthr) ? p0 : 0.f;
+                    p1 = dropout_keep(drow, dcol + 2 * x + 1, dthr) ? p1 : 0.f;
+                    p2 = dropout_keep(drow, dcol + 2 * x + 2, dthr) ? p2 : 0.f;
+                    p3 = dropout_keep(drow, dcol + 2 * x + 3, dthr) ? p3 : 0.f;
+                  }
                   pk[x] = pack_bf16x2(p0, p1);
                   pk[x + 1] = pack_bf16x2(p2, p3);
                 }
@@ -474,7 +493,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           const uint32_t w0 = g ? pw.y : pw.x;
-          const int mode = (int)(w0 & 0xffu);
+          int mode = (int)(w0 & 0xffu);
           if (mode == plan::DEAD) {
             dead_mask |= 1u << g;
             continue;
@@ -482,13 +501,15 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           const int g0 = key0 + 32 * g;
           const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
           const bool masked = mre && !mask_pe && (rc.q_e != (g ? pe.y : pe.x));
+          // literal mode: a masked score keeps x * scale + rel -> per-element form (EDGE with a full span)
+          if (lit && mode == plan::FAST && __any_sync(0xffffffffu, masked)) mode = plan::EDGE;
           const float mterm = masked ? a.neg : 0.f;
           const int ccls = (int)((w0 >> 8) & 0xffu);
           const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
           float gmul, gadd, gmax;
           if (mode == plan::FAST) {
             // every row of the warp masked here and already holding a real maximum: p == 0 exactly
-            if (mre && __all_sync(0xffffffffu, masked && m > -1e8f)) {
+            if (mre && skip_ok && __all_sync(0xffffffffu, masked && m > real_thr)) {
               dead_mask |= 1u << g;
               continue;
             }
@@ -687,16 +708,23 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             uint32_t v[32];
             tmem_ld32(t_s + 32 * g, v);
             tmem_wait_ld();
+            const int dcol = sc.col_base + key0 + 32 * g;
 #pragma unroll
             for (int x = 0; x < 16; x += 2) {
-              const float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
-              const float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
-              const float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, gsub));
-              const float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, gsub));
+              float p0 = ex2(fmaf(__uint_as_float(v[2 * x]), gmul, gsub));
+              float p1 = ex2(fmaf(__uint_as_float(v[2 * x + 1]), gmul, gsub));
+              float p2 = ex2(fmaf(__uint_as_float(v[2 * x + 2]), gmul, gsub));
+              float p3 = ex2(fmaf(__uint_as_float(v[2 * x + 3]), gmul, gsub));
               ls0 += p0;
               ls1 += p1;
               ls2 += p2;
               ls3 += p3;
+              if constexpr (DROP) {
+                p0 = dropout_keep(drow, dcol + 2 * x, dthr) ? p0 : 0.f;
+                p1 = dropout_keep(drow, dcol + 2 * x + 1, dthr) ? p1 : 0.f;
+                p2 = dropout_keep(drow, dcol + 2 * x + 2, dthr) ? p2 : 0.f;
+                p3 = dropout_keep(drow, dcol + 2 * x + 3, dthr) ? p3 : 0.f;
+              }
               pk[x] = pack_bf16x2(p0, p1);
               pk[x + 1] = pack_bf16x2(p2, p3);
             }
@@ -718,7 +746,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_wait_warp(&bars->o_full[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
       tc_fence_after_sync();
     }
-    const float inv = 1.f / l;
+    const float inv = (DROP ? a.drop.inv_keep : 1.f) / l;
     __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(a.out, b, i, h);
 #pragma unroll 1
     for (int hh = 0; hh < 2; ++hh) {
@@ -752,18 +780,23 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-bool t4_ok(const T4& t) {
-  return t.ptr && (t.sb % 8 == 0) && (t.sl % 8 == 0) && (t.sh % 8 == 0) &&
-         (reinterpret_cast<uintptr_t>(t.ptr) % 16 == 0);
-}
-
 }  // namespace
+
+// A [B, len, H, 64] bf16 view the TMA path can address: 16-byte base and strides; a zero (broadcast)
+// stride is only representable over an extent of 1 (tensor maps need non-zero strides), so broadcast
+// views over more than one element take the SIMT kernels, which handle them.
+bool tc_t4_ok(const T4& t, int B, int len, int H) {
+  if (!t.ptr || reinterpret_cast<uintptr_t>(t.ptr) % 16) return false;
+  if (t.sb % 8 || t.sl % 8 || t.sh % 8) return false;
+  if ((t.sb == 0 && B > 1) || (t.sl == 0 && len > 1) || (t.sh == 0 && H > 1)) return false;
+  return true;
+}
 
 bool tc_fwd_args_supported(const FwdArgs& a, int dtype, int d) {
   if (dtype != MLT_BF16 || d != 64 || a.rows.R > 64) return false;
-  if (!t4_ok(a.rows.q) || !t4_ok(a.out)) return false;
+  if (!tc_t4_ok(a.rows.q, a.B, a.rows.len, a.H) || !tc_t4_ok(a.out, a.B, a.rows.len, a.H)) return false;
   for (int s = 0; s < a.nseg; ++s)
-    if (!t4_ok(a.seg[s].k) || !t4_ok(a.seg[s].v)) return false;
+    if (!tc_t4_ok(a.seg[s].k, a.B, a.seg[s].len, a.H) || !tc_t4_ok(a.seg[s].v, a.B, a.seg[s].len, a.H)) return false;
   if (a.rows.R > 0 && reinterpret_cast<uintptr_t>(a.rows.emb) % 16) return false;
   return get_encode_tiled() != nullptr;
 }
@@ -775,16 +808,20 @@ extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace(unsig
 #endif
 
 int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
-  // experiment knob: extra dynamic shared memory forces one CTA per SM
-  static const int extra_smem = getenv("MLT_FWD_ONE_CTA") ? 100 * 1024 : 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC + extra_smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  // the shared-memory opt-in is a per-device function attribute: once per device, thread-safe
+  static PerDeviceOnce once;
+  const int ae = once.run([] {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kernel) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC);
+    };
+    set(tc_fwd_kernel<false, false>);
+    set(tc_fwd_kernel<true, false>);
+    set(tc_fwd_kernel<false, true>);
+    set(tc_fwd_kernel<true, true>);
+    return (int)e;
+  });
+  if (ae) return ae;
   TcFwdParams p;
   p.a = a;
   p.rpad = a.rows.R > 0 ? (a.rows.R + 15) / 16 * 16 : 0;
@@ -804,10 +841,13 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   }
   if (e) return MLT_ERR_UNSUPPORTED;
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
-  if (side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side)))
-    tc_fwd_kernel<true><<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
-  else
-    tc_fwd_kernel<false><<<grid, NTHREADS, SM_ALLOC + extra_smem, st>>>(mq, mk0, mv0, mk1, mv1, me, p);
+  const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
+  const bool dr = a.drop.thr != 0;
+  auto launch = [&](auto kernel) { kernel<<<grid, NTHREADS, SM_ALLOC, st>>>(mq, mk0, mv0, mk1, mv1, me, p); };
+  if (ex && dr) launch(tc_fwd_kernel<true, true>);
+  else if (ex) launch(tc_fwd_kernel<true, false>);
+  else if (dr) launch(tc_fwd_kernel<false, true>);
+  else launch(tc_fwd_kernel<false, false>);
   return (int)cudaGetLastError();
 }
 

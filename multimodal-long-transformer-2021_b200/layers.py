@@ -17,15 +17,17 @@ ops, unchanged -- exactly the split the north star prescribes.
   RelativeTransformerLayers    the stack the reference instantiates (dense attention)
   GlobalLocalTransformerLayers the long-input stack (global-local attention)
 
-Attention-probability dropout (``att_dropout_prob`` / ``attention_probs_dropout_prob``) is not
-implemented inside the fused kernels; in training mode with a non-zero rate a warning is
-emitted once and the probabilities are left un-dropped ("Out of scope").
+Attention-probability dropout (``att_dropout_prob`` / ``attention_probs_dropout_prob``, reference
+default 0.1, ``src/configs/encoders.py:87-88``) runs inside the fused kernels (``ops`` arguments
+``dropout_p`` / ``dropout_seed``).
+
+``training`` follows Keras: an explicit ``training=True/False`` applies to THIS call and to every
+nested layer (attention-probability dropout, hidden dropout, feed-forward dropout) without changing
+the module's own mode; ``training=None`` falls back to the module mode (``.train()`` / ``.eval()``).
 """
 
 from __future__ import annotations
 
-import math
-import warnings
 from typing import Optional
 
 import torch
@@ -35,15 +37,9 @@ import torch.nn.functional as F
 from . import ops
 from .feature_utils import CompactSideInputs
 
-_warned_dropout = False
-
-
-def _check_dropout(rate: float, training: bool):
-  global _warned_dropout
-  if training and rate > 0.0 and not _warned_dropout:
-    warnings.warn('attention-probability dropout is not applied by the fused attention kernels '
-                  '(att_dropout_prob is ignored); hidden dropout is unaffected.')
-    _warned_dropout = True
+def resolve_training(module: nn.Module, training) -> bool:
+  """Keras ``training`` argument: explicit value wins, ``None`` -> the module's mode."""
+  return module.training if training is None else bool(training)
 
 
 def _trunc_normal_(t: torch.Tensor, std: float):
@@ -115,13 +111,13 @@ class QkvRelativeAttention(_RelativeTables):
               compact: Optional[ops.DenseCompactSideInputs] = None):
     if relative_att_ids is not None and self.relative_vocab_size is None:
       raise ValueError('Cannot use `relative_att_ids` without specifying `relative_vocab_size`.')
-    _check_dropout(self.att_dropout_prob, bool(training))
+    rate = self.att_dropout_prob if resolve_training(self, training) else 0.0
     emb, bias = self.tables(queries.dtype)
     if relative_att_ids is None and compact is None:
       emb = bias = None
     return ops.dense_relative_attention(queries, keys, values, emb, bias, att_mask=att_mask,
                                         relative_att_ids=relative_att_ids, compact=compact,
-                                        impl=self.impl)
+                                        impl=self.impl, dropout_p=rate)
 
 
 class QkvRelativeLocalAttention(_RelativeTables):
@@ -149,7 +145,7 @@ class QkvRelativeLocalAttention(_RelativeTables):
       raise ValueError('`att_implementation` must be one of ["auto", "sparse", "full"].')
     if relative_att_ids is not None and self.relative_vocab_size is None:
       raise ValueError('Cannot use `relative_att_ids` without specifying `relative_vocab_size`.')
-    _check_dropout(self.att_dropout_prob, bool(training))
+    rate = self.att_dropout_prob if resolve_training(self, training) else 0.0
     emb, bias = self.tables(queries.dtype)
     if relative_att_ids is None and side_relative_att_ids is None and compact is None:
       emb = bias = None
@@ -157,7 +153,7 @@ class QkvRelativeLocalAttention(_RelativeTables):
         queries, keys, values, emb, bias, local_radius=self.local_radius, att_mask=att_mask,
         relative_att_ids=relative_att_ids, side_keys=side_keys, side_values=side_values,
         side_att_mask=side_att_mask, side_relative_att_ids=side_relative_att_ids, compact=compact,
-        impl=self.impl)
+        impl=self.impl, dropout_p=rate)
 
 
 class RelativeAttention(nn.Module):
@@ -255,7 +251,7 @@ class FusedGlobalLocalAttention(nn.Module):
               compact_side_inputs: Optional[CompactSideInputs] = None):
     if att_implementation not in ('auto', 'sparse', 'full'):
       raise ValueError('`att_implementation` must be one of ["auto", "sparse", "full"].')
-    _check_dropout(self.att_dropout_prob, bool(training))
+    rate = self.att_dropout_prob if resolve_training(self, training) else 0.0
     lq = self.long_query_projection(long_input)
     lk = self.long_key_projection(long_input)
     lv = self.long_value_projection(long_input)
@@ -277,7 +273,8 @@ class FusedGlobalLocalAttention(nn.Module):
     lemb, lbias = self.long_tables.tables(lq.dtype) if use_rel else (None, None)
     gemb, gbias = self.global_tables.tables(lq.dtype) if use_rel else (None, None)
     lo, go = ops.global_local_attention(lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbias,
-                                        local_radius=self.local_radius, side=side, impl=self.impl)
+                                        local_radius=self.local_radius, side=side, impl=self.impl,
+                                        dropout_p=rate)
     long_output = self.long_output_projection(lo.reshape(*lo.shape[:2], -1))
     global_output = self.global_output_projection(go.reshape(*go.shape[:2], -1))
     return [long_output, global_output]
@@ -293,10 +290,11 @@ class _ResidualFeedForward(nn.Module):
       _trunc_normal_(lin.weight, initializer_range)
       nn.init.zeros_(lin.bias)
     self.act = hidden_act
-    self.dropout = nn.Dropout(hidden_dropout_prob)
+    self.hidden_dropout_prob = hidden_dropout_prob
 
-  def forward(self, x):
-    return self.dropout(self.outer(self.act(self.inner(x))))
+  def forward(self, x, training=None):
+    return F.dropout(self.outer(self.act(self.inner(x))), self.hidden_dropout_prob,
+                     resolve_training(self, training))
 
 
 class RelativeTransformerLayers(nn.Module):
@@ -326,23 +324,23 @@ class RelativeTransformerLayers(nn.Module):
                              initializer_range) for _ in range(num_hidden_layers)])
     self.attention_norms = nn.ModuleList([nn.LayerNorm(hidden_size, eps=1e-12) for _ in range(num_hidden_layers)])
     self.feed_forward_norms = nn.ModuleList([nn.LayerNorm(hidden_size, eps=1e-12) for _ in range(num_hidden_layers)])
-    self.attention_dropout = nn.Dropout(hidden_dropout_prob)
+    self.hidden_dropout_prob = hidden_dropout_prob
     self.output_layer_norm = nn.LayerNorm(hidden_size, eps=1e-12) if use_pre_activation_order else None
 
   def forward(self, inputs, att_mask=None, relative_att_ids=None, training=None, compact=None):
-    if training is not None:
-      self.train(bool(training))
+    tr = resolve_training(self, training)   # applies to this call only; the module mode is untouched
+    drop = lambda t: F.dropout(t, self.hidden_dropout_prob, tr)
     x = inputs
     for att, ffn, n1, n2 in zip(self.attention_layers, self.feed_forward_layers,
                                 self.attention_norms, self.feed_forward_norms):
       if self.use_pre_activation_order:
-        x = x + self.attention_dropout(att(n1(x), att_mask=att_mask, relative_att_ids=relative_att_ids,
-                                           training=self.training, compact=compact))
-        x = x + ffn(n2(x))
+        x = x + drop(att(n1(x), att_mask=att_mask, relative_att_ids=relative_att_ids,
+                         training=tr, compact=compact))
+        x = x + ffn(n2(x), training=tr)
       else:
-        x = n1(x + self.attention_dropout(att(x, att_mask=att_mask, relative_att_ids=relative_att_ids,
-                                              training=self.training, compact=compact)))
-        x = n2(x + ffn(x))
+        x = n1(x + drop(att(x, att_mask=att_mask, relative_att_ids=relative_att_ids,
+                            training=tr, compact=compact)))
+        x = n2(x + ffn(x, training=tr))
     if self.output_layer_norm is not None:
       x = self.output_layer_norm(x)
     return x
@@ -387,7 +385,7 @@ class GlobalLocalTransformerLayers(nn.Module):
     ln = lambda size: nn.ModuleList([nn.LayerNorm(size, eps=1e-12) for _ in range(n)])
     self.long_att_norms, self.global_att_norms = ln(long_hidden_size), ln(global_hidden_size)
     self.long_ffn_norms, self.global_ffn_norms = ln(long_hidden_size), ln(global_hidden_size)
-    self.dropout = nn.Dropout(hidden_dropout_prob)
+    self.hidden_dropout_prob = hidden_dropout_prob
     self.long_output_norm = nn.LayerNorm(long_hidden_size, eps=1e-12) if use_pre_activation_order else None
     self.global_output_norm = nn.LayerNorm(global_hidden_size, eps=1e-12) if use_pre_activation_order else None
 
@@ -395,25 +393,27 @@ class GlobalLocalTransformerLayers(nn.Module):
               g2l_att_mask=None, l2l_relative_att_ids=None, g2g_relative_att_ids=None,
               l2g_relative_att_ids=None, g2l_relative_att_ids=None, att_implementation='auto',
               training=None, compact_side_inputs: Optional[CompactSideInputs] = None):
-    if training is not None:
-      self.train(bool(training))
+    tr = resolve_training(self, training)   # applies to this call only; the module mode is untouched
+    drop = lambda t: F.dropout(t, self.hidden_dropout_prob, tr)
     xl, xg = long_input, global_input
     side = dict(l2l_att_mask=l2l_att_mask, g2g_att_mask=g2g_att_mask, l2g_att_mask=l2g_att_mask,
                 g2l_att_mask=g2l_att_mask, l2l_relative_att_ids=l2l_relative_att_ids,
                 g2g_relative_att_ids=g2g_relative_att_ids, l2g_relative_att_ids=l2g_relative_att_ids,
                 g2l_relative_att_ids=g2l_relative_att_ids, att_implementation=att_implementation,
-                training=self.training, compact_side_inputs=compact_side_inputs)
+                training=tr, compact_side_inputs=compact_side_inputs)
     for idx, att in enumerate(self.fused_att_layers):
       n_la, n_ga = self.long_att_norms[idx], self.global_att_norms[idx]
       n_lf, n_gf = self.long_ffn_norms[idx], self.global_ffn_norms[idx]
       if self.use_pre_activation_order:
         al, ag = att(n_la(xl), n_ga(xg), **side)
-        xl, xg = xl + self.dropout(al), xg + self.dropout(ag)
-        xl, xg = xl + self.long_ffn[idx](n_lf(xl)), xg + self.global_ffn[idx](n_gf(xg))
+        xl, xg = xl + drop(al), xg + drop(ag)
+        xl = xl + self.long_ffn[idx](n_lf(xl), training=tr)
+        xg = xg + self.global_ffn[idx](n_gf(xg), training=tr)
       else:
         al, ag = att(xl, xg, **side)
-        xl, xg = n_la(xl + self.dropout(al)), n_ga(xg + self.dropout(ag))
-        xl, xg = n_lf(xl + self.long_ffn[idx](xl)), n_gf(xg + self.global_ffn[idx](xg))
+        xl, xg = n_la(xl + drop(al)), n_ga(xg + drop(ag))
+        xl = n_lf(xl + self.long_ffn[idx](xl, training=tr))
+        xg = n_gf(xg + self.global_ffn[idx](xg, training=tr))
     if self.long_output_norm is not None:
       xl, xg = self.long_output_norm(xl), self.global_output_norm(xg)
     return [xl, xg]

@@ -75,7 +75,7 @@ class MmtEncoder(nn.Module):
     layers._trunc_normal_(self.patch_embedding_projection.weight, initializer_range)
     nn.init.zeros_(self.patch_embedding_projection.bias)
     self.embedding_norm = nn.LayerNorm(hidden_size, eps=1e-12)
-    self.embedding_dropout = nn.Dropout(hidden_dropout_prob)
+    self.hidden_dropout_prob = hidden_dropout_prob
     self.local_radius = local_radius
     self.num_global_tokens = num_global_tokens
     common = dict(hidden_act=inner_activation, hidden_dropout_prob=hidden_dropout_prob,
@@ -103,11 +103,12 @@ class MmtEncoder(nn.Module):
       layers._trunc_normal_(self.pooler.weight, initializer_range)
       nn.init.zeros_(self.pooler.bias)
 
-  def embed(self, word_ids, segment_ids=None, patch_embeddings=None):
+  def embed(self, word_ids, segment_ids=None, patch_embeddings=None, training=None):
     """Reference mmt_encoder.py:189-218."""
     if segment_ids is None:
       segment_ids = torch.ones_like(word_ids)
-    word = self.embedding_dropout(self.embedding_norm(self.word_embeddings(word_ids)))
+    word = torch.nn.functional.dropout(self.embedding_norm(self.word_embeddings(word_ids)),
+                                       self.hidden_dropout_prob, layers.resolve_training(self, training))
     emb = word + self.segment_embeddings(segment_ids)
     if self.position_embeddings is not None:
       emb = emb + self.position_embeddings[:emb.shape[1]].unsqueeze(0)
@@ -121,18 +122,19 @@ class MmtEncoder(nn.Module):
 
   def forward(self, word_ids, segment_ids=None, att_mask=None, relative_att_ids=None,
               patch_embeddings=None, training=None, compact=None, compact_side_inputs=None):
-    if training is not None:
-      self.train(bool(training))
-    emb = self.embed(word_ids, segment_ids, patch_embeddings)
+    # Keras semantics: `training` applies to this call and every nested layer; the module mode is
+    # only the default when it is None (reference passes training=True at src/tasks/pretraining.py:279)
+    tr = layers.resolve_training(self, training)
+    emb = self.embed(word_ids, segment_ids, patch_embeddings, training=tr)
     if self.local_radius is None:
       out = self.transformer_layers(emb, att_mask=att_mask, relative_att_ids=relative_att_ids,
-                                    training=self.training, compact=compact)
+                                    training=tr, compact=compact)
       global_out = None
     else:
       if compact_side_inputs is None:
         raise ValueError('the long-input stack needs `compact_side_inputs`.')
       glob = self.global_embeddings.to(emb.dtype).expand(emb.shape[0], self.num_global_tokens, -1)
-      out, global_out = self.transformer_layers(emb, glob, training=self.training,
+      out, global_out = self.transformer_layers(emb, glob, training=tr,
                                                 compact_side_inputs=compact_side_inputs)
     outputs = {'sequence_output': out}
     if global_out is not None:

@@ -67,8 +67,36 @@ def _int32(t: Optional[torch.Tensor], shape, name: str) -> Optional[torch.Tensor
   return t.to(torch.int32).contiguous()
 
 
-def _stream() -> int:
-  return torch.cuda.current_stream().cuda_stream
+def _stream(device) -> int:
+  return torch.cuda.current_stream(device).cuda_stream
+
+
+def _same_device(*tensors):
+  """All CUDA tensors of one call must live on one device; returns it."""
+  dev = None
+  for t in tensors:
+    if t is None:
+      continue
+    if not t.is_cuda:
+      raise _lib.MltLibraryError('tensors must live on a CUDA device: there is no CPU path')
+    if dev is None:
+      dev = t.device
+    elif t.device != dev:
+      raise ValueError(f'all tensors of one call must share a device, got {dev} and {t.device}')
+  return dev
+
+
+def _dropout_args(dropout_p: float, dropout_seed: Optional[int]):
+  """Validated (p, seed).  A missing seed is drawn from torch's CPU generator (reproducible under
+  ``torch.manual_seed``); the same seed is replayed by the backward pass."""
+  p = float(dropout_p)
+  if not 0.0 <= p < 1.0:
+    raise ValueError(f'dropout_p must lie in [0, 1), got {p}')
+  if p == 0.0:
+    return 0.0, 0
+  if dropout_seed is None:
+    dropout_seed = int(torch.randint(0, 2**62, (1,)).item())
+  return p, int(dropout_seed) & (2**64 - 1)
 
 
 def _tables(emb, bias, h, d, dtype, name):
@@ -90,10 +118,13 @@ def _tables(emb, bias, h, d, dtype, name):
 class _GlCfg:
   """Non-tensor arguments of one global-local call."""
 
-  def __init__(self, local_radius, side, impl):
+  def __init__(self, local_radius, side, impl, dropout_p=0.0, dropout_seed=0, neg=NEG):
     self.local_radius = local_radius
     self.side = side
     self.impl = impl
+    self.dropout_p = dropout_p
+    self.dropout_seed = dropout_seed
+    self.neg = neg
 
 
 def _fill_gl_params(p: GlParams, lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbias, r_vocab,
@@ -106,9 +137,9 @@ def _fill_gl_params(p: GlParams, lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbia
   p.B, p.L, p.G, p.H, p.d, p.R = b, l, g, h, d, r_vocab
   p.local_radius = cfg.local_radius
   p.scale = 1.0 / math.sqrt(d)
-  p.neg = NEG
-  p.dropout_p = 0.0
-  p.dropout_seed = 0
+  p.neg = cfg.neg
+  p.dropout_p = cfg.dropout_p
+  p.dropout_seed = cfg.dropout_seed
   p.long_q, p.long_k, p.long_v = _t4(lq), _t4(lk), _t4(lv)
   p.global_q, p.global_k, p.global_v = _t4(gq), _t4(gk), _t4(gv)
   p.long_tables = RelTables(_ptr(lemb), _ptr(lbias))
@@ -138,10 +169,12 @@ class _GlobalLocalAttnFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbias, cfg):
     lib = _lib.load()
+    dev = _same_device(lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbias)
     lq, lk, lv, gq, gk, gv = map(_prep, (lq, lk, lv, gq, gk, gv))
     b, l, h, d = lq.shape
     g = gq.shape[1]
     dt = lq.dtype
+    ctx.table_dtypes = [None if t is None else t.dtype for t in (lemb, lbias, gemb, gbias)]
     lemb, lbias, r1 = _tables(lemb, lbias, h, d, dt, 'long tables')
     gemb, gbias, r2 = _tables(gemb, gbias, h, d, dt, 'global tables')
     if r1 != r2:
@@ -158,7 +191,8 @@ class _GlobalLocalAttnFn(torch.autograd.Function):
     nbytes = lib.mlt_gl_workspace_bytes(C.byref(p), 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=lq.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
-    _lib.check(lib.mlt_gl_attn_fwd(C.byref(p), _stream()), 'mlt_gl_attn_fwd')
+    with torch.cuda.device(dev):
+      _lib.check(lib.mlt_gl_attn_fwd(C.byref(p), _stream(dev)), 'mlt_gl_attn_fwd')
     ctx.cfg = cfg
     ctx.r_vocab = r1
     ctx.save_for_backward(lq, lk, lv, gq, gk, gv, lemb, lbias, gemb, gbias, long_out,
@@ -194,15 +228,18 @@ class _GlobalLocalAttnFn(torch.autograd.Function):
              torch.empty((r_vocab, h, d), **f32), torch.empty((r_vocab, h), **f32)]
       gr.d_long_emb, gr.d_long_bias, gr.d_global_emb, gr.d_global_bias = (
           t.data_ptr() for t in tab)
-    _lib.check(lib.mlt_gl_attn_bwd(C.byref(p), C.byref(gr), _stream()), 'mlt_gl_attn_bwd')
-    if r_vocab > 0:
-      tab = [t.to(lq.dtype) for t in tab]
+    with torch.cuda.device(lq.device):
+      _lib.check(lib.mlt_gl_attn_bwd(C.byref(p), C.byref(gr), _stream(lq.device)), 'mlt_gl_attn_bwd')
+    if r_vocab > 0:   # table gradients are accumulated in fp32; hand them back in the tables' own dtype
+      tab = [t.to(dt) for t, dt in zip(tab, ctx.table_dtypes)]
     return (*grads, *tab, None)
 
 
 def global_local_attention(long_q, long_k, long_v, global_q, global_k, global_v,
                            long_emb=None, long_bias=None, global_emb=None, global_bias=None,
-                           *, local_radius: int, side=None, impl: str = 'auto'):
+                           *, local_radius: int, side=None, impl: str = 'auto',
+                           dropout_p: float = 0.0, dropout_seed: Optional[int] = None,
+                           neg: float = NEG):
   """Core of ``FusedGlobalLocalAttention.call`` [UPSTREAM-RECALLED].
 
   Args:
@@ -214,13 +251,18 @@ def global_local_attention(long_q, long_k, long_v, global_q, global_k, global_v,
       ``g2l_relative_att_ids``; missing mask = all ones, missing ids = no relative term)
       or a ``CompactSideInputs`` (masks / ids rebuilt inside the kernels).
     impl: ``'auto' | 'simt' | 'tc'``.
+    dropout_p / dropout_seed: attention-probability dropout (reference default 0.1 in training,
+      ``src/configs/encoders.py:87-88``), applied to the softmax output inside the kernels; the keep
+      mask is a counter-based hash of (seed, batch, head, row, key), regenerated in the backward.
+    neg: the additive mask constant (ABI field ``neg``).
 
   Returns ``(long_out [B,L,H,d], global_out [B,G,H,d])``; differentiable w.r.t. the six
   q/k/v tensors and the four tables.
   """
   if local_radius < 1:
     raise ValueError('`local_radius` must be positive.')
-  cfg = _GlCfg(local_radius, side, impl)
+  dropout_p, dropout_seed = _dropout_args(dropout_p, dropout_seed)
+  cfg = _GlCfg(local_radius, side, impl, dropout_p, dropout_seed, neg)
   return _GlobalLocalAttnFn.apply(long_q, long_k, long_v, global_q, global_k, global_v,
                                   long_emb, long_bias, global_emb, global_bias, cfg)
 
@@ -247,11 +289,14 @@ class DenseCompactSideInputs:
 
 class _DenseCfg:
 
-  def __init__(self, att_mask, relative_att_ids, compact, impl):
+  def __init__(self, att_mask, relative_att_ids, compact, impl, dropout_p=0.0, dropout_seed=0, neg=NEG):
     self.att_mask = att_mask
     self.relative_att_ids = relative_att_ids
     self.compact = compact
     self.impl = impl
+    self.dropout_p = dropout_p
+    self.dropout_seed = dropout_seed
+    self.neg = neg
 
 
 def _fill_dense_params(p: DenseParams, q, k, v, emb, bias, r_vocab, cfg: _DenseCfg, keep):
@@ -262,8 +307,9 @@ def _fill_dense_params(p: DenseParams, q, k, v, emb, bias, r_vocab, cfg: _DenseC
   p.impl = _lib.IMPL[cfg.impl]
   p.B, p.Lq, p.Lk, p.H, p.d, p.R = b, lq, lk, h, d, r_vocab
   p.scale = 1.0 / math.sqrt(d)
-  p.neg = NEG
-  p.dropout_p = 0.0
+  p.neg = cfg.neg
+  p.dropout_p = cfg.dropout_p
+  p.dropout_seed = cfg.dropout_seed
   p.q, p.k, p.v = _t4(q), _t4(k), _t4(v)
   p.tables = RelTables(_ptr(emb), _ptr(bias))
   if cfg.compact is not None:
@@ -287,8 +333,10 @@ class _DenseRelAttnFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, q, k, v, emb, bias, cfg):
     lib = _lib.load()
+    dev = _same_device(q, k, v, emb, bias)
     q, k, v = map(_prep, (q, k, v))
     b, lq, h, d = q.shape
+    ctx.table_dtypes = [None if t is None else t.dtype for t in (emb, bias)]
     emb, bias, r_vocab = _tables(emb, bias, h, d, q.dtype, 'tables')
     out = torch.empty((b, lq, h, d), dtype=q.dtype, device=q.device)
     stats = torch.empty((b, h, lq, 2), dtype=torch.float32, device=q.device)
@@ -299,7 +347,8 @@ class _DenseRelAttnFn(torch.autograd.Function):
     nbytes = lib.mlt_dense_workspace_bytes(C.byref(p), 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
-    _lib.check(lib.mlt_dense_rel_attn_fwd(C.byref(p), _stream()), 'mlt_dense_rel_attn_fwd')
+    with torch.cuda.device(dev):
+      _lib.check(lib.mlt_dense_rel_attn_fwd(C.byref(p), _stream(dev)), 'mlt_dense_rel_attn_fwd')
     ctx.cfg, ctx.r_vocab = cfg, r_vocab
     ctx.save_for_backward(q, k, v, emb, bias, out, stats)
     return out
@@ -326,23 +375,26 @@ class _DenseRelAttnFn(torch.autograd.Function):
       d_emb = torch.empty((r_vocab, h, d), dtype=torch.float32, device=q.device)
       d_bias = torch.empty((r_vocab, h), dtype=torch.float32, device=q.device)
       gr.d_emb, gr.d_bias = d_emb.data_ptr(), d_bias.data_ptr()
-    _lib.check(lib.mlt_dense_rel_attn_bwd(C.byref(p), C.byref(gr), _stream()),
-               'mlt_dense_rel_attn_bwd')
+    with torch.cuda.device(q.device):
+      _lib.check(lib.mlt_dense_rel_attn_bwd(C.byref(p), C.byref(gr), _stream(q.device)),
+                 'mlt_dense_rel_attn_bwd')
     if r_vocab > 0:
-      d_emb, d_bias = d_emb.to(q.dtype), d_bias.to(q.dtype)
+      d_emb, d_bias = d_emb.to(ctx.table_dtypes[0]), d_bias.to(ctx.table_dtypes[1])
     return dq, dk, dv, d_emb, d_bias, None
 
 
 def dense_relative_attention(q, k, v, emb=None, bias=None, att_mask=None,
                              relative_att_ids=None, compact: Optional[DenseCompactSideInputs] = None,
-                             impl: str = 'auto'):
+                             impl: str = 'auto', dropout_p: float = 0.0,
+                             dropout_seed: Optional[int] = None, neg: float = NEG):
   """``QkvRelativeAttention.call`` core [UPSTREAM-RECALLED].
 
   ``q [B,Lq,H,d]``, ``k/v [B,Lk,H,d]``; ``att_mask`` / ``relative_att_ids`` int32
   ``[B,Lq,Lk]`` exactly as the reference feeds them
   (``src/modeling/models/mmt_encoder.py:220-224``), or ``compact`` descriptors.
   """
-  cfg = _DenseCfg(att_mask, relative_att_ids, compact, impl)
+  dropout_p, dropout_seed = _dropout_args(dropout_p, dropout_seed)
+  cfg = _DenseCfg(att_mask, relative_att_ids, compact, impl, dropout_p, dropout_seed, neg)
   return _DenseRelAttnFn.apply(q, k, v, emb, bias, cfg)
 
 
@@ -363,7 +415,10 @@ class LocalCompactSideInputs:
 class _LocalCfg:
 
   def __init__(self, local_radius, att_mask, relative_att_ids, side_att_mask,
-               side_relative_att_ids, compact, impl):
+               side_relative_att_ids, compact, impl, dropout_p=0.0, dropout_seed=0, neg=NEG):
+    self.dropout_p = dropout_p
+    self.dropout_seed = dropout_seed
+    self.neg = neg
     self.local_radius = local_radius
     self.att_mask = att_mask
     self.relative_att_ids = relative_att_ids
@@ -382,8 +437,9 @@ def _fill_local_params(p: LocalParams, q, k, v, sk, sv, emb, bias, r_vocab, cfg:
   p.B, p.L, p.G, p.H, p.d, p.R = b, l, g, h, d, r_vocab
   p.local_radius = cfg.local_radius
   p.scale = 1.0 / math.sqrt(d)
-  p.neg = NEG
-  p.dropout_p = 0.0
+  p.neg = cfg.neg
+  p.dropout_p = cfg.dropout_p
+  p.dropout_seed = cfg.dropout_seed
   p.q, p.k, p.v = _t4(q), _t4(k), _t4(v)
   if g:
     p.side_k, p.side_v = _t4(sk), _t4(sv)
@@ -414,10 +470,12 @@ class _LocalRelAttnFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, q, k, v, sk, sv, emb, bias, cfg):
     lib = _lib.load()
+    dev = _same_device(q, k, v, sk, sv, emb, bias)
     q, k, v = map(_prep, (q, k, v))
     if sk is not None:
       sk, sv = _prep(sk), _prep(sv)
     b, l, h, d = q.shape
+    ctx.table_dtypes = [None if t is None else t.dtype for t in (emb, bias)]
     emb, bias, r_vocab = _tables(emb, bias, h, d, q.dtype, 'tables')
     out = torch.empty((b, l, h, d), dtype=q.dtype, device=q.device)
     stats = torch.empty((b, h, l, 2), dtype=torch.float32, device=q.device)
@@ -428,7 +486,8 @@ class _LocalRelAttnFn(torch.autograd.Function):
     nbytes = lib.mlt_local_workspace_bytes(C.byref(p), 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
-    _lib.check(lib.mlt_local_rel_attn_fwd(C.byref(p), _stream()), 'mlt_local_rel_attn_fwd')
+    with torch.cuda.device(dev):
+      _lib.check(lib.mlt_local_rel_attn_fwd(C.byref(p), _stream(dev)), 'mlt_local_rel_attn_fwd')
     ctx.cfg, ctx.r_vocab = cfg, r_vocab
     ctx.save_for_backward(q, k, v, sk, sv, emb, bias, out, stats)
     return out
@@ -459,17 +518,20 @@ class _LocalRelAttnFn(torch.autograd.Function):
       d_emb = torch.empty((r_vocab, h, d), dtype=torch.float32, device=q.device)
       d_bias = torch.empty((r_vocab, h), dtype=torch.float32, device=q.device)
       gr.d_emb, gr.d_bias = d_emb.data_ptr(), d_bias.data_ptr()
-    _lib.check(lib.mlt_local_rel_attn_bwd(C.byref(p), C.byref(gr), _stream()),
-               'mlt_local_rel_attn_bwd')
+    with torch.cuda.device(q.device):
+      _lib.check(lib.mlt_local_rel_attn_bwd(C.byref(p), C.byref(gr), _stream(q.device)),
+                 'mlt_local_rel_attn_bwd')
     if r_vocab > 0:
-      d_emb, d_bias = d_emb.to(q.dtype), d_bias.to(q.dtype)
+      d_emb, d_bias = d_emb.to(ctx.table_dtypes[0]), d_bias.to(ctx.table_dtypes[1])
     return dq, dk, dv, dsk, dsv, d_emb, d_bias, None
 
 
 def local_relative_attention(q, k, v, emb=None, bias=None, *, local_radius: int, att_mask=None,
                              relative_att_ids=None, side_keys=None, side_values=None,
                              side_att_mask=None, side_relative_att_ids=None,
-                             compact: Optional[LocalCompactSideInputs] = None, impl: str = 'auto'):
+                             compact: Optional[LocalCompactSideInputs] = None, impl: str = 'auto',
+                             dropout_p: float = 0.0, dropout_seed: Optional[int] = None,
+                             neg: float = NEG):
   """``QkvRelativeLocalAttention.call`` core [UPSTREAM-RECALLED].
 
   ``q/k/v [B,L,H,d]``; window masks / ids ``[B,L,2r+1]`` (column k <-> key ``i+k-r``);
@@ -480,8 +542,9 @@ def local_relative_attention(q, k, v, emb=None, bias=None, *, local_radius: int,
     raise ValueError('`local_radius` must be positive.')
   if (side_keys is None) != (side_values is None):
     raise ValueError('`side_keys` and `side_values` go together.')
+  dropout_p, dropout_seed = _dropout_args(dropout_p, dropout_seed)
   cfg = _LocalCfg(local_radius, att_mask, relative_att_ids, side_att_mask, side_relative_att_ids,
-                  compact, impl)
+                  compact, impl, dropout_p, dropout_seed, neg)
   return _LocalRelAttnFn.apply(q, k, v, side_keys, side_values, emb, bias, cfg)
 
 
@@ -499,8 +562,9 @@ def build_dense_side_inputs(example_ids: torch.Tensor, max_distance: int,
   mask = torch.empty((b, s, s), dtype=torch.int32, device=e.device) if want_mask else None
   ids = torch.empty((b, s, s), dtype=torch.int32, device=e.device) if want_ids else None
   layout = IdLayout(num_patch_per_row, num_core_layers, max_distance)
-  _lib.check(lib.mlt_build_dense_side_inputs(e.data_ptr(), b, s, layout, _ptr(mask), _ptr(ids),
-                                             _stream()), 'mlt_build_dense_side_inputs')
+  with torch.cuda.device(e.device):
+    _lib.check(lib.mlt_build_dense_side_inputs(e.data_ptr(), b, s, layout, _ptr(mask), _ptr(ids),
+                                               _stream(e.device)), 'mlt_build_dense_side_inputs')
   return mask, ids
 
 
@@ -517,7 +581,8 @@ def build_gl_side_inputs(compact: CompactSideInputs, local_radius: int):
   out = {k: torch.empty(shapes[k[:3]], dtype=torch.int32, device=le.device)
          for k in _GL_SIDE_KEYS}
   arr = (C.c_void_p * 8)(*[out[k].data_ptr() for k in _GL_SIDE_KEYS])
-  _lib.check(lib.mlt_build_gl_side_inputs(le.data_ptr(), ge.data_ptr(), sid.data_ptr(), b, l, g,
-                                          local_radius, compact.relative_pos_max_distance,
-                                          C.byref(arr), _stream()), 'mlt_build_gl_side_inputs')
+  with torch.cuda.device(le.device):
+    _lib.check(lib.mlt_build_gl_side_inputs(le.data_ptr(), ge.data_ptr(), sid.data_ptr(), b, l, g,
+                                            local_radius, compact.relative_pos_max_distance,
+                                            C.byref(arr), _stream(le.device)), 'mlt_build_gl_side_inputs')
   return out

@@ -70,7 +70,9 @@ class MaskedPP(nn.Module):
   def __init__(self, hidden_size: int, output_num_classes: int, activation=None):
     super().__init__()
     self.layer_norm = nn.LayerNorm(hidden_size, eps=1e-12)
-    self.dense = nn.Linear(hidden_size, output_num_classes, bias=False)
+    # Keras Dense keeps its own bias; `output_bias` is added on top (reference :62-72, :95-97)
+    self.dense = nn.Linear(hidden_size, output_num_classes, bias=True)
+    nn.init.zeros_(self.dense.bias)
     self.act = activation
     self.bias = nn.Parameter(torch.zeros(output_num_classes))
 
@@ -89,11 +91,12 @@ class ClassificationHead(nn.Module):
     super().__init__()
     self.name = name
     self.dense = nn.Linear(hidden_size, hidden_size)
-    self.dropout = nn.Dropout(dropout_rate)
+    self.dropout_rate = dropout_rate
     self.out_proj = nn.Linear(hidden_size, num_classes)
 
-  def forward(self, sequence_output):
-    return self.out_proj(self.dropout(torch.tanh(self.dense(sequence_output[:, 0]))))
+  def forward(self, sequence_output, training=None):
+    x = torch.tanh(self.dense(sequence_output[:, 0]))
+    return self.out_proj(F.dropout(x, self.dropout_rate, layers.resolve_training(self, training)))
 
 
 class MmtPretrainingModel(nn.Module):
@@ -121,7 +124,7 @@ class MmtPretrainingModel(nn.Module):
     if mpp_positions is not None:
       outputs['mpp_logits'] = self.masked_pp(seq, mpp_positions)
     for head in self.classification_heads:
-      outputs[f'{head.name}_logits'] = head(seq)
+      outputs[f'{head.name}_logits'] = head(seq, training=training)   # Keras hands `training` to every layer
     return outputs
 
 

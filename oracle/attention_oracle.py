@@ -54,8 +54,19 @@ def _lookup(allrel, ids):
   return gathered * valid.unsqueeze(-1).to(allrel.dtype)
 
 
-def relative_scores(q, k, att_mask, relative_att_ids, emb, bias, candidate=None):
+def _dropout(p, keep, rate):
+  """Attention-probability dropout AFTER the softmax (``training=True``, reference
+  ``src/configs/encoders.py:87-88``, ``src/tasks/pretraining.py:279``): ``keep`` is a boolean
+  ``[B,Lq,Lk,H]`` mask supplied by the test (the kernels' counter-based mask restated in
+  ``tests/dropout_ref.py``), kept entries are scaled by ``1 / (1 - rate)``."""
+  if keep is None:
+    return p
+  return p * keep.to(p.dtype) / (1.0 - rate)
+
+
+def relative_scores(q, k, att_mask, relative_att_ids, emb, bias, candidate=None, neg=None):
   """Masked, scaled score tensor [B,Lq,Lk,H] (before softmax)."""
+  neg = NEG if neg is None else neg
   d = q.shape[-1]
   s = torch.einsum('bqhd,bkhd->bqkh', q, k)
   if relative_att_ids is not None:
@@ -64,17 +75,18 @@ def relative_scores(q, k, att_mask, relative_att_ids, emb, bias, candidate=None)
   if att_mask is not None:
     # The reference adds NEG in fp32, where |x| < 32 is absorbed (ulp(1e9) = 64):
     # a fully-masked row is then *uniform*.  Reproduce that rounding in fp64.
-    masked = (s.to(torch.float32) + NEG).to(s.dtype)
+    masked = (s.to(torch.float32) + neg).to(s.dtype)
     s = torch.where(att_mask.bool().unsqueeze(-1), s, masked)
   if candidate is not None:
     s = s.masked_fill(~candidate.unsqueeze(-1), float('-inf'))
   return s
 
 
-def qkv_relative_attention(q, k, v, att_mask, relative_att_ids, emb, bias):
+def qkv_relative_attention(q, k, v, att_mask, relative_att_ids, emb, bias, neg=None, keep=None,
+                           rate=0.0):
   """Contract (A): QkvRelativeAttention.call [UPSTREAM-RECALLED] (row a2)."""
-  s = relative_scores(q, k, att_mask, relative_att_ids, emb, bias)
-  p = torch.softmax(s, dim=2)
+  s = relative_scores(q, k, att_mask, relative_att_ids, emb, bias, neg=neg)
+  p = _dropout(torch.softmax(s, dim=2), keep, rate)
   return torch.einsum('bqkh,bkhd->bqhd', p, v)
 
 
@@ -100,7 +112,8 @@ def band_candidates(l, r):
 
 def qkv_relative_local_attention(q, k, v, att_mask, relative_att_ids, emb, bias,
                                  local_radius, side_k=None, side_v=None,
-                                 side_att_mask=None, side_relative_att_ids=None):
+                                 side_att_mask=None, side_relative_att_ids=None, neg=None,
+                                 keep=None, rate=0.0):
   """Long rows of contract (B): QkvRelativeLocalAttention.call (row a3).
 
   Dense-with-band formulation ("full" att_implementation [UPSTREAM-RECALLED]).
@@ -110,19 +123,19 @@ def qkv_relative_local_attention(q, k, v, att_mask, relative_att_ids, emb, bias,
   cand = band_candidates(l, local_radius).unsqueeze(0).expand(b, l, l)
   mask_d = None if att_mask is None else band_to_dense(att_mask, 0)
   ids_d = None if relative_att_ids is None else band_to_dense(relative_att_ids, -1)
-  s = relative_scores(q, k, mask_d, ids_d, emb, bias, candidate=cand)
+  s = relative_scores(q, k, mask_d, ids_d, emb, bias, candidate=cand, neg=neg)
   vv = v
   if side_k is not None:
     s_side = relative_scores(q, side_k, side_att_mask, side_relative_att_ids,
-                             emb, bias)
+                             emb, bias, neg=neg)
     s = torch.cat([s, s_side], dim=2)
     vv = torch.cat([v, side_v], dim=1)
-  p = torch.softmax(s, dim=2)
+  p = _dropout(torch.softmax(s, dim=2), keep, rate)   # keep: [B, L, L + G, H]
   return torch.einsum('bqkh,bkhd->bqhd', p, vv)
 
 
 def global_rows_attention(gq, gk, gv, lk, lv, g2g_mask, g2g_ids, g2l_mask,
-                          g2l_ids, emb, bias):
+                          g2l_ids, emb, bias, neg=None, keep=None, rate=0.0):
   """Global rows of contract (B): keys = all global (+) all long, one softmax."""
   k = torch.cat([gk, lk], dim=1)
   v = torch.cat([gv, lv], dim=1)
@@ -132,11 +145,12 @@ def global_rows_attention(gq, gk, gv, lk, lv, g2g_mask, g2g_ids, g2l_mask,
   ids = None
   if g2g_ids is not None:
     ids = torch.cat([g2g_ids, g2l_ids], dim=2)
-  return qkv_relative_attention(gq, k, v, mask, ids, emb, bias)
+  return qkv_relative_attention(gq, k, v, mask, ids, emb, bias, neg=neg, keep=keep, rate=rate)
 
 
 def fused_global_local_attention(lq, lk, lv, gq, gk, gv, side, long_tables,
-                                 global_tables, local_radius):
+                                 global_tables, local_radius, neg=None, keep_long=None,
+                                 keep_global=None, rate=0.0):
   """Core of FusedGlobalLocalAttention.call (row a4), projections excluded.
 
   ``side`` is a dict with the eight l2l/l2g/g2g/g2l mask/id tensors; ``*_tables``
@@ -146,9 +160,10 @@ def fused_global_local_attention(lq, lk, lv, gq, gk, gv, side, long_tables,
       lq, lk, lv, side.get('l2l_att_mask'), side.get('l2l_relative_att_ids'),
       long_tables[0], long_tables[1], local_radius, side_k=gk, side_v=gv,
       side_att_mask=side.get('l2g_att_mask'),
-      side_relative_att_ids=side.get('l2g_relative_att_ids'))
+      side_relative_att_ids=side.get('l2g_relative_att_ids'), neg=neg, keep=keep_long, rate=rate)
   global_out = global_rows_attention(
       gq, gk, gv, lk, lv, side.get('g2g_att_mask'),
       side.get('g2g_relative_att_ids'), side.get('g2l_att_mask'),
-      side.get('g2l_relative_att_ids'), global_tables[0], global_tables[1])
+      side.get('g2l_relative_att_ids'), global_tables[0], global_tables[1], neg=neg,
+      keep=keep_global, rate=rate)
   return long_out, global_out

@@ -77,9 +77,12 @@ def test_validation_codes_without_gpu(lib):
   p.dtype = _lib.MLT_F32
   assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -2  # MLT_ERR_SHAPE (all dims zero)
   p.B, p.L, p.G, p.H, p.d, p.R, p.local_radius = 1, 8, 2, 1, 64, 0, 2
-  p.dropout_p = 0.1
-  assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -7  # MLT_ERR_DROPOUT
-  p.dropout_p = 0.0
+  p.dropout_p = 1.0
+  assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -7  # MLT_ERR_DROPOUT: rate outside [0, 1)
+  p.dropout_p = -0.1
+  assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -7
+  p.dropout_p = 0.1                                    # a valid rate passes on to the next check
+
   assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -1  # tensors are NULL
   p.d = 48
   assert lib.mlt_gl_attn_fwd(C.byref(p), None) == -3  # MLT_ERR_UNSUPPORTED head dim
