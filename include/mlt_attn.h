@@ -74,7 +74,9 @@ enum { MLT_SIDE_EXPLICIT = 0, MLT_SIDE_COMPACT = 1 }; /* how masks / ids are sup
 enum {                                               /* backend selection                */
   MLT_IMPL_AUTO = 0,   /* tcgen05 kernels when (bf16, d == 64, R <= 64), else SIMT        */
   MLT_IMPL_SIMT = 1,   /* force the fp32-accumulate CUDA-core kernels                    */
-  MLT_IMPL_TC = 2      /* force tcgen05 kernels (MLT_ERR_UNSUPPORTED if not applicable)   */
+  MLT_IMPL_TC = 2,     /* force tcgen05 kernels (MLT_ERR_UNSUPPORTED if not applicable)   */
+  MLT_IMPL_TC_GENERIC = 3 /* as MLT_IMPL_TC, but skip the kernels specialised for compact
+                             global-local side inputs (cross-check of the two tcgen05 paths)  */
 };
 
 /* [B, len, H, d] view, d contiguous; strides in elements. */

@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, 'libmlt_attn.so')
 MLT_ABI_VERSION = 1
 MLT_F32, MLT_BF16 = 0, 1
 MLT_SIDE_EXPLICIT, MLT_SIDE_COMPACT = 0, 1
-MLT_IMPL_AUTO, MLT_IMPL_SIMT, MLT_IMPL_TC = 0, 1, 2
-IMPL = {'auto': MLT_IMPL_AUTO, 'simt': MLT_IMPL_SIMT, 'tc': MLT_IMPL_TC}
+MLT_IMPL_AUTO, MLT_IMPL_SIMT, MLT_IMPL_TC, MLT_IMPL_TC_GENERIC = 0, 1, 2, 3
+IMPL = {'auto': MLT_IMPL_AUTO, 'simt': MLT_IMPL_SIMT, 'tc': MLT_IMPL_TC, 'tc_generic': MLT_IMPL_TC_GENERIC}
 
 
 class Tensor4(C.Structure):

@@ -405,10 +405,12 @@ bool dense_fwd_on_tc(const mlt_dense_params* p) {
 }
 
 int launch_fwd(const FwdArgs& a, bool tc, int dtype, int d, const char* name, double flops,
-               double bytes, cudaStream_t st) {
+               double bytes, cudaStream_t st, bool allow_gl2 = false) {
   char full[48];
-  snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
+  const bool gl2 = tc && allow_gl2 && gl2_fwd_long_supported(a, dtype, d);
+  snprintf(full, sizeof(full), "%s_%s", gl2 ? "gl2" : (tc ? "tc" : "simt"), name);
   ProfileScope ps(full, flops, bytes, st);
+  if (gl2) return gl2_launch_fwd_long(a, st);
   if (tc) return tc_launch_fwd(a, st);
   MLT_CUDA(simt_launch_fwd(a, dtype, d, st));
   return MLT_OK;
@@ -494,7 +496,7 @@ int mlt_dense_rel_attn_fwd(const mlt_dense_params* p, void* cuda_stream) {
   MLT_TRY(validate_dense(p));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const bool tc = dense_fwd_on_tc(p);
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
   const int32_t* plane = nullptr;
   if (tc && dense_ids_plane_bytes(p)) {
@@ -544,7 +546,7 @@ int mlt_dense_rel_attn_bwd(const mlt_dense_params* p, const mlt_dense_grads* g, 
   kv.B = p->B; kv.H = p->H; kv.scale = p->scale; kv.neg = p->neg;
 
   const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(q, p->dtype, p->d) && bwd_kv_on_tc(kv);
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, pairs = (double)p->Lq * p->Lk;
   if (tc && dense_ids_plane_bytes(p)) {   // compact 2-D ids: one [Lq, Lk] plane, read through the EXPL form
     int32_t* w = dense_ids_plane(p, 1);
@@ -573,7 +575,7 @@ int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
   MLT_TRY(validate_gl(p));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const bool tc = gl_fwd_on_tc(p);
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H;
   const double pl = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
   const double pg = (double)p->G * (p->G + p->L);
@@ -584,7 +586,8 @@ int mlt_gl_attn_fwd(const mlt_gl_params* p, void* cuda_stream) {
                      qkv_bytes(bh, 2.0 * p->L + 4.0 * p->G, p->d, p->dtype, 1), fk.side()));
   MLT_TRY(launch_fwd(gl_long_fwd_args(p), tc, p->dtype, p->d, "fwd_long_rows",
                      fwd_flops(bh, pl, p->d, p->R, p->L),
-                     qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
+                     qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st,
+                     p->impl != MLT_IMPL_TC_GENERIC));
   return MLT_OK;
 }
 
@@ -648,7 +651,7 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
 
   const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(ql, p->dtype, p->d) &&
                   tc_bwd_q_supported(qg, p->dtype, p->d) && bwd_kv_on_tc(kl) && bwd_kv_on_tc(kg);
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   void* ws_lg[2] = {tc_wl, tc_wg};
 
   const double bh = (double)p->B * p->H, dd = p->d, RR = p->R;
@@ -769,11 +772,12 @@ int mlt_local_rel_attn_fwd(const mlt_local_params* p, void* cuda_stream) {
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const FwdArgs a = local_fwd_args(p);
   const bool tc = p->impl != MLT_IMPL_SIMT && tc_fwd_args_supported(a, p->dtype, p->d);
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H;
   const double pairs = band_pairs(p->L, p->local_radius) + (double)p->L * p->G;
   return launch_fwd(a, tc, p->dtype, p->d, "fwd_local_rows", fwd_flops(bh, pairs, p->d, p->R, p->L),
-                    qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st);
+                    qkv_bytes(bh, 4.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st,
+                    p->impl != MLT_IMPL_TC_GENERIC);
 }
 
 int mlt_local_rel_attn_bwd(const mlt_local_params* p, const mlt_local_grads* g, void* cuda_stream) {
@@ -819,7 +823,7 @@ int mlt_local_rel_attn_bwd(const mlt_local_params* p, const mlt_local_grads* g, 
   }
   const bool tc = p->impl != MLT_IMPL_SIMT && tc_bwd_q_supported(q, p->dtype, p->d) && bwd_kv_on_tc(kl) &&
                   (p->G == 0 || bwd_kv_on_tc(ks));
-  if (p->impl == MLT_IMPL_TC && !tc) return MLT_ERR_UNSUPPORTED;
+  if ((p->impl == MLT_IMPL_TC || p->impl == MLT_IMPL_TC_GENERIC) && !tc) return MLT_ERR_UNSUPPORTED;
   const double bh = (double)p->B * p->H, dd = p->d;
   const double p_l = band_pairs(p->L, p->local_radius), p_s = (double)p->L * p->G;
   MLT_TRY(launch_bwd_q(q, tc, tcw[0], p->dtype, p->d, "bwd_q_local_rows",

@@ -44,6 +44,11 @@ bool tc_fwd_args_supported(const FwdArgs& a, int dtype, int d);
 int tc_launch_fwd(const FwdArgs& a, cudaStream_t st);
 
 
+// ---- gl2: persistent kernels specialised for compact global-local attention (gl2_*.cu) ----------
+// Long rows, forward: bf16, d = 64, example-id masks, 1-D band ids + sentence cross ids, R <= 32, no dropout.
+bool gl2_fwd_long_supported(const FwdArgs& a, int dtype, int d);
+int gl2_launch_fwd_long(const FwdArgs& a, cudaStream_t st);
+
 // ---- backward (tc_bwd.cu) -------------------------------------------------------------------
 // Extra workspace (bytes) of one row set: rowstat [B,H,Lpad] float4 + allrel [B,H,Lpad,R4] f32.
 size_t tc_bwd_rows_ws_bytes(int B, int H, int len, int R);

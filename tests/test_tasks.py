@@ -47,11 +47,14 @@ def test_gather_indexes_and_recall():
   seq = torch.arange(2 * 4 * 3, dtype=torch.float32).reshape(2, 4, 3)
   got = tasks.gather_indexes(seq, torch.tensor([[0, 3], [2, 2]]))
   assert torch.equal(got, torch.stack([seq[0, 0], seq[0, 3], seq[1, 2], seq[1, 2]]))
-  scores = torch.tensor([0.9, 0.1, 0.5, 0.2, 0.8, 0.7])
-  q = torch.tensor([0, 0, 0, 1, 1, 1])
-  match = torch.tensor([False, False, True, True, False, False])
-  r = tasks.recall_at_k(scores, q, match, ks=(1, 2, 3))
-  assert r == {'recall@1': 0.0, 'recall@2': 0.5, 'recall@3': 1.0}
+  # hand-checked retrieval case: 2 texts x 3 images, text 0 <-> image 2, text 1 <-> image 0
+  text, image = tasks.enumerate_image_text_pairs(num_images=3, num_texts=2)
+  scores = torch.tensor([0.9, 0.1, 0.5, 0.2, 0.8, 0.7], dtype=torch.float64)
+  r = tasks.get_recall_at_k(image, text, torch.tensor([2, 0])[text], scores, topks=(1, 2, 3))
+  # text -> image: text 0 ranks its image 2nd, text 1 ranks its image 3rd
+  assert [r['t2i @  1'], r['t2i @  2'], r['t2i @  3']] == [0.0, 0.5, 1.0]
+  # image -> text: image 0 (gt of text 1) ranks it 2nd of 2; image 2 (gt of text 0) ranks it 2nd of 2
+  assert [r['i2t @  1'], r['i2t @  2']] == [0.0, 1.0]
 
 
 WORKER = r'''
@@ -72,17 +75,32 @@ class Tiny(torch.nn.Module):
     g = lambda pos: torch.gather(x, 1, pos[..., None].expand(-1, -1, 8))
     return {'mlm_logits': self.mlm(g(mlm_positions)), 'mpp_logits': self.mpp(g(mpp_positions)), 'itm_logits': self.itm(x[:, 0])}
 model = Tiny()
+init = {k: v.clone() for k, v in model.state_dict().items()}
 opt = torch.optim.SGD(model.parameters(), lr=0.1)
-step = tasks.PretrainingStep(model, opt, micro_batch_size=2)
+step = tasks.PretrainingStep(model, opt, micro_batch_size=2, bucket_mb=0.0001)   # several buckets even for this toy
 g = torch.Generator().manual_seed(100 + rank)      # different data per rank
 inputs = {'word_ids': torch.randint(0, 16, (4, 6), generator=g), 'mlm_positions': torch.randint(0, 6, (4, 2), generator=g),
           'mpp_positions': torch.randint(0, 6, (4, 2), generator=g)}
 labels = {'mlm_label_ids': torch.randint(0, 16, (4, 2), generator=g), 'mlm_label_weights': torch.ones(4, 2),
           'mpp_label_ids': torch.randint(0, 4, (4, 2), generator=g), 'mpp_label_weights': torch.ones(4, 2),
           'itm_label_ids': torch.randint(0, 2, (4,), generator=g), 'itm_label_weights': torch.ones(4)}
+nb = sum(len(gr['buckets']) for gr in step.groups)
 loss = step(inputs, labels)
+# reference semantics (scale_loss=False): the applied gradient is the SUM over the replicas of each replica's
+# mean-over-micro-batches gradient.  Recompute it without the step machinery and compare.
+ref_model = Tiny(); ref_model.load_state_dict(init)
+tot = None
+for sl in (slice(0, 2), slice(2, 4)):
+  out = ref_model(**{k: v[sl] for k, v in inputs.items()})
+  l = tasks.pretraining_losses({k: v[sl] for k, v in labels.items()}, out) / 2
+  gs = torch.autograd.grad(l, list(ref_model.parameters()))
+  tot = gs if tot is None else [a + b for a, b in zip(tot, gs)]
+flat_ref = torch.cat([t.reshape(-1) for t in tot])
+dist.all_reduce(flat_ref)
+want = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]) - 0.1 * flat_ref
 flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
-print(json.dumps({"rank": rank, "loss": float(loss), "checksum": float(flat.double().sum()), "norm": float(flat.norm())}))
+print(json.dumps({"rank": rank, "loss": float(loss), "checksum": float(flat.double().sum()), "norm": float(flat.norm()),
+                  "buckets": nb, "err_vs_manual": float((flat - want).abs().max())}))
 dist.destroy_process_group()
 '''
 
@@ -104,6 +122,8 @@ def test_gradient_allreduce_keeps_replicas_identical(tmp_path):
   assert len(rows) == 2
   assert rows[0]['loss'] != rows[1]['loss']                       # different data per replica
   assert abs(rows[0]['checksum'] - rows[1]['checksum']) < 1e-9    # identical parameters after the step
+  assert rows[0]['buckets'] >= 3                                  # the bucketed, hook-driven path was exercised
+  assert max(r['err_vs_manual'] for r in rows) < 1e-6             # = SGD on the replica-summed gradient
 
 
 def _long_model(device, layers_n=2):
@@ -148,3 +168,34 @@ def test_e2e_pretraining_step_and_retrieval_on_long_inputs():
   assert losses[-1] < losses[0]          # memorises the fixed batch
   scores = tasks.retrieval_scores(model, [dict(inputs, compact_side_inputs=compact)])
   assert scores.shape == (4,) and bool(((scores >= 0) & (scores <= 1)).all())
+
+
+# ---- retrieval: pair enumeration, sharding, labels, recall@k pinned to the reference function ---------
+
+def test_recall_at_k_matches_reference_function_outputs():
+  """tests/golden/recall_golden.json holds outputs of the reference's own get_recall_at_k_from_dataframe
+  (src/prediction_helper.py:30-89, executed by tests/golden/make_golden_recall.py), including ties and
+  examples that do not share one candidate pool."""
+  import json, pathlib
+  golden = json.loads((pathlib.Path(__file__).parent / 'golden' / 'recall_golden.json').read_text())
+  assert len(golden['cases']) >= 5
+  for case in golden['cases']:
+    got = tasks.get_recall_at_k(torch.tensor(case['image_index']), torch.tensor(case['text_index']),
+                                torch.tensor(case['gt_image_index']), torch.tensor(case['output'], dtype=torch.float64))
+    assert list(got) == list(case['expected'])
+    for key, want in case['expected'].items():
+      assert f'{got[key]:.4f}' == want, (key, got[key], want)
+
+
+def test_pair_enumeration_sharding_and_labels():
+  text, image = tasks.enumerate_image_text_pairs(num_images=3, num_texts=2)
+  # text outer, image inner (reference retrieval_dataloader.py:188-195)
+  assert text.tolist() == [0, 0, 0, 1, 1, 1] and image.tolist() == [0, 1, 2, 0, 1, 2]
+  shards = [tasks.shard_pairs(6, 4, r).tolist() for r in range(4)]
+  assert shards == [[0, 4], [1, 5], [2], [3]]                      # dataset.shard semantics
+  assert sorted(sum(shards, [])) == list(range(6))                 # a partition: no pair lost or doubled
+  gt = torch.tensor([2, 0])[text]
+  label, weight = tasks.retrieval_labels(image, gt, pos_weight=4.0)
+  assert label.tolist() == [0, 0, 1, 1, 0, 0] and weight.tolist() == [1, 1, 4, 4, 1, 1]
+  with pytest.raises(ValueError):
+    tasks.shard_pairs(6, 2, 2)
