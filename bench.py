@@ -165,7 +165,8 @@ def time_cpu(workload_shape, steps, warmup, sample_batch=1):
     cpu_blocked_step(shape, x, side)
     times.append(time.perf_counter() - t0)
   sec = sum(times) / len(times)
-  return dict(tokens_per_s=shape.tokens / sec, sec_per_step=sec, cores=cores,
+  return dict(tokens_per_s=shape.tokens / sec, sec_per_step=sec, cores=cores, sample_batch=sample_batch,
+              steps=steps, warmup=warmup,
               sample=(f'{WORKLOAD} with batch {sample_batch} (= {shape.tokens} long tokens per '
                       f'fwd+bwd; full workload batch {workload_shape.batch}), fp32, ETC blocked '
                       f'algorithm restated in PyTorch-CPU (oracle/blocked_etc.py), '
@@ -187,8 +188,11 @@ def run_reference(args):
       'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
       'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'note': 'TensorFlow/etcmodel cannot run in this image; '
-                 'this arm times the CPU restatement of the same algorithm (kind=port)'},
+      'config': {'workload': WORKLOAD, 'cpu_sample_batch': r['sample_batch'], 'cpu_warmup': r['warmup'],
+                 'cpu_steps': r['steps'],
+                 'note': 'TensorFlow/etcmodel cannot run in this image; this arm times the CPU restatement of '
+                         'the same algorithm (kind=port) on a batch-1 sample of the workload, all host threads; '
+                         'tokens/s is per token, so it compares with the GPU arm\'s full batch'},
       'cpu_baseline': {'value': r['tokens_per_s'], 'unit': UNIT, 'cores': r['cores'],
                        'kind': 'port', 'sample': r['sample']},
       'e2e': {'value': r['tokens_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
@@ -359,16 +363,16 @@ def run_cuda(args):
   if old_affinity is not None:      # every pinned buffer exists now: give the CPU arm all cores back
     os.sched_setaffinity(0, old_affinity)
   # The first steps after an idle period run at a fraction of the link rate (18 - 37 ms per step against
-  # 10 ms in steady state were seen): warm-up above, then three windows of e2e_steps steps; the fastest
-  # one is reported, all three are listed.
+  # 10 ms in steady state were seen): warm-up above, then five windows of e2e_steps steps; the MEDIAN
+  # window is reported, all are listed.
   e2e_windows = []
-  for _ in range(3):
+  for _ in range(5):
     w0 = time.perf_counter()
     for k in range(e2e_steps):
       e2e_step(k)
     barrier()                                # all three streams drained: every result is on the host
     e2e_windows.append((time.perf_counter() - w0) / e2e_steps * 1e3)
-  e2e_ms = min(e2e_windows)
+  e2e_ms = sorted(e2e_windows)[len(e2e_windows) // 2]
   t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -396,15 +400,23 @@ def run_cuda(args):
     total = sum(k['ms'] for k in kernels.values())
     top_name, top = max(kernels.items(), key=lambda kv: kv[1]['ms'])
     achieved = top['flops'] / (top['ms'] * 1e-3) / 1e12
-    peak = peaks['tflops_sustained']
+    # the timed region is K x ~2 ms: far below the ~1 s it takes the clocks to settle to the sustained
+    # figure, so the burst peak is the honest denominator; the sustained fraction is printed beside it
+    burst_region = ms_total < 1000.0
+    peak = peaks['tflops_burst'] if burst_region else peaks['tflops_sustained']
+    step_tflops = 3 * shape.flops_fwd() / (ms_per_step * 1e-3) / 1e12
     roofline = {
         'bound': 'tensor', 'kernel': top_name, 'achieved': achieved, 'peak': peak,
         'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': load_traffic(top_name),
-        'peak_source': peaks['source'] + ', sustained bf16 figure (kernel timed inside the step loop)',
+        'peak_source': peaks['source'] + (', burst bf16 figure (timed region %.0f ms < 1 s)' % ms_total
+                                          if burst_region else ', sustained bf16 figure (long timed region)'),
+        'frac_of_sustained_peak': achieved / peaks['tflops_sustained'],
+        'frac_of_burst_peak': achieved / peaks['tflops_burst'],
         'kernel_ms': top['ms'], 'kernel_share_of_step': top['ms'] / total if total else None,
         'algorithmic_flops_per_launch': top['flops'],
-        'step_achieved_tflops': 3 * shape.flops_fwd() / (ms_per_step * 1e-3) / 1e12,
-        'step_frac_of_peak': 3 * shape.flops_fwd() / (ms_per_step * 1e-3) / 1e12 / peak,
+        'step_achieved_tflops': step_tflops,
+        'step_frac_of_peak': step_tflops / peak,
+        'step_frac_of_sustained_peak': step_tflops / peaks['tflops_sustained'],
     }
 
   cpu = None
@@ -414,7 +426,7 @@ def run_cuda(args):
            'sample': r['sample']}
 
   if rank == 0:
-    uses_tc = any(n.startswith('tc_') for n in kernels)
+    uses_tc = any(n.startswith('tc_') or n.startswith('gl2_') for n in kernels)
     line = {
         'metric': METRIC, 'value': tokens_per_s, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
@@ -427,6 +439,7 @@ def run_cuda(args):
             'max_distance': shape.max_distance, 'side_inputs': 'compact (built in-kernel)',
             'pass': 'fwd+bwd', 'tokens_per_step_per_gpu': shape.tokens,
             'kernel_path': 'tcgen05' if uses_tc else 'simt',
+            'fp32_note': 'fp32 inputs (BASELINE configs[0]) run on the CUDA-core SIMT kernels only: no tensor-core path',
             'l2_policy': 'per-step working set (~1.3 GB of q/k/v/out/grads) exceeds the 126 MB L2; no flush',
             'parallelism': f'batch x head units sharded over {world} GPU(s), no collective',
         },
@@ -435,7 +448,13 @@ def run_cuda(args):
                 'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': t.item(), 'steps': e2e_steps,
                 'pipelining': 'copy-in / kernels / copy-out on three streams, two buffer sets',
                 'host_numa_node': numa_node,
-                'ms_per_step_windows': [round(w, 3) for w in e2e_windows]},
+                'reported': 'median of the windows',
+                'ms_per_step_windows': [round(w, 3) for w in e2e_windows],
+                # what limits e2e: PCIe per GPU at N = 1 (~46 GB/s per direction with both busy), the host's
+                # aggregate PCIe / DRAM throughput at larger N (single-socket virtualised box: ~100-135 GB/s)
+                'link_gb_per_s_per_gpu_per_direction': h2d_bytes / (t.item() * 1e-3) / 1e9,
+                'host_aggregate_gb_per_s': world * (h2d_bytes + d2h_bytes) / (t.item() * 1e-3) / 1e9,
+                'limiter': 'PCIe link of the GPU' if world == 1 else 'host aggregate PCIe / DRAM throughput'},
         'gpu_launches': launches,
         'roofline': roofline,
         'kernels_ms': {k: round(v['ms'], 4) for k, v in kernels.items()},
@@ -448,6 +467,197 @@ def run_cuda(args):
     dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# Callers of the hot path: same JSON contract, selected with
+# --workload.  The headline default (c3_4096) is untouched.
+
+EXTRA_WORKLOADS = {
+    'c2_encoder': dict(metric='mmt_encoder_fwd_tokens_per_s', unit='tokens/s',
+                       what='BASELINE configs[1]: 12-layer d=768 encoder forward, S = 512 = 2 + 196 patches + text, '
+                            'bf16, the reference\'s explicit [B,S,S] int32 mask + 2-D relative ids'),
+    'c4_pretrain': dict(metric='mmt_pretraining_step_tokens_per_s', unit='tokens/s',
+                        what='BASELINE configs[3]: pretraining step (MLM + masked-patch + ITM heads, AdamW, micro-batch '
+                             'accumulation, bucketed NCCL gradient all-reduce overlapped with backward), long-input '
+                             'encoder L 4096 + 256 global tokens, bf16'),
+    'c5_retrieval': dict(metric='image_text_pair_scoring_pairs_per_s', unit='pairs/s',
+                         what='BASELINE configs[4]: retrieval pair scoring softmax(itm_logits)[:,1], dense encoder S 512, '
+                              'pairs enumerated text-major and sharded over the ranks'),
+}
+
+
+def run_extra(args):
+  import torch
+  import torch.distributed as dist
+  import mlt_b200  # noqa: F401
+  from mlt_b200 import _lib, feature_utils as fu, mmt_encoder, ops, tasks
+  name = args.workload
+  info = EXTRA_WORKLOADS[name]
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if args.impl == 'reference':
+    if rank == 0:
+      print(json.dumps({'impl': 'reference', 'metric': info['metric'], 'unit': info['unit'],
+                        'config': {'workload': name},
+                        'unavailable': 'the CPU restatement covers the attention path (default workload) only; '
+                                       'the reference\'s TF model stack cannot run in this image'}))
+    return
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback)')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  _lib.load()
+  VOCAB, S, NPR, D, R = 30522, 512, 14, 12, 32
+  torch.manual_seed(0)            # identical initial weights on every rank
+  gen = torch.Generator().manual_seed(100 + rank)
+  pin = lambda t: t.pin_memory()
+  cfg = {}
+  if name == 'c2_encoder' or name == 'c5_retrieval':
+    B = 32 if name == 'c2_encoder' else 64
+    enc = mmt_encoder.MmtEncoder(vocab_size=VOCAB, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                 intermediate_size=3072, relative_vocab_size=49 if name == 'c2_encoder' else R,
+                                 relative_pos_max_distance=D, patch_embedding_size=768)
+    model = tasks.MmtPretrainingModel(enc, mpp_output_num_classes=8192,
+                                      classification_heads=[tasks.ClassificationHead(768, 2, 'itm')])
+    model = model.to(dev).to(torch.bfloat16).eval()
+    lengths = torch.randint(S // 2, S + 1, (B,), generator=gen)
+    eid = (torch.arange(S)[None] < lengths[:, None]).to(torch.int32)
+    host = {'word_ids': pin(torch.randint(0, VOCAB, (B, S), generator=gen)),
+            'patch_embeddings': pin(torch.randn(B, NPR * NPR, 768, generator=gen).to(torch.bfloat16)),
+            'example_ids': pin(eid)}
+    if name == 'c2_encoder':
+      units, cfg = B * S, dict(batch_per_gpu=B, seq_len=S, layers=12, side_inputs='explicit [B,S,S] mask + 2-D ids, '
+                               'built on the device per step from example ids (mlt_build_dense_side_inputs)')
+
+      def run(d):
+        mask, ids = ops.build_dense_side_inputs(d['example_ids'], D, num_patch_per_row=NPR, num_core_layers=2)
+        with torch.no_grad():
+          out = model.encoder(d['word_ids'], att_mask=mask, relative_att_ids=ids,
+                              patch_embeddings=d['patch_embeddings'], training=False)
+        return out['sequence_output'][:, 0].float()
+    else:
+      # pairs = (text, image) combinations, text-major, sharded like dataset.shard (no collective)
+      n_img = n_txt = 16
+      text_i, image_i = tasks.enumerate_image_text_pairs(n_img, n_txt)
+      mine = tasks.shard_pairs(text_i.numel() * world, world, rank)[:B] // world   # B pairs of this rank's shard
+      units, cfg = B, dict(pairs_per_gpu_per_step=B, seq_len=S, layers=12, side_inputs='compact 2-D descriptors',
+                           pair_order='text-major enumeration, dataset.shard over ranks')
+
+      def run(d):
+        batch = {'word_ids': d['word_ids'], 'patch_embeddings': d['patch_embeddings'],
+                 'compact': ops.DenseCompactSideInputs(d['example_ids'], max_distance=D, num_patch_per_row=NPR,
+                                                       num_core_layers=2)}
+        return tasks.retrieval_scores(model, [batch])
+  else:
+    L, B, MICRO = 4096, 4, 2
+    G = L // 16
+    enc = mmt_encoder.MmtEncoder(vocab_size=VOCAB, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                 intermediate_size=3072, relative_vocab_size=R, relative_pos_max_distance=D,
+                                 use_pre_activation_order=True, patch_embedding_size=768, local_radius=64,
+                                 num_global_tokens=G)
+    model = tasks.MmtPretrainingModel(enc, mpp_output_num_classes=8192,
+                                      classification_heads=[tasks.ClassificationHead(768, 2, 'itm')])
+    model = model.to(dev).to(torch.bfloat16)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    stepper = tasks.PretrainingStep(model, opt, micro_batch_size=MICRO)
+    lengths = torch.randint(L // 2, L + 1, (B,), generator=gen)
+    host = {'word_ids': pin(torch.randint(0, VOCAB, (B, L), generator=gen)),
+            'patch_embeddings': pin(torch.randn(B, 196, 768, generator=gen).to(torch.bfloat16)),
+            'mlm_positions': pin(torch.randint(198, L // 2, (B, 64), generator=gen)),
+            'mpp_positions': pin(torch.randint(2, 198, (B, 32), generator=gen)),
+            'long_example_ids': pin((torch.arange(L)[None] < lengths[:, None]).to(torch.int32)),
+            'mlm_label_ids': pin(torch.randint(0, VOCAB, (B, 64), generator=gen)),
+            'mpp_label_ids': pin(torch.randint(0, 8192, (B, 32), generator=gen)),
+            'itm_label_ids': pin(torch.randint(0, 2, (B,), generator=gen))}
+    sent = ((torch.arange(L) * G) // L)[None].expand(B, L).to(torch.int32).contiguous().to(dev)
+    ge = torch.ones(B, G, dtype=torch.int32, device=dev)
+    units = B * L
+    cfg = dict(batch_per_gpu=B, micro_batch=MICRO, long_len=L, global_len=G, layers=12,
+               params=sum(p.numel() for p in model.parameters()), dropout='attention 0.1 + hidden 0.1 (reference defaults)',
+               allreduce='bucketed (25 MB), fp32, overlapped with the last micro-batch backward')
+
+    def run(d):
+      inputs = {k: d[k] for k in ('word_ids', 'patch_embeddings', 'mlm_positions', 'mpp_positions')}
+      labels = {'mlm_label_ids': d['mlm_label_ids'], 'mlm_label_weights': torch.ones(B, 64, device=dev),
+                'mpp_label_ids': d['mpp_label_ids'], 'mpp_label_weights': torch.ones(B, 32, device=dev),
+                'itm_label_ids': d['itm_label_ids'], 'itm_label_weights': torch.ones(B, device=dev)}
+      compact = fu.CompactSideInputs(d['long_example_ids'], ge, sent, D)
+      return stepper(inputs, labels, compact_side_inputs=compact).reshape(1)
+
+  resident = {k: v.to(dev) for k, v in host.items()}
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  warm = max(args.warmup, 3)
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  for _ in range(warm):
+    run(resident)
+  barrier()
+  launches0 = _lib.launch_count()
+  beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  sampler.mark_begin()
+  beg.record()
+  for _ in range(args.steps):
+    run(resident)
+  end.record()
+  barrier()
+  launches = _lib.launch_count() - launches0
+  sampler.mark_end()
+  clocks = sampler.stop()
+  t = torch.tensor([beg.elapsed_time(end) / args.steps], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = t.item()
+  # end to end: inputs from pinned host memory every step, result back to the host every step
+  out_host = None
+  e2e_steps = max(2, min(args.steps, 10))
+  def e2e_once():
+    nonlocal out_host
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    r = run(d)
+    if out_host is None:
+      out_host = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+    out_host.copy_(r, non_blocking=True)
+  for _ in range(2):
+    e2e_once()
+  barrier()
+  w0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_once()
+  barrier()
+  te = torch.tensor([(time.perf_counter() - w0) / e2e_steps * 1e3], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+  # share of a step inside the attention kernels (library profiler hook serialises them: upper bound)
+  att_ms = None
+  if rank == 0:
+    _lib.profile_enable(True)
+    run(resident)
+    torch.cuda.synchronize()
+    att_ms = sum(r[1] for r in _lib.profile_read(1 << 16))
+    _lib.profile_enable(False)
+  if rank == 0:
+    cfg.update(workload=name, what=info['what'], attention_kernels_ms_per_step=att_ms,
+               parallelism=f'data parallel over {world} GPU(s)' + (', NCCL gradient all-reduce' if name == 'c4_pretrain' else ', no collective'),
+               l2_policy='activations of one step exceed the 126 MB L2; no flush')
+    print(json.dumps({
+        'metric': info['metric'], 'value': world * units / (ms * 1e-3), 'unit': info['unit'], 'n_gpus': world,
+        'steps': args.steps, 'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
+        'e2e': {'value': world * units / (te.item() * 1e-3), 'unit': info['unit'],
+                'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()),
+                'd2h_bytes_per_step': out_host.numel() * out_host.element_size(), 'ms_per_step': te.item()},
+        'gpu_launches': launches, 'roofline': None, 'cpu_baseline': None}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -456,10 +666,15 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
-  ap.add_argument('--workload', default='c3_4096', choices=['c3_2048', 'c3_4096', 'c3_8192'],
-                  help='long-input sweep point (BASELINE.json configs[2]); the default is the one the '
-                       'metric is quoted on, the others hold B*L = 65 536 tokens per GPU as well')
+  ap.add_argument('--workload', default='c3_4096',
+                  choices=['c3_2048', 'c3_4096', 'c3_8192', 'c2_encoder', 'c4_pretrain', 'c5_retrieval'],
+                  help='c3_*: long-input sweep point (BASELINE.json configs[2]); the default is the one the '
+                       'metric is quoted on, the others hold B*L = 65 536 tokens per GPU as well.  '
+                       'c2_encoder / c4_pretrain / c5_retrieval: the callers of the hot path (configs[1], [3], [4])')
   args = ap.parse_args()
+  if args.workload in EXTRA_WORKLOADS:
+    run_extra(args)
+    return
   globals()['WORKLOAD'] = args.workload
   if args.impl == 'reference':
     run_reference(args)

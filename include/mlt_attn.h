@@ -30,13 +30,20 @@
  *     void*); the call returns immediately.
  *   - Errors: int return. 0 = ok; < 0 = MLT_ERR_* (bad argument / unsupported shape);
  *     > 0 = a cudaError_t from the launch.  Nothing throws, nothing exits.
- *   - Threading: re-entrant; the only global state is per-process one-time kernel attribute
- *     setup guarded by std::call_once.
+ *   - Threading: re-entrant from any host thread and for any device.  Global state is limited to
+ *     per-device one-time kernel attribute setup (mutex-guarded), a by-value cache of TMA tensor
+ *     maps, and a small per-device pool of side streams taken with try_lock (a call never waits for
+ *     another call: when the pool is busy it runs on the caller's stream alone).
  *   - q/k/v/out tensors are [B, len, H, d] with d contiguous (heads NOT transposed, as
  *     ProjectAttentionHeads produces them); strides are in elements.
  *   - Semantics:  s = (q.k + allrel[id]) * scale + neg * (1 - mask),
  *     allrel[p] = q.E[p] + bias[p], ids outside [0, R) contribute 0 (one-hot lookup),
- *     p = softmax over ALL key segments of the row jointly.
+ *     p = softmax over ALL key segments of the row jointly; with dropout_p > 0 (training) the
+ *     probabilities are dropped AFTER the softmax and the kept ones scaled by 1 / (1 - dropout_p)
+ *     (reference attention_probs_dropout_prob, src/configs/encoders.py:87-88).  The keep mask is a
+ *     counter-based hash of (dropout_seed, batch, head, row set, query row, key column) -- see
+ *     csrc/mlt_common.cuh (dropout_keep) and its numpy restatement tests/dropout_ref.py -- so the
+ *     backward regenerates it from the seed; nothing is stored.
  */
 #ifndef MLT_ATTN_H_
 #define MLT_ATTN_H_
@@ -65,7 +72,7 @@ enum {
   MLT_ERR_STRIDE = -4,      /* stride / alignment requirement violated                   */
   MLT_ERR_WORKSPACE = -5,   /* workspace missing or too small                            */
   MLT_ERR_DTYPE = -6,       /* unknown dtype enum                                        */
-  MLT_ERR_DROPOUT = -7      /* dropout_p != 0 (attention-prob dropout not implemented)   */
+  MLT_ERR_DROPOUT = -7      /* dropout_p outside [0, 1)                                  */
 };
 
 /* ---- enums ------------------------------------------------------------------------- */
@@ -110,12 +117,13 @@ typedef struct {
   int32_t impl;               /* MLT_IMPL_* */
   int32_t B, Lq, Lk, H, d, R; /* R = relative_vocab_size (0 if no tables) */
   float scale;                /* 1/sqrt(d) */
-  float neg;                  /* -1e9 */
-  float dropout_p;            /* must be 0 */
-  uint64_t dropout_seed;
+  float neg;                  /* additive mask constant, honoured literally (reference: -1e9) */
+  float dropout_p;            /* attention-probability dropout rate in [0, 1); 0 = off */
+  uint64_t dropout_seed;      /* keep mask = hash(seed, b, h, row, key); pass the same seed to _bwd */
   mlt_tensor4 q, k, v;        /* inputs */
   mlt_tensor4 out;            /* output [B, Lq, H, d] */
-  float* stats;               /* output [B, H, Lq, 2] = (row max, row sum of exp); required */
+  float* stats;               /* output [B, H, Lq, 2] = (m, sum_j exp(s_j - m)) with m >= row max a
+                               * softmax reference (the row max itself on most paths); required */
   mlt_rel_tables tables;
   int32_t side_mode;          /* MLT_SIDE_* */
   /* MLT_SIDE_EXPLICIT: int32 [B, Lq, Lk] each, contiguous; NULL mask = all ones, NULL ids = no
@@ -147,7 +155,7 @@ typedef struct {
   int32_t local_radius;
   float scale;
   float neg;
-  float dropout_p;            /* must be 0 */
+  float dropout_p;            /* as in mlt_dense_params */
   uint64_t dropout_seed;
   mlt_tensor4 long_q, long_k, long_v;       /* [B, L, H, d] */
   mlt_tensor4 global_q, global_k, global_v; /* [B, G, H, d] */
@@ -200,7 +208,7 @@ typedef struct {
   int32_t local_radius;
   float scale;
   float neg;
-  float dropout_p;            /* must be 0 */
+  float dropout_p;            /* as in mlt_dense_params */
   uint64_t dropout_seed;
   mlt_tensor4 q, k, v;        /* [B, L, H, d] */
   mlt_tensor4 side_k, side_v; /* [B, G, H, d]; ignored when G == 0 */

@@ -629,10 +629,10 @@ int gl2_launch_fwd_long(const FwdArgs& a, cudaStream_t st) {
   CUtensorMap mq, mk, mv, mgk, mgv, me;
   int e = 0;
   e |= make_qkv_tensor_map(&mq, a.rows.q.ptr, a.rows.q.sb, a.rows.q.sl, a.rows.q.sh, a.B, p.L, a.H, gl2::TM);
-  e |= make_qkv_tensor_map(&mk, a.seg[0].k.ptr, a.seg[0].k.sb, a.seg[0].k.sl, a.seg[0].k.sh, a.B, p.L, a.H, gl2::TK);
-  e |= make_qkv_tensor_map(&mv, a.seg[0].v.ptr, a.seg[0].v.sb, a.seg[0].v.sl, a.seg[0].v.sh, a.B, p.L, a.H, gl2::TK);
-  e |= make_qkv_tensor_map(&mgk, a.seg[1].k.ptr, a.seg[1].k.sb, a.seg[1].k.sl, a.seg[1].k.sh, a.B, p.G, a.H, gl2::TK);
-  e |= make_qkv_tensor_map(&mgv, a.seg[1].v.ptr, a.seg[1].v.sb, a.seg[1].v.sl, a.seg[1].v.sh, a.B, p.G, a.H, gl2::TK);
+  e |= make_qkv_tensor_map(&mk, a.seg[0].k.ptr, a.seg[0].k.sb, a.seg[0].k.sl, a.seg[0].k.sh, a.B, p.L, a.H, 64);
+  e |= make_qkv_tensor_map(&mv, a.seg[0].v.ptr, a.seg[0].v.sb, a.seg[0].v.sl, a.seg[0].v.sh, a.B, p.L, a.H, 64);
+  e |= make_qkv_tensor_map(&mgk, a.seg[1].k.ptr, a.seg[1].k.sb, a.seg[1].k.sl, a.seg[1].k.sh, a.B, p.G, a.H, 64);
+  e |= make_qkv_tensor_map(&mgv, a.seg[1].v.ptr, a.seg[1].v.sb, a.seg[1].v.sl, a.seg[1].v.sh, a.B, p.G, a.H, 64);
   e |= make_qkv_tensor_map(&me, a.rows.emb, (int64_t)p.R * a.H * 64, (int64_t)a.H * 64, 64, 1, p.R, a.H, 32);
   if (e) return MLT_ERR_UNSUPPORTED;
   const int grid = p.total_pairs < sm_count[dev] ? p.total_pairs : sm_count[dev];
