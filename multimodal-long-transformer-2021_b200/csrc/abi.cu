@@ -425,11 +425,12 @@ bool bwd_kv_on_tc(const BwdKVArgs& kv) {
 }
 
 int launch_bwd_q(const BwdQArgs& a, bool tc, void* tc_ws, int dtype, int d, const char* name, double flops,
-                 double bytes, cudaStream_t st) {
+                 double bytes, cudaStream_t st, bool allow_gl2 = false) {
   char full[48];
-  snprintf(full, sizeof(full), "%s_%s", tc ? "tc" : "simt", name);
+  const bool gl2 = tc && allow_gl2 && gl2_bwd_q_long_supported(a, dtype, d);
+  snprintf(full, sizeof(full), "%s_%s", gl2 ? "gl2" : (tc ? "tc" : "simt"), name);
   ProfileScope ps(full, flops, bytes, st, tc ? 2 : 1);   // tcgen05 path = row-record preprocess + main kernel
-  if (tc) return tc_launch_bwd_q(a, tc_ws, st);
+  if (tc) return tc_launch_bwd_q(a, tc_ws, st, gl2);
   MLT_CUDA(simt_launch_bwd_q(a, dtype, d, st));
   return MLT_OK;
 }
@@ -664,7 +665,8 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                          qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), fk.side()));
   MLT_TRY(launch_bwd_q(ql, tc, tc_wl, p->dtype, p->d, "bwd_q_long_rows",
                        bh * (4 * dd * (p_l2l + p_lg) + 2 * dd * RR * p->L),
-                       qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
+                       qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st,
+                       p->impl != MLT_IMPL_TC_GENERIC));
   }
   // Main stream: the long-key kernel (longest).  Side stream: global-key kernel, then the small
   // table-gradient kernels, which only need the bins of the query-centric pass and are light

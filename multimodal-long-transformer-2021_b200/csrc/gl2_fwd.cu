@@ -24,6 +24,7 @@
 // exactly 0 (exp(-1e9 + ...) flushes): masked rows / groups are simply skipped.
 #include "tc_api.cuh"
 
+#include "gl2_geom.cuh"
 #include "mlt_common.cuh"
 #include "profile.cuh"
 #include "tc_ptx.cuh"
@@ -33,11 +34,7 @@ namespace gl2 {
 
 using namespace ptx;
 
-constexpr int TM = 128;          // query rows per tile
-constexpr int TK = 128;          // keys per chunk (two blocks of 64)
-constexpr int NST = 3;           // K/V ring stages
 constexpr int NTHREADS = 320;
-constexpr float LOG2E = 1.4426950408889634f;
 constexpr float GROW_LOG2 = 8.f; // lazy-rescale threshold (log2 units)
 
 constexpr int SM_Q = 0;                               // [2 bufs][2 tiles] x 16 KB
@@ -78,7 +75,6 @@ static_assert(sizeof(Bars) <= 256, "barrier block");
 // of a tile carry (4, 3, 2, 1) and (1, 2, 3, 4) live 32-key groups and every chunk waits for its
 // slowest quadrant (8 group-times for 5 groups of work); interleaved it is (3, 3, 2, 2) / (2, 2, 3, 3).
 // Chunk order of a pair: A(k0,k2), B(k0,k2), A(k1,k3), B(k1,k3), then the global-token chunks (shared).
-constexpr int RAD = 64;
 struct Pair {
   int b, h, i0;        // first row of tile A
   int nglob;           // global-token chunks
@@ -111,12 +107,6 @@ __device__ __forceinline__ void chunk_blocks(const Pair& q, int pc, int& ka, int
     ka = (pc - NBAND) * TK;
     kb = ka + 64;
   }
-}
-
-__device__ __forceinline__ int slot_of_id(int id, int D) {   // ids 0..2D in offset order -D..D, others unchanged
-  if (id <= D) return D + id;
-  if (id <= 2 * D) return 2 * D - id;
-  return id;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -180,10 +170,15 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           chunk_blocks(q, pc, ka, kb);
           const CUtensorMap* mk = pc < NBAND ? &map_k : &map_gk;
           const CUtensorMap* mv = pc < NBAND ? &map_v : &map_gv;
-          tma_load_4d(ks, mk, &bars->kv_full[st], 0, ka, q.h, q.b);              // boxes of 64 keys
-          tma_load_4d(ks + 64 * 128, mk, &bars->kv_full[st], 0, kb, q.h, q.b);
-          tma_load_4d(vs, mv, &bars->kv_full[st], 0, ka, q.h, q.b);
-          tma_load_4d(vs + 64 * 128, mv, &bars->kv_full[st], 0, kb, q.h, q.b);
+          // A box that lies entirely outside the tensor is not issued as such: its start is clamped so that
+          // at least one row is in range (the kernel's own geometry marks those keys dead, and what lands
+          // in shared memory is finite either way: zero fill or real rows)
+          const int klen = (pc < NBAND) ? p.L : p.G;
+          const int ca = min(max(ka, -63), klen - 1), cb = min(max(kb, -63), klen - 1);
+          tma_load_4d(ks, mk, &bars->kv_full[st], 0, ca, q.h, q.b);              // boxes of 64 keys
+          tma_load_4d(ks + 64 * 128, mk, &bars->kv_full[st], 0, cb, q.h, q.b);
+          tma_load_4d(vs, mv, &bars->kv_full[st], 0, ca, q.h, q.b);
+          tma_load_4d(vs + 64 * 128, mv, &bars->kv_full[st], 0, cb, q.h, q.b);
         }
       }
     }
@@ -514,7 +509,10 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                       [&](int jj) { return (unsigned)(jj - jlo) < span; });
                 } else {
                   run([&](int jj) { return base[min(max(sD + jj, 0), 2 * D) * TM] - m2; },
-                      [&](int jj) { return (unsigned)(jj - jlo) < span && __shfl_sync(0xffffffffu, ceg, jj) == q_e; });
+                      [&](int jj) {   // the shuffle is executed by every lane (no short-circuit in front of it)
+                        const bool same = __shfl_sync(0xffffffffu, ceg, jj) == q_e;
+                        return same && (unsigned)(jj - jlo) < span;
+                      });
                 }
               } break;
               default: {
@@ -527,11 +525,16 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 } else {
                   const float k0 = cX - m2, k1 = cX1 - m2;
                   run([&](int jj) { return sp == jj ? k1 : k0; },
-                      [&](int jj) { return jj < jhi && __shfl_sync(0xffffffffu, ceg, jj) == q_e; });
+                      [&](int jj) {
+                        const bool same = __shfl_sync(0xffffffffu, ceg, jj) == q_e;
+                        return same && jj < jhi;
+                      });
                 }
               } break;
             }
           }
+          // the per-lane table reads of the diagonal forms may leave the warp diverged: tcgen05.st is .aligned
+          __syncwarp();
           // P of keys [32g, 32g+32) -> packed columns [32g, 32g+16) of the same group's score columns
           tmem_st16(t_base + T_S + 32 * g, pk);
         }

@@ -48,13 +48,17 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st);
 // Long rows, forward: bf16, d = 64, example-id masks, 1-D band ids + sentence cross ids, R <= 32, no dropout.
 bool gl2_fwd_long_supported(const FwdArgs& a, int dtype, int d);
 int gl2_launch_fwd_long(const FwdArgs& a, cudaStream_t st);
+// Long rows, query-centric backward (dQ, table-gradient partials, row records for the key-centric pass).
+// `rowstat` / `rec_ws` are the workspace areas tc_launch_bwd_q carves (tc_bwd_prep_kernel has filled rowstat).
+bool gl2_bwd_q_long_supported(const BwdQArgs& a, int dtype, int d);
+int gl2_launch_bwd_q_long(const BwdQArgs& a, const float4* rowstat, float* rec_ws, int lp, int rw, cudaStream_t st);
 
 // ---- backward (tc_bwd.cu) -------------------------------------------------------------------
 // Extra workspace (bytes) of one row set: rowstat [B,H,Lpad] float4 + allrel [B,H,Lpad,R4] f32.
 size_t tc_bwd_rows_ws_bytes(int B, int H, int len, int R);
 bool tc_bwd_q_supported(const BwdQArgs& a, int dtype, int d);
 // Query-centric pass: dq, dallrel (a.dallrel, [B,H,Lq,R]); publishes rowstat / allrel into `ws`.
-int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st);
+int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st, bool allow_gl2 = false);
 // Key-centric pass: dk, dv.  ws[s] is the workspace tc_launch_bwd_q filled for query source s.
 int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st);
 

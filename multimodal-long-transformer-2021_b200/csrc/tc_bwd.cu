@@ -1798,7 +1798,7 @@ struct BkLaunch {
 };
 }  // namespace
 
-int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
+int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st, bool allow_gl2) {
   static PerDeviceOnce once;
   const int ae = once.run([] {
     cudaError_t e = BqLaunch<2, false>::attrs();
@@ -1840,6 +1840,9 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st) {
     cudaError_t pe = cudaGetLastError();
     if (pe != cudaSuccess) return (int)pe;
   }
+  // compact global-local long rows: the persistent specialised kernel (gl2_bwd_q.cu), same workspace format
+  if (allow_gl2 && gl2_bwd_q_long_supported(a, MLT_BF16, 64))
+    return gl2_launch_bwd_q_long(a, p.rowstat, p.rec_ws, p.lp, p.rw, st);
   dim3 grid((a.rows.len + TM - 1) / TM, a.H, a.B);
   // chunks per tile: with many chunks (dense global rows) two warp sets on alternate chunks win;
   // with few (long rows: band + G/64) the extra per-tile prologue work does not pay off.
