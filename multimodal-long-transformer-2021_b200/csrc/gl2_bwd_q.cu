@@ -7,14 +7,16 @@
 //   dQ += dallrel.E,  per-tile table-gradient partial dallrel^T.Q,  and the exponent-ready row records the
 //   key-centric pass consumes (same workspace format as tc_bwd.cu, so the two families interoperate).
 //
-// One CTA per SM, 320 threads, persistent over 128-row query tiles:
-//   warps 0-7   elementwise: warp w owns row quadrant (w & 3) and the column half (w >> 2) of every
-//               128-key chunk (two threads per row: the backward needs no row reductions)
-//   warp  8     TMA producer: Q / dO / E tiles of the NEXT tile while the current one computes; K/V chunks
+// One CTA per SM, 576 threads, persistent over 128-row query tiles:
+//   warps 0-15  elementwise: warp w owns row quadrant (w & 3) and the 32-key group (w >> 2) of every
+//               128-key chunk (four threads per row: the backward needs no row reductions, and with only
+//               ~10 warps per SM these kernels are bound by per-warp latency, not by issue slots)
+//   warp 16     TMA producer: Q / dO / E tiles of the NEXT tile while the current one computes; K/V chunks
 //               (two interleaved 64-key blocks each, see gl2_fwd.cu) through a 3-stage ring
-//   warp  9     MMA issuer.  S runs one chunk ahead in a second buffer; dP_c follows dQ_{c-1}
-// TMEM (512 columns): S0 [128] S1 [128] dP / dS [128] dQ [64] allrel / dallrel [32]; the table-gradient
-// tile (M = 64) reuses S0 after the last chunk.
+//   warp 17     MMA issuer.  S runs one chunk ahead in a second buffer; dP_c follows dQ_{c-1}
+// TMEM (512 columns): S0 [128] S1 [128] dP / dS [128] dQ [64] allrel / dallrel 2 x [32]; the table-gradient
+// tile (M = 64) reuses S1 after the last chunk.  The MMA warp starts the next tile (allrel, S_0, dP_0) as
+// soon as this tile's last MMAs are issued, i.e. under the elementwise warps' epilogue.
 #include "tc_api.cuh"
 
 #include "gl2_geom.cuh"
@@ -28,8 +30,9 @@ namespace bq {
 
 using namespace ptx;
 
-constexpr int NTHREADS = 320;
-constexpr int NEW = 256;                 // elementwise threads
+constexpr int NEWARPS = 16;              // elementwise warps
+constexpr int NTHREADS = (NEWARPS + 2) * 32;
+constexpr int NEW = NEWARPS * 32;        // elementwise threads
 constexpr int RSF = 68;                  // record field stride (floats), see tc_bwd.cu
 
 constexpr int SM_Q = 0;                               // [2 bufs] x (Q 16 KB + dO 16 KB)
@@ -38,15 +41,31 @@ constexpr int SM_KV = SM_E + 2 * 32 * 128;            // NST x (K 16 KB + V 16 K
 constexpr int SM_REL = SM_KV + NST * 2 * TK * 128;    // [32 slots][128 rows] f32, log2 units
 constexpr int SM_BIN = SM_REL + 32 * TM * 4;          // [32 slots][128 rows] f32
 constexpr int SM_A = SM_BIN + 32 * TM * 4;            // dallrel^T tile, bf16 [128 rows][64 ids] SW128 (16 KB)
-constexpr int SM_CMB = SM_A + TM * 128;               // class sums of the second column half [4][128] f32
-constexpr int SM_BS = SM_CMB + 4 * TM * 4;            // bias partial sums [4 quadrants][32]
+constexpr int SM_CMB = SM_A + TM * 128;               // class sums of column groups 1..3: [3][4][128] f32
+constexpr int SM_BS = SM_CMB + 3 * 4 * TM * 4;        // bias partial sums [4 quadrants][32]
 constexpr int SM_BIAS = SM_BS + 4 * 32 * 4;           // [32] bias * scale * log2e
 constexpr int SM_BAR = SM_BIAS + 32 * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;
 static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t T_S0 = 0, T_S1 = 128, T_DP = 256, T_DQ = 384, T_REL = 448, T_DE = 0;
+// allrel / dallrel alternate between two 32-column buffers so that the next tile's allrel MMA can run under
+// this tile's epilogue; the table-gradient tile (M = 64) lands in S1, which the next tile needs last
+constexpr uint32_t T_S0 = 0, T_S1 = 128, T_DP = 256, T_DQ = 384, T_REL = 448, T_DE = T_S1;
+
+#ifdef MLT_TC_TRACE
+__device__ long long g_trace_q[3][1024];
+__device__ int g_trace_n[3];
+#define GTRACE(role, code)                                                               \
+  do {                                                                                   \
+    if (blockIdx.x == 3) {                                                               \
+      const int n_ = g_trace_n[role];                                                    \
+      if (n_ < 511) { g_trace_q[role][2 * n_] = clock64(); g_trace_q[role][2 * n_ + 1] = (code); g_trace_n[role] = n_ + 1; } \
+    }                                                                                    \
+  } while (0)
+#else
+#define GTRACE(role, code) do {} while (0)
+#endif
 
 struct Params {
   int B, H, L, G, R, D;
@@ -125,7 +144,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     mbar_init(&bars->tile_done, NEW);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == NEWARPS + 1) tmem_alloc<512>(&bars->tmem_base);
   // id columns 32..63 of the dallrel^T tile are never written: zero the tile once
   for (int x = tid; x < TM * 128 / 16; x += NTHREADS) reinterpret_cast<uint4*>(smem + SM_A)[x] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
@@ -134,7 +153,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == NEWARPS) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0, kvc = 0;
@@ -150,7 +169,9 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int nc = 2 + q.nglob;
         for (int c = 0; c < nc; ++c, ++kvc) {
           const int st = kvc % NST;
+          GTRACE(2, 200 + c);
           mbar_wait(&bars->kv_empty[st], ((kvc / NST) & 1) ^ 1);
+          GTRACE(2, 210 + c);
           uint8_t* ks = smem + SM_KV + st * (2 * TK * 128);
           uint8_t* vs = ks + TK * 128;
           mbar_arrive_expect_tx(&bars->kv_full[st], 2 * TK * 128);
@@ -170,7 +191,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == NEWARPS + 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(TM, TK, 0, 0);
@@ -180,20 +201,39 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const uint32_t a_addr = smem_u32(smem + SM_A);
       int it = 0, kv_base = 0;
       uint32_t ds_cnt = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const Tile q = make_tile(p, t);
-        const int buf = it & 1;
-        const int nc = 2 + q.nglob;
-        // the elementwise warps have read dQ / dE / allrel of the previous tile
-        mbar_wait(&bars->tile_done, (it & 1) ^ 1);
-        mbar_wait(&bars->q_full[buf], (it >> 1) & 1);
+      // tile prologue on the tensor core: allrel = Q.E^T, S_0, dP_0 (issued one tile ahead of the elementwise warps)
+      auto kv_stage = [&](int base, int c) { return (base + c) % NST; };
+      auto start_tile = [&](int it_, int base) {
+        const int buf = it_ & 1;
+        mbar_wait(&bars->q_full[buf], (it_ >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t q_addr = smem_u32(smem + SM_Q + buf * 2 * TM * 128), do_addr = q_addr + TM * 128;
         const uint32_t e_addr = smem_u32(smem + SM_E + buf * 32 * 128);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem + T_REL, sdesc(q_addr).at(kk * 32), sdesc(e_addr).at(kk * 32), idesc_r, kk > 0);
+          umma_ss(tmem + T_REL + 32 * (it_ & 1), sdesc(q_addr).at(kk * 32), sdesc(e_addr).at(kk * 32), idesc_r, kk > 0);
         umma_commit(&bars->rel_full);
+        const int st = kv_stage(base, 0);
+        mbar_wait(&bars->kv_full[st], (base / NST) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smem + SM_KV + st * (2 * TK * 128)), v_addr = k_addr + TK * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + T_S0, sdesc(q_addr).at(kk * 32), sdesc(k_addr).at(kk * 32), idesc_s, kk > 0);
+        umma_commit(&bars->s_full[0]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem + T_DP, sdesc(do_addr).at(kk * 32), sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
+        umma_commit(&bars->dp_full);
+      };
+      if ((int)blockIdx.x < p.total_tiles) start_tile(0, 0);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const Tile q = make_tile(p, t);
+        const int buf = it & 1;
+        const int nc = 2 + q.nglob;
+        const uint32_t q_addr = smem_u32(smem + SM_Q + buf * 2 * TM * 128), do_addr = q_addr + TM * 128;
+        const uint32_t e_addr = smem_u32(smem + SM_E + buf * 32 * 128);
+        const uint32_t t_rel = tmem + T_REL + 32 * (it & 1);
         auto kv_addr = [&](int c) { return smem_u32(smem + SM_KV + ((kv_base + c) % NST) * (2 * TK * 128)); };
         auto issue_s = [&](int c) {
           mbar_wait(&bars->kv_full[(kv_base + c) % NST], ((kv_base + c) / NST) & 1);
@@ -211,8 +251,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             umma_ss(tmem + T_DP, sdesc(do_addr).at(kk * 32), sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
           umma_commit(&bars->dp_full);
         };
-        issue_s(0);
-        issue_dp(0);
+        // S1 holds the previous tile's table-gradient tile until the elementwise warps have read it
+        mbar_wait(&bars->tile_done, (it & 1) ^ 1);
         for (int c = 0; c < nc; ++c) {
           if (c + 1 < nc) issue_s(c + 1);
           mbar_wait(&bars->ds_full, ds_cnt & 1);
@@ -231,13 +271,16 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
-          umma_ts(tmem + T_DQ, tmem + T_REL + kk * 8, sdesc(e_addr).at(kk * 2048), idesc_dq, 1u);
+          umma_ts(tmem + T_DQ, t_rel + kk * 8, sdesc(e_addr).at(kk * 2048), idesc_dq, 1u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_ss(tmem + T_DE, sdesc(a_addr).at(kk * 2048), sdesc(q_addr).at(kk * 2048), idesc_de, kk > 0);
         umma_commit(&bars->dq_full);
         umma_commit(&bars->q_empty[buf]);
         kv_base += nc;
+        // next tile's prologue under this tile's epilogue: allrel -> the other buffer, S_0 -> S0 (free since the
+        // last even chunk), dP_0 -> dP (its dS was consumed by the dQ MMAs above: MMAs execute in issue order)
+        if (t + (int)gridDim.x < p.total_tiles) start_tile(it + 1, kv_base);
       }
     }
   } else {
@@ -262,6 +305,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const int i = q.i0 + row;
       const bool row_ok = i < p.L;
       const int a_lo = q.i0 + quad * 32;
+      if (tid == 0) GTRACE(0, 0);
       int q_e = -2, q_sent = -1;
       float nm2l = -INFINITY, delta = 0.f;
       if (row_ok) {
@@ -278,8 +322,10 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // ---- relative table (log2 units) + row records; the four (half 0) warps extract allrel ----
       const int rs_stride = p.rw + 4;
       float* rec_row = p.rec_ws + (((int64_t)(b * p.H + h) * (p.lp >> 6) + (i >> 6)) * rs_stride) * RSF + (i & 63);
-      if (hf == 0) {
-        if (row_ok) {
+      const uint32_t t_rel = t_base + T_REL + 32 * (it & 1);
+      {
+        // every column group extracts 8 of the 32 ids (table slots + the records of the key-centric pass)
+        if (hf == 0 && row_ok) {
           rec_row[0] = nm2l;
           rec_row[RSF] = -INFINITY;    // masked elements: every row holds a real maximum, p == 0
           rec_row[2 * RSF] = delta;
@@ -287,17 +333,19 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         mbar_wait_warp(&bars->rel_full, it & 1);
         tc_fence_after_sync();
-        uint32_t v[32];
-        tmem_ld32(t_base + T_REL, v);
+        uint32_t v[8];
+        tmem_ld8(t_rel + 8 * hf, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const float val = x < R ? fmaf(__uint_as_float(v[x]), scale2, bias_s[x]) : 0.f;
+        for (int x8 = 0; x8 < 8; ++x8) {
+          const int x = 8 * hf + x8;
+          const float val = x < R ? fmaf(__uint_as_float(v[x8]), scale2, bias_s[x]) : 0.f;
           rel_s[slot_of_id(x, D) * TM + row] = val;
           if (row_ok && x < p.rw) rec_row[(4 + x) * RSF] = val + nm2l;
         }
       }
       named_bar_sync(1, NEW);   // rel_s visible to both column halves
+      if (tid == 0) GTRACE(0, 1);
       const float cP = rel_s[(2 * D) * TM + row] + nm2l;
       const float cN = rel_s[0 * TM + row] + nm2l;
       const float cX = rel_s[(2 * D + 1) * TM + row] + nm2l;
@@ -312,27 +360,24 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const bool band = c < 2;
         int ka, kb;
         chunk_blocks(q, c, ka, kb);
-        const int kbase = hf ? kb : ka;            // this warp's 64-key block of the chunk
+        const int g0 = ((hf < 2) ? ka : kb) + 32 * (hf & 1);   // this warp's 32-key group of the chunk
         const int klen = band ? p.L : p.G;
-        int ce[2];
+        int ceg;
         {
           const int32_t* eids = (band ? p.long_eid + (int64_t)b * p.L : p.glob_eid + (int64_t)b * p.G);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = kbase + 32 * g + lane;
-            ce[g] = (col >= 0 && col < klen) ? __ldg(eids + col) : -1;
-          }
+          const int col = g0 + lane;
+          ceg = (col >= 0 && col < klen) ? __ldg(eids + col) : -1;
         }
+        if (tid == 0) GTRACE(0, 10 + c);
         mbar_wait_warp(&bars->s_full[c & 1], s_par[c & 1]);
+        if (tid == 0) GTRACE(0, 20 + c);
         s_par[c & 1] ^= 1;
         tc_fence_after_sync();
         bool dp_ready = false;
-        const uint32_t t_s = t_base + ((c & 1) ? T_S1 : T_S0) + 64 * hf;
-        const uint32_t t_dp = t_base + T_DP + 64 * hf;
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-          const int g0 = kbase + 32 * g;
-          const int ceg = g ? ce[1] : ce[0];
+        const uint32_t t_s = t_base + ((c & 1) ? T_S1 : T_S0) + 32 * hf;
+        const uint32_t t_dp = t_base + T_DP + 32 * hf;
+        {
+          constexpr int g = 0;
           const int c0 = __shfl_sync(0xffffffffu, ceg, 0);
           const bool uni = __all_sync(0xffffffffu, ceg == c0) && c0 != -1;
           // ---- classify (warp-uniform), same forms as the forward (gl2_fwd.cu) ----
@@ -511,43 +556,49 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->ds_full);
+        if (tid == 0) GTRACE(0, 30 + c);
       }
       // ---- epilogue ----
       // class sums: the second column half hands its partial sums to the first
-      if (hf == 1) {
-        cmb[0 * TM + row] = accP;
-        cmb[1 * TM + row] = accN;
-        cmb[2 * TM + row] = accX;
-        cmb[3 * TM + row] = accX1;
+      if (hf > 0) {
+        float* cm = cmb + (hf - 1) * 4 * TM;
+        cm[0 * TM + row] = accP;
+        cm[1 * TM + row] = accN;
+        cm[2 * TM + row] = accX;
+        cm[3 * TM + row] = accX1;
       }
       named_bar_sync(1, NEW);
       if (hf == 0) {
-        bins[(2 * D) * TM + row] = accP + cmb[0 * TM + row];       // id D    (offset >= D)
-        bins[0 * TM + row] = accN + cmb[1 * TM + row];             // id 2D   (offset <= -D)
-        bins[(2 * D + 1) * TM + row] = accX + cmb[2 * TM + row];
-        bins[(2 * D + 2) * TM + row] = accX1 + cmb[3 * TM + row];
+        auto sum3 = [&](int k, float a0) {   // fixed order: deterministic
+          return ((a0 + cmb[k * TM + row]) + cmb[(4 + k) * TM + row]) + cmb[(8 + k) * TM + row];
+        };
+        bins[(2 * D) * TM + row] = sum3(0, accP);       // id D    (offset >= D)
+        bins[0 * TM + row] = sum3(1, accN);             // id 2D   (offset <= -D)
+        bins[(2 * D + 1) * TM + row] = sum3(2, accX);
+        bins[(2 * D + 2) * TM + row] = sum3(3, accX1);
       }
       named_bar_sync(1, NEW);   // bins complete
+      if (tid == 0) GTRACE(0, 40);
       {
-        // each column half packs 16 ids: bf16 A operand (TMEM) for dQ += dallrel.E, the dallrel^T tile for the
-        // table-gradient MMA, and the bias partial sums of the warp's 32 rows
-        const int c0 = 16 * hf;
-        float w16[16];
+        // each of the four column groups packs 8 ids: bf16 A operand (TMEM) for dQ += dallrel.E, the
+        // dallrel^T tile for the table-gradient MMA, and the bias partial sums of the warp's 32 rows
+        const int c0 = 8 * hf;
+        float w16[8];
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
+        for (int x = 0; x < 8; ++x) {
           const int pid = c0 + x;
           w16[x] = (pid < R && row_ok) ? bins[slot_of_id(pid, D) * TM + row] : 0.f;
         }
-        uint32_t pk8[8];
+        uint32_t pk4[4];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) pk8[x] = pack_bf16x2(w16[2 * x], w16[2 * x + 1]);
-        tmem_st8(t_base + T_REL + c0 / 2, pk8);
+        for (int x = 0; x < 4; ++x) pk4[x] = pack_bf16x2(w16[2 * x], w16[2 * x + 1]);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_rel + c0 / 2),
+                     "r"(pk4[0]), "r"(pk4[1]), "r"(pk4[2]), "r"(pk4[3])
+                     : "memory");
+        *reinterpret_cast<uint4*>(a_tile + row * 128 + (((c0 >> 3) ^ (row & 7)) << 4)) =
+            make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
 #pragma unroll
-        for (int y = 0; y < 2; ++y)
-          *reinterpret_cast<uint4*>(a_tile + row * 128 + ((((c0 >> 3) + y) ^ (row & 7)) << 4)) =
-              make_uint4(pk8[4 * y], pk8[4 * y + 1], pk8[4 * y + 2], pk8[4 * y + 3]);
-#pragma unroll
-        for (int x = 0; x < 16; ++x) {
+        for (int x = 0; x < 8; ++x) {
           float r = w16[x];
           r += __shfl_xor_sync(0xffffffffu, r, 16);
           r += __shfl_xor_sync(0xffffffffu, r, 8);
@@ -561,36 +612,36 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_before_sync();
         mbar_arrive(&bars->dar_full);
       }
+      if (tid == 0) GTRACE(0, 41);
       mbar_wait_warp(&bars->dq_full, it & 1);
+      if (tid == 0) GTRACE(0, 42);
       tc_fence_after_sync();
       const int64_t pidx = ((int64_t)(b * p.tiles_per_bh + q.tile) * p.H + h);
-      if (hf == 0) {
-        // table-gradient tile: M = 64 accumulator rows live in lanes {0-15, 32-47, 64-79, 96-111}
+      {
+        // table-gradient tile: M = 64 accumulator rows live in lanes {0-15, 32-47, 64-79, 96-111}; each column
+        // group stores 16 of the 64 columns
         const int pid = quad * 16 + lane;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld32(t_base + T_DE + hh * 32, v);
-          tmem_wait_ld();
-          if (lane < 16 && pid < R) {
-            float4* dst = reinterpret_cast<float4*>(p.tg_partial + (pidx * R + pid) * 64 + hh * 32);
+        uint32_t v[16];
+        tmem_ld16(t_base + T_DE + hf * 16, v);
+        tmem_wait_ld();
+        if (lane < 16 && pid < R) {
+          float4* dst = reinterpret_cast<float4*>(p.tg_partial + (pidx * R + pid) * 64 + hf * 16);
 #pragma unroll
-            for (int x = 0; x < 8; ++x)
-              dst[x] = make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
-                                   __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
-          }
+          for (int x = 0; x < 4; ++x)
+            dst[x] = make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
+                                 __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
         }
       }
       named_bar_sync(1, NEW);   // bias sums of all four quadrants are in shared memory
       if (tid < R) p.tg_partial_bias[pidx * R + tid] = (bs[tid] + bs[32 + tid]) + (bs[64 + tid] + bs[96 + tid]);
       {
-        uint32_t v[32];
-        tmem_ld32(t_base + T_DQ + 32 * hf, v);
+        uint32_t v[16];
+        tmem_ld16(t_base + T_DQ + 16 * hf, v);
         tmem_wait_ld();
         if (row_ok) {
-          __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.d_q, b, i, h) + 32 * hf;
+          __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.d_q, b, i, h) + 16 * hf;
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
+          for (int x = 0; x < 2; ++x) {
             uint4 o4;
             o4.x = pack_bf16x2(__uint_as_float(v[8 * x + 0]) * p.scale, __uint_as_float(v[8 * x + 1]) * p.scale);
             o4.y = pack_bf16x2(__uint_as_float(v[8 * x + 2]) * p.scale, __uint_as_float(v[8 * x + 3]) * p.scale);
@@ -602,15 +653,23 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       tc_fence_before_sync();
       mbar_arrive(&bars->tile_done);
+      if (tid == 0) GTRACE(0, 43);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == NEWARPS + 1) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace bq
 }  // namespace gl2
+
+#ifdef MLT_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_gl2q(long long* out, int* n) {
+  cudaMemcpyFromSymbol(n, gl2::bq::g_trace_n, sizeof(int) * 3);
+  return (int)cudaMemcpyFromSymbol(out, gl2::bq::g_trace_q, sizeof(long long) * 3 * 1024);
+}
+#endif
 
 bool gl2_bwd_q_long_supported(const BwdQArgs& a, int dtype, int d) {
   FwdArgs f{};

@@ -5,13 +5,17 @@
 // cross ids towards the global tokens, relative vocabulary <= 32.  Everything else keeps the general
 // kernels of tc_fwd.cu.
 //
-// Structure (one CTA per SM, 320 threads, persistent over PAIRS of adjacent 128-row query tiles):
-//   warps 0-3   softmax warpgroup 0: tile A of the pair, thread t owns query row t == TMEM lane t
-//   warps 4-7   softmax warpgroup 1: tile B of the pair
-//   warp  8     TMA producer: Q tiles + relative-embedding tile of the NEXT pair while the current one
+// Structure (one CTA per SM, 576 threads, persistent over PAIRS of adjacent 128-row query tiles):
+//   warps 0-7   softmax group 0: tile A of the pair.  Warp w owns row quadrant (w & 3) == TMEM lanes and the
+//               column half ((w >> 2) & 1) of every 128-key chunk: two threads per row.  (With one thread
+//               per row the kernel ran at 36 % issue utilisation on ~10 warps per SM: per-warp latency, not
+//               issue slots, was the limit.)  The two threads of a row agree on the softmax reference through
+//               one shared-memory exchange per chunk.
+//   warps 8-15  softmax group 1: tile B of the pair
+//   warp 16     TMA producer: Q tiles + relative-embedding tile of the NEXT pair while the current one
 //               computes, K/V chunks of 128 keys through a 3-stage ring shared by both tiles (the band
 //               chunks of the two tiles overlap; the global-token chunks are common)
-//   warp  9     MMA issuer (one elected lane): per tile S = Q.K_c^T (M 128, N 128, K 64) and
+//   warp 17     MMA issuer (one elected lane): per tile S = Q.K_c^T (M 128, N 128, K 64) and
 //               O += P_c.V_c (P from TMEM), the two tiles ping-pong through the tensor core so that
 //               one warpgroup's softmax covers the other's MMAs
 // TMEM (512 columns): per warpgroup S / P [128] + O [64] + allrel [32].
@@ -34,7 +38,8 @@ namespace gl2 {
 
 using namespace ptx;
 
-constexpr int NTHREADS = 320;
+constexpr int NSW = 16;                   // softmax warps: 2 tile slots x 4 row quadrants x 2 column halves
+constexpr int NTHREADS = (NSW + 2) * 32;
 constexpr float GROW_LOG2 = 8.f; // lazy-rescale threshold (log2 units)
 
 constexpr int SM_Q = 0;                               // [2 bufs][2 tiles] x 16 KB
@@ -42,7 +47,8 @@ constexpr int SM_E = SM_Q + 4 * TM * 128;             // [2 bufs] x 4 KB (32 ids
 constexpr int SM_KV = SM_E + 2 * 32 * 128;            // NST x (K 16 KB + V 16 KB)
 constexpr int SM_REL = SM_KV + NST * 2 * TK * 128;    // [2 tiles][32 slots][128 rows] f32 (log2 units)
 constexpr int SM_BIAS = SM_REL + 2 * 32 * TM * 4;     // [2 tiles][32] f32
-constexpr int SM_BAR = SM_BIAS + 2 * 32 * 4;
+constexpr int SM_XCH = SM_BIAS + 2 * 32 * 4;          // [2 parities][2 tiles][2 halves][128 rows] f32: pair exchange
+constexpr int SM_BAR = SM_XCH + 2 * 2 * 2 * TM * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;
 
@@ -125,9 +131,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&bars->q_empty[s], 1);
       mbar_init(&bars->rel_full[s], 1);
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->p_full[s], 128);
+      mbar_init(&bars->p_full[s], 256);
       mbar_init(&bars->o_full[s], 1);
-      mbar_init(&bars->o_empty[s], 128);
+      mbar_init(&bars->o_empty[s], 256);
     }
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars->kv_full[s], 1);
@@ -135,13 +141,13 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == NSW + 1) tmem_alloc<512>(&bars->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == NSW) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       prefetch_tensormap(&map_q);
@@ -182,7 +188,7 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == NSW + 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(TM, TK, 0, 0);
@@ -266,17 +272,21 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
   } else {
-    // ===================== softmax warpgroups =====================
-    const int w = warp >> 2;                 // tile slot
+    // ===================== softmax groups =====================
+    const int w = warp >> 3;                 // tile slot
+    const int hf = (warp >> 2) & 1;          // column half of every chunk
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     const uint32_t t_base = tmem + w * T_WG + lane_sel;
     float* rel_s = reinterpret_cast<float*>(smem + SM_REL) + w * 32 * TM;   // [slot][row], log2 units
     float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS) + w * 32;
+    float* xch = reinterpret_cast<float*>(smem + SM_XCH) + w * 2 * TM;      // [parity][tile][half][row]
+    const uint32_t bar_group = 1 + w;                  // 256 threads of the tile slot
+    const uint32_t bar_pair = 3 + w * 4 + quad;        // the two warps that share 32 rows
     const float scale2 = p.scale * LOG2E;
     const int D = p.D, R = p.R, rad = p.radius;
-    uint32_t s_par = 0, tile_par = 0;   // parities of s_full / per-tile barriers
+    uint32_t s_par = 0, tile_par = 0, xpar = 0;   // parities of s_full / per-tile barriers / exchange buffer
     for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
       const Pair q = make_pair(p, pair);
       if (!tile_exists(q, w)) continue;
@@ -290,9 +300,10 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         q_e = __ldg(p.long_eid + (int64_t)b * p.L + i);
         q_sent = __ldg(p.sent + (int64_t)b * p.L + i);
       }
-      // ---- per-tile relative table: rel_s[slot][row] = (allrel[id] * scale + bias[id] * scale) * log2e
-      if (row < 32) bias_s[row] = row < R ? __bfloat162float(p.bias[row * p.H + h]) * scale2 : 0.f;
-      named_bar_sync(1 + w, 128);
+      // ---- per-tile relative table: rel_s[slot][row] = (allrel[id] * scale + bias[id] * scale) * log2e;
+      // each column half builds 16 of the 32 ids
+      if (hf == 0 && row < 32) bias_s[row] = row < R ? __bfloat162float(p.bias[row * p.H + h]) * scale2 : 0.f;
+      named_bar_sync(bar_group, 256);
       mbar_wait_warp(&bars->rel_full[w], tile_par);
       tc_fence_after_sync();
       float relmax = 0.f;   // ids outside [0, R) contribute 0, and so may any key: the bound includes 0
@@ -303,11 +314,11 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           const float val = x < R ? fmaf(__uint_as_float(v[x]), scale2, bias_s[x]) : 0.f;
-          rel_s[slot_of_id(x, D) * TM + row] = val;
+          if ((x >> 4) == hf) rel_s[slot_of_id(x, D) * TM + row] = val;
           relmax = fmaxf(relmax, val);
         }
       }
-      // a thread only reads its own column of rel_s: no barrier needed
+      named_bar_sync(bar_group, 256);   // both halves of the table are visible
       const float cP = rel_s[(2 * D) * TM + row];        // offset >= D   (id D      -> slot 2D)
       const float cN = rel_s[0 * TM + row];              // offset <= -D  (id 2D     -> slot 0)
       const float cX = rel_s[(2 * D + 1) * TM + row];    // cross, other sentence
@@ -328,12 +339,13 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         chunk_blocks(q, pc, ka, kb);
         const int klen = band ? p.L : p.G;
         // column example ids, one per lane and group (issued before the wait: latency hidden)
-        int ce[4];
+        const int kbase = hf ? kb : ka;   // this warp's 64-key block of the chunk
+        int ce[2];
         {
           const int32_t* eids = (band ? p.long_eid + (int64_t)b * p.L : p.glob_eid + (int64_t)b * p.G);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = (g < 2 ? ka : kb) + 32 * (g & 1) + lane;
+          for (int g = 0; g < 2; ++g) {
+            const int col = kbase + 32 * g + lane;
             ce[g] = (col >= 0 && col < klen) ? __ldg(eids + col) : -1;
           }
         }
@@ -344,11 +356,11 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // form: 0 dead | 1 FAST: all live, uniform mask, constant relative term | band, mask uniform, group
         // inside the sequence, by G0 = first key - first row of the warp: 2 (G0 = -64: lower band edge),
         // 3 (+64: upper band edge), 4 (-32), 5 (0: the diagonal), 6 (+32) | 7 general band | 8 general global
-        int form[4];
-        int ce0[4];
+        int form[2];
+        int ce0[2];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int g0 = (g < 2 ? ka : kb) + 32 * (g & 1);
+        for (int g = 0; g < 2; ++g) {
+          const int g0 = kbase + 32 * g;
           ce0[g] = __shfl_sync(0xffffffffu, ce[g], 0);
           const bool uni = __all_sync(0xffffffffu, ce[g] == ce0[g]) && ce0[g] != -1;
           int f;
@@ -375,21 +387,19 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         // ---- pass 1: upper bound of the chunk's row maximum from the raw accumulator ----
         float xmax = -INFINITY;
-#pragma unroll
-        for (int gp = 0; gp < 2; ++gp) {
-          if (form[2 * gp] == 0 && form[2 * gp + 1] == 0) continue;
+        const uint32_t t_s = t_base + T_S + 64 * hf;
+        if (form[0] != 0 || form[1] != 0) {
           uint32_t v[64];
-          tmem_ld32(t_base + T_S + 64 * gp, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld32(t_base + T_S + 64 * gp + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_wait_ld();
 #pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            const int g = 2 * gp + gg;
+          for (int g = 0; g < 2; ++g) {
             if (form[g] == 0) continue;
             float r4[4];
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-              const uint32_t* u = v + 32 * gg + 8 * y;
+              const uint32_t* u = v + 32 * g + 8 * y;
               r4[y] = fmaxf(fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), __uint_as_float(u[2]));
               r4[y] = fmaxf(fmaxf(r4[y], __uint_as_float(u[3])), __uint_as_float(u[4]));
               r4[y] = fmaxf(fmaxf(r4[y], __uint_as_float(u[5])), __uint_as_float(u[6]));
@@ -400,7 +410,13 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             if (!(!(form[g] & 16) && q_e != ce0[g])) xmax = fmaxf(xmax, gm);
           }
         }
-        const float u2 = fmaf(xmax, scale2, relmax);   // -inf when nothing is live for this row
+        // the two threads of a row exchange their bounds: one reference for the whole row
+        float* xb = xch + xpar * (2 * 2 * TM);
+        xpar ^= 1;
+        const float mine = fmaf(xmax, scale2, relmax);
+        xb[hf * TM + row] = mine;
+        named_bar_sync(bar_pair, 64);
+        const float u2 = fmaxf(mine, xb[(hf ^ 1) * TM + row]);   // -inf when nothing is live for this row
         // ---- reference update, lazy rescale of O ----
         const bool fresh = (m2 == -INFINITY);
         const bool grow = !fresh && (u2 - m2 > GROW_LOG2);
@@ -410,32 +426,31 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const float f = grow ? ex2(m2 - u2) : 1.f;
           if (grow) m2 = u2;
           l *= f;
-#pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
+          {   // each half rescales its 32 columns of O
             uint32_t v[32];
-            tmem_ld32(t_base + T_O + hh * 32, v);
+            tmem_ld32(t_base + T_O + hf * 32, v);
             tmem_wait_ld();
 #pragma unroll
             for (int x = 0; x < 32; ++x) v[x] = __float_as_uint(__uint_as_float(v[x]) * f);
-            tmem_st32(t_base + T_O + hh * 32, v);
+            tmem_st32(t_base + T_O + hf * 32, v);
           }
           tmem_wait_st();
         }
         // ---- pass 2: probabilities, row sum, P (bf16) back into TMEM ----
         float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          const int fm = g == 0 ? form[0] : (g == 1 ? form[1] : (g == 2 ? form[2] : form[3]));
-          const int c0 = g == 0 ? ce0[0] : (g == 1 ? ce0[1] : (g == 2 ? ce0[2] : ce0[3]));
-          const int ceg = g == 0 ? ce[0] : (g == 1 ? ce[1] : (g == 2 ? ce[2] : ce[3]));
-          const int g0 = (g < 2 ? ka : kb) + 32 * (g & 1);
+        for (int g = 0; g < 2; ++g) {
+          const int fm = g == 0 ? form[0] : form[1];
+          const int c0 = g == 0 ? ce0[0] : ce0[1];
+          const int ceg = g == 0 ? ce[0] : ce[1];
+          const int g0 = kbase + 32 * g;
           uint32_t pk[16];
           if (fm == 0) {
 #pragma unroll
             for (int x = 0; x < 16; ++x) pk[x] = 0u;
           } else {
             uint32_t v[32];
-            tmem_ld32(t_base + T_S + 32 * g, v);
+            tmem_ld32(t_s + 32 * g, v);
             tmem_wait_ld();
             // p = ex2(x * scale2 + addf(jj)) where livef(jj), else 0: four elements per step
             auto run = [&](auto addf, auto livef) {
@@ -536,27 +551,31 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           // the per-lane table reads of the diagonal forms may leave the warp diverged: tcgen05.st is .aligned
           __syncwarp();
           // P of keys [32g, 32g+32) -> packed columns [32g, 32g+16) of the same group's score columns
-          tmem_st16(t_base + T_S + 32 * g, pk);
+          tmem_st16(t_s + 32 * g, pk);
         }
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[w]);
         l += (ls0 + ls1) + (ls2 + ls3);
       }
-      // ---- epilogue: O / l -> out, statistics ----
+      // ---- epilogue: O / l -> out, statistics.  The halves add up their row sums, each stores 32 columns ----
+      {
+        float* xb = xch + xpar * (2 * 2 * TM);
+        xpar ^= 1;
+        xb[hf * TM + row] = l;
+        named_bar_sync(bar_pair, 64);
+        l = hf ? xb[row] + l : l + xb[TM + row];   // same association in both threads
+      }
       mbar_wait_warp(&bars->o_full[w], tile_par);
       tc_fence_after_sync();
       const float inv = 1.f / l;
-      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.out, b, i, h);
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
+      __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.out, b, i, h) + hf * 32;
+      {
         uint32_t v[32];
-        tmem_ld32(t_base + T_O + hh * 32, v);
+        tmem_ld32(t_base + T_O + hf * 32, v);
         tmem_wait_ld();
-        if (hh == 1) {   // O has been read: the next tile of this slot may overwrite it
-          tc_fence_before_sync();
-          mbar_arrive(&bars->o_empty[w]);
-        }
+        tc_fence_before_sync();
+        mbar_arrive(&bars->o_empty[w]);   // O has been read: the next tile of this slot may overwrite it
         if (row_ok) {
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
@@ -565,11 +584,11 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             o4.y = pack_bf16x2(__uint_as_float(v[8 * x + 2]) * inv, __uint_as_float(v[8 * x + 3]) * inv);
             o4.z = pack_bf16x2(__uint_as_float(v[8 * x + 4]) * inv, __uint_as_float(v[8 * x + 5]) * inv);
             o4.w = pack_bf16x2(__uint_as_float(v[8 * x + 6]) * inv, __uint_as_float(v[8 * x + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * x) = o4;
+            *reinterpret_cast<uint4*>(dst + 8 * x) = o4;
           }
         }
       }
-      if (row_ok) {
+      if (row_ok && hf == 0) {
         // (reference >= row maximum, sum of exp relative to it): a consistent pair is all the backward needs
         float2* st = reinterpret_cast<float2*>(p.stats) + ((int64_t)(b * p.H + h) * p.L + i);
         *st = make_float2(m2 * (1.f / LOG2E), l);
@@ -579,7 +598,7 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == NSW + 1) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace gl2
