@@ -55,6 +55,15 @@ constexpr int SM_ALLOC = SM_TOTAL + 1024;
 constexpr uint32_t T_WG = 224;   // TMEM columns per warpgroup
 constexpr uint32_t T_S = 0, T_O = 128, T_REL = 192;
 
+#ifdef MLT_TC_TRACE
+// cheap timeline: per-role event log in registers / local arrays, flushed once at kernel end (CTA 3 only)
+__device__ long long g_trace_f[2][2048];
+__device__ int g_trace_fn[2];
+#define FTRACE(buf, n, code) do { if (n < 1000) { buf[2 * n] = clock64(); buf[2 * n + 1] = (code); ++n; } } while (0)
+#else
+#define FTRACE(buf, n, code) do {} while (0)
+#endif
+
 struct Params {
   int B, H, L, G, R, D, radius;
   float scale;
@@ -195,6 +204,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const uint32_t idesc_o = make_idesc_bf16(TM, 64, 0, 1);
       const uint32_t idesc_r = make_idesc_bf16(TM, 32, 0, 0);
       int it = 0, kv_base = 0;
+#ifdef MLT_TC_TRACE
+      long long tb1[2048]; int tn1 = 0;
+#endif
       uint32_t s_cnt[2] = {0, 0};    // S MMAs issued per tile slot (parity of s_full is kept by the softmax side)
       uint32_t p_cnt[2] = {0, 0};    // P chunks consumed per tile slot
       uint32_t tile_cnt[2] = {0, 0}; // tiles started per slot
@@ -248,7 +260,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               mbar_arrive(&bars->kv_empty[st]);   // absent consumer
               continue;
             }
+            FTRACE(tb1, tn1, 100 + 10 * w + pc);
             mbar_wait(&bars->p_full[w], p_cnt[w] & 1);
+            FTRACE(tb1, tn1, 200 + 10 * w + pc);
             ++p_cnt[w];
             tc_fence_after_sync();
             if (pc == first[w]) {   // O of the previous tile in this slot has been read out
@@ -268,8 +282,12 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         umma_commit(&bars->q_empty[buf]);   // every MMA that reads this pair's Q / E has been issued
+        FTRACE(tb1, tn1, 300);
         kv_base += npc;
       }
+#ifdef MLT_TC_TRACE
+      if (blockIdx.x == 3) { for (int k = 0; k < 2 * tn1; ++k) g_trace_f[1][k] = tb1[k]; g_trace_fn[1] = tn1; }
+#endif
     }
   } else {
     // ===================== softmax groups =====================
@@ -287,6 +305,13 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float scale2 = p.scale * LOG2E;
     const int D = p.D, R = p.R, rad = p.radius;
     uint32_t s_par = 0, tile_par = 0, xpar = 0;   // parities of s_full / per-tile barriers / exchange buffer
+#ifdef MLT_TC_TRACE
+    long long tb0[2048]; int tn0 = 0;
+    const bool tr = (tid == 0);
+#define ST(code) do { if (tr) FTRACE(tb0, tn0, code); } while (0)
+#else
+#define ST(code) do {} while (0)
+#endif
     for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
       const Pair q = make_pair(p, pair);
       if (!tile_exists(q, w)) continue;
@@ -304,7 +329,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       // each column half builds 16 of the 32 ids
       if (hf == 0 && row < 32) bias_s[row] = row < R ? __bfloat162float(p.bias[row * p.H + h]) * scale2 : 0.f;
       named_bar_sync(bar_group, 256);
+      ST(1);
       mbar_wait_warp(&bars->rel_full[w], tile_par);
+      ST(2);
       tc_fence_after_sync();
       float relmax = 0.f;   // ids outside [0, R) contribute 0, and so may any key: the bound includes 0
       {
@@ -349,7 +376,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             ce[g] = (col >= 0 && col < klen) ? __ldg(eids + col) : -1;
           }
         }
+        ST(10 + pc);
         mbar_wait_warp(&bars->s_full[w], s_par);
+        ST(20 + pc);
         s_par ^= 1;
         tc_fence_after_sync();
         // ---- classify the four 32-key groups (warp-uniform) ----
@@ -415,7 +444,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         xpar ^= 1;
         const float mine = fmaf(xmax, scale2, relmax);
         xb[hf * TM + row] = mine;
+        ST(30 + pc);
         named_bar_sync(bar_pair, 64);
+        ST(40 + pc);
         const float u2 = fmaxf(mine, xb[(hf ^ 1) * TM + row]);   // -inf when nothing is live for this row
         // ---- reference update, lazy rescale of O ----
         const bool fresh = (m2 == -INFINITY);
@@ -556,6 +587,7 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[w]);
+        ST(50 + pc);
         l += (ls0 + ls1) + (ls2 + ls3);
       }
       // ---- epilogue: O / l -> out, statistics.  The halves add up their row sums, each stores 32 columns ----
@@ -566,7 +598,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         named_bar_sync(bar_pair, 64);
         l = hf ? xb[row] + l : l + xb[TM + row];   // same association in both threads
       }
+      ST(60);
       mbar_wait_warp(&bars->o_full[w], tile_par);
+      ST(61);
       tc_fence_after_sync();
       const float inv = 1.f / l;
       __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.out, b, i, h) + hf * 32;
@@ -594,7 +628,11 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         *st = make_float2(m2 * (1.f / LOG2E), l);
       }
       tile_par ^= 1;
+      ST(62);
     }
+#ifdef MLT_TC_TRACE
+    if (tr && blockIdx.x == 3) { for (int k = 0; k < 2 * tn0; ++k) g_trace_f[0][k] = tb0[k]; g_trace_fn[0] = tn0; }
+#endif
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -602,6 +640,13 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 }  // namespace gl2
+
+#ifdef MLT_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int mlt_debug_read_trace_gl2f(long long* out, int* n) {
+  cudaMemcpyFromSymbol(n, gl2::g_trace_fn, sizeof(int) * 2);
+  return (int)cudaMemcpyFromSymbol(out, gl2::g_trace_f, sizeof(long long) * 2 * 2048);
+}
+#endif
 
 // The specialised kernel serves the long rows of a compact global-local problem.
 bool gl2_fwd_long_supported(const FwdArgs& a, int dtype, int d) {

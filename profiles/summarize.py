@@ -63,7 +63,7 @@ def main():
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       f.write(f'| `{k}` | {n} | {t:,.0f} | {100 * t / tot:.1f}% |\n')
   with open(f'profiles/{tag}_ncu_full.md', 'w') as f:
-    f.write(f'# {tag}: `ncu --set full --clock-control none -k regex:tc_ -c 7` on `bench.py --steps 1 --warmup 3 --no-cpu-baseline` '
+    f.write(f'# {tag}: `ncu --set full --clock-control none -k regex:tc_|gl2_ -c 7` on `bench.py --steps 1 --warmup 3 --no-cpu-baseline` '
             '(workload c3_4096)\n\n')
     for name, d in full(rep):
       f.write(f'## `{name}` grid {d["launch__grid_size"][0]}\n\n| metric | value | unit |\n|---|---|---|\n')
@@ -80,21 +80,36 @@ def main():
       v, u = d[key]
       scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
       return float(v) * scale
-    kind = 'fwd' if 'fwd' in name else ('bwd_q' if 'bwd_q' in name else ('bwd_kv' if 'bwd_kv' in name else None))
-    if kind is None:
+    full_name = name
+    if 'gl2_fwd_long' in full_name:
+      key = 'gl2_fwd_long_rows'
+    elif 'gl2_bwd_q_long' in full_name:
+      key = 'gl2_bwd_q_long_rows'
+    elif 'tc_fwd_kernel' in full_name:
+      key = 'fwd'
+    elif 'tc_bwd_q_kernel' in full_name:
+      key = 'bwd_q'
+    elif 'tc_bwd_kv_kernel' in full_name:
+      key = 'bwd_kv'
+    else:
       continue
-    traffic.setdefault(kind, []).append((grid, as_bytes('dram__bytes_read.sum') + as_bytes('dram__bytes_write.sum')))
+    traffic.setdefault(key, []).append((grid, as_bytes('dram__bytes_read.sum') + as_bytes('dram__bytes_write.sum')))
   out = {}
   for kind, lst in traffic.items():
     lst.sort()
     small, large = lst[0], lst[-1]
+    if kind.startswith('gl2_'):     # persistent kernels: one launch per step, named like bench.py's timing key
+      out[kind] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
+      continue
     names = {'fwd': ('tc_fwd_global_rows', 'tc_fwd_long_rows'),
              'bwd_q': ('tc_bwd_q_global_rows', 'tc_bwd_q_long_rows'),
              'bwd_kv': ('tc_bwd_kv_global_keys', 'tc_bwd_kv_long_keys')}[kind]
     if len(lst) > 1:
       out[names[0]] = {'grid': small[0], 'dram_bytes_per_launch': small[1]}
-    out[names[1]] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
-  out['_source'] = f'{tag}: ncu --set full --clock-control none -k regex:tc_ on bench.py --steps 1 --warmup 3 (workload c3_4096, batch 16)'
+      out[names[1]] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
+    else:                            # only the global-row launch of this family is left on the general kernels
+      out[names[0]] = {'grid': small[0], 'dram_bytes_per_launch': small[1]}
+  out['_source'] = f'{tag}: ncu --set full --clock-control none -k 'regex:tc_|gl2_' on bench.py --steps 1 --warmup 3 (workload c3_4096, batch 16)'
   json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
   print('wrote', f'profiles/{tag}_launches.md', f'profiles/{tag}_ncu_full.md', 'profiles/traffic.json')
 
