@@ -638,8 +638,9 @@ def run_extra(args):
   att_ms = None
   if rank == 0:
     _lib.profile_enable(True)
-    run(resident)
-    torch.cuda.synchronize()
+  run(resident)          # every rank runs it: the pretraining step contains a collective
+  barrier()
+  if rank == 0:
     att_ms = sum(r[1] for r in _lib.profile_read(1 << 16))
     _lib.profile_enable(False)
   if rank == 0:

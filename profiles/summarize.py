@@ -109,7 +109,7 @@ def main():
       out[names[1]] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
     else:                            # only the global-row launch of this family is left on the general kernels
       out[names[0]] = {'grid': small[0], 'dram_bytes_per_launch': small[1]}
-  out['_source'] = f'{tag}: ncu --set full --clock-control none -k 'regex:tc_|gl2_' on bench.py --steps 1 --warmup 3 (workload c3_4096, batch 16)'
+  out['_source'] = f'{tag}: ncu --set full --clock-control none -k regex:tc_|gl2_ on bench.py --steps 1 --warmup 3 (workload c3_4096, batch 16)'
   json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
   print('wrote', f'profiles/{tag}_launches.md', f'profiles/{tag}_ncu_full.md', 'profiles/traffic.json')
 
