@@ -576,7 +576,7 @@ def run_extra(args):
     units = B * L
     cfg = dict(batch_per_gpu=B, micro_batch=MICRO, long_len=L, global_len=G, layers=12,
                params=sum(p.numel() for p in model.parameters()), dropout='attention 0.1 + hidden 0.1 (reference defaults)',
-               allreduce='bucketed (25 MB), fp32, overlapped with the last micro-batch backward')
+               allreduce='bucketed (50 MB), fp32, overlapped with the last micro-batch backward')
 
     def run(d):
       inputs = {k: d[k] for k in ('word_ids', 'patch_embeddings', 'mlm_positions', 'mpp_positions')}

@@ -168,20 +168,34 @@ class PretrainingStep:
   like the reference, does not apply the 1 / num_small_steps factor in that branch)."""
 
   def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, micro_batch_size: int,
-               scale_loss: bool = False, bucket_mb: float = 25.0, overlap: bool = True):
+               scale_loss: bool = False, bucket_mb: float = 50.0, overlap: bool = True):
     self.model, self.optimizer, self.micro = model, optimizer, micro_batch_size
-    self.scale_loss, self.overlap = scale_loss, overlap
+    self.scale_loss, self.overlap, self.bucket_mb = scale_loss, overlap, bucket_mb
+    # first guess of the gradient-ready order: reverse registration order.  The first step records the order
+    # in which the gradients really arrive and the buffers are laid out again in that order (what DDP's
+    # bucket rebuild does): modules that register their parameters by kind (all attention layers, then all
+    # feed-forward layers, then all norms) would otherwise put parameters of the first and the last layer
+    # into the same bucket, and no bucket would be complete before the end of the backward pass.
     self.params = [p for p in reversed(list(model.parameters())) if p.requires_grad]
+    self._armed = False
+    self._pending, self._works, self._launched = [], [], []
+    self._ready_order, self._ordered = [], False
+    self._layout(self.params)
+    for p in self.params:
+      p.register_post_accumulate_grad_hook(self._on_grad)
+
+  def _layout(self, ordered_params):
+    """(Re)builds the flat gradient / fp32 accumulation buffers and the buckets for this parameter order."""
     self.groups = []       # one per (dtype, device): dict(grad=flat, acc=flat fp32, buckets=[(lo, hi)], ...)
     self._slot = {}        # param -> (group index, bucket index)
     by_key = {}
-    for p in self.params:
+    for p in ordered_params:
       by_key.setdefault((p.dtype, p.device), []).append(p)
     for key, ps in by_key.items():
       n = sum(p.numel() for p in ps)
       grad = torch.zeros(n, dtype=key[0], device=key[1])
       acc = grad if key[0] == torch.float32 else torch.zeros(n, dtype=torch.float32, device=key[1])
-      limit = max(1, int(bucket_mb * 2**20 / 4))
+      limit = max(1, int(self.bucket_mb * 2**20 / 4))
       buckets, counts, off, lo = [], [], 0, 0
       gi = len(self.groups)
       for p in ps:
@@ -199,10 +213,6 @@ class PretrainingStep:
       counts = counts[:len(buckets)]
       stream = torch.cuda.Stream(device=key[1]) if key[1].type == 'cuda' else None
       self.groups.append(dict(grad=grad, acc=acc, buckets=buckets, counts=counts, stream=stream))
-    self._armed = False
-    self._pending, self._works, self._launched = [], [], []
-    for p in self.params:
-      p.register_post_accumulate_grad_hook(self._on_grad)
     # kept for callers that inspect the flat gradient buffers (tests, checkpoints)
     self.flat = {(g['grad'].dtype, g['grad'].device): g['grad'] for g in self.groups}
 
@@ -233,6 +243,8 @@ class PretrainingStep:
   def _on_grad(self, p):
     if not self._armed:
       return
+    if not self._ordered:
+      self._ready_order.append(p)
     gi, bi = self._slot[p]
     self._pending[gi][bi] -= 1
     if self._pending[gi][bi] == 0:
@@ -287,6 +299,13 @@ class PretrainingStep:
         g['grad'].copy_(g['acc'])     # reduced fp32 gradients -> the parameters' dtype, for the optimizer
     self._launched = []
     self.optimizer.step()
+    if not self._ordered:
+      # lay the buffers out again in the observed gradient-ready order (parameters that received no gradient
+      # keep their place at the end); the optimizer reads p.grad afresh every step, so the new views are safe
+      self._ordered = True
+      seen = set(id(p) for p in self._ready_order)
+      self._layout(self._ready_order + [p for p in self.params if id(p) not in seen])
+      self._ready_order = []
     return total
 
 

@@ -85,19 +85,27 @@ labels = {'mlm_label_ids': torch.randint(0, 16, (4, 2), generator=g), 'mlm_label
           'mpp_label_ids': torch.randint(0, 4, (4, 2), generator=g), 'mpp_label_weights': torch.ones(4, 2),
           'itm_label_ids': torch.randint(0, 2, (4,), generator=g), 'itm_label_weights': torch.ones(4)}
 nb = sum(len(gr['buckets']) for gr in step.groups)
-loss = step(inputs, labels)
 # reference semantics (scale_loss=False): the applied gradient is the SUM over the replicas of each replica's
-# mean-over-micro-batches gradient.  Recompute it without the step machinery and compare.
+# mean-over-micro-batches gradient.  Two steps: the second one runs on the buffers re-laid out in the observed
+# gradient-ready order.  Recompute both without the step machinery and compare.
 ref_model = Tiny(); ref_model.load_state_dict(init)
-tot = None
-for sl in (slice(0, 2), slice(2, 4)):
-  out = ref_model(**{k: v[sl] for k, v in inputs.items()})
-  l = tasks.pretraining_losses({k: v[sl] for k, v in labels.items()}, out) / 2
-  gs = torch.autograd.grad(l, list(ref_model.parameters()))
-  tot = gs if tot is None else [a + b for a, b in zip(tot, gs)]
-flat_ref = torch.cat([t.reshape(-1) for t in tot])
-dist.all_reduce(flat_ref)
-want = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]) - 0.1 * flat_ref
+for it in range(2):
+  loss = step(inputs, labels)
+  tot = None
+  for sl in (slice(0, 2), slice(2, 4)):
+    out = ref_model(**{k: v[sl] for k, v in inputs.items()})
+    l = tasks.pretraining_losses({k: v[sl] for k, v in labels.items()}, out) / 2
+    gs = torch.autograd.grad(l, list(ref_model.parameters()))
+    tot = gs if tot is None else [a + b for a, b in zip(tot, gs)]
+  flat_ref = torch.cat([t.reshape(-1) for t in tot])
+  dist.all_reduce(flat_ref)
+  off = 0
+  with torch.no_grad():
+    for p_ in ref_model.parameters():
+      p_ -= 0.1 * flat_ref[off:off + p_.numel()].view_as(p_)
+      off += p_.numel()
+assert step._ordered
+want = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()])
 flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
 print(json.dumps({"rank": rank, "loss": float(loss), "checksum": float(flat.double().sum()), "norm": float(flat.norm()),
                   "buckets": nb, "err_vs_manual": float((flat - want).abs().max())}))
