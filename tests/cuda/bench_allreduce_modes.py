@@ -8,7 +8,8 @@ L, B, MICRO, G, VOCAB = 4096, 4, 2, 256, 30522
 world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
 torch.cuda.set_device(rank); dev = torch.device('cuda', rank)
 if world > 1:
-  dist.init_process_group('nccl', device_id=dev)
+  opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=bool(int(os.environ.get('MLT_NCCL_HIPRI', '0'))))
+  dist.init_process_group('nccl', device_id=dev, pg_options=opts)
 res = {}
 for mode in ('overlap', 'after'):
   torch.manual_seed(0)
