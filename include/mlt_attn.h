@@ -288,6 +288,30 @@ MLT_API int mlt_build_gl_side_inputs(const int32_t* long_example_ids, const int3
                              int32_t local_radius, int32_t max_distance, int32_t* const out[8],
                              void* cuda_stream);
 
+/* Recognition of generator-shaped explicit side inputs: the inverse of the two constructors above.
+ * The Keras-level signatures (reference src/modeling/models/mmt_encoder.py:220-224; FusedGlobalLocalAttention.call
+ * [UPSTREAM-RECALLED]) only carry the O(S^2) int32 tensors.  These calls derive candidate compact descriptors
+ * from them and then compare EVERY element of every tensor with the value the compact rule gives; they are
+ * meant to be called once per batch (the tensors are shared by all layers), after which every layer's
+ * forward and backward can run with MLT_SIDE_COMPACT.
+ *   result: device int32[4].  result[0] = 1 iff every element of every tensor is reproduced exactly
+ *           (only then may the descriptors replace the tensors); result[1] = max_distance; [2], [3] scratch.
+ *   Outputs are written whether or not recognition succeeds.  Asynchronous like everything else: the caller
+ *   reads result[] after synchronising the stream.
+ * mlt_dense_compact_from_explicit: att_mask, relative_att_ids int32 [B,S,S] (square self-attention) ->
+ *   q_example_ids, k_example_ids [B,S].  hint.num_patch_per_row > 0 checks the ids against that 2-D layout
+ *   (hint.max_distance / num_core_layers as in mlt_id_layout); num_patch_per_row == 0 checks the 1-D rule with
+ *   hint.max_distance, or with the distance read from the ids themselves when hint.max_distance < 0.
+ * mlt_gl_compact_from_explicit: in[] in the order of mlt_build_gl_side_inputs' out[] (all eight required)
+ *   -> long_example_ids [B,L], global_example_ids [B,G], sentence_ids [B,L] (-1 = no global token of its own). */
+MLT_API int mlt_dense_compact_from_explicit(const int32_t* att_mask, const int32_t* relative_att_ids,
+                                    int32_t B, int32_t S, mlt_id_layout hint, int32_t* q_example_ids,
+                                    int32_t* k_example_ids, int32_t* result, void* cuda_stream);
+MLT_API int mlt_gl_compact_from_explicit(const int32_t* const in[8], int32_t B, int32_t L, int32_t G,
+                                 int32_t local_radius, int32_t* long_example_ids,
+                                 int32_t* global_example_ids, int32_t* sentence_ids, int32_t* result,
+                                 void* cuda_stream);
+
 /* ---- profiling facility (bench.py; off by default) ------------------------------------ */
 typedef struct {
   char name[48];   /* kernel role, e.g. "fwd_long_rows" */

@@ -119,6 +119,7 @@ EXPORTS = (
     'mlt_dense_uses_tensor_cores', 'mlt_dense_workspace_bytes', 'mlt_gl_workspace_bytes',
     'mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd', 'mlt_gl_attn_bwd',
     'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs',
+    'mlt_dense_compact_from_explicit', 'mlt_gl_compact_from_explicit',
     'mlt_profile_enable', 'mlt_profile_read', 'mlt_launch_count',
     'mlt_local_workspace_bytes', 'mlt_local_rel_attn_fwd', 'mlt_local_rel_attn_bwd',
 )
@@ -162,8 +163,14 @@ def load() -> C.CDLL:
   lib.mlt_build_gl_side_inputs.argtypes = [
       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
       C.c_int32, C.POINTER(C.c_void_p * 8), C.c_void_p]
+  lib.mlt_dense_compact_from_explicit.argtypes = [
+      C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, IdLayout, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+  lib.mlt_gl_compact_from_explicit.argtypes = [
+      C.POINTER(C.c_void_p * 8), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+      C.c_void_p, C.c_void_p, C.c_void_p]
   for name in ('mlt_dense_rel_attn_fwd', 'mlt_dense_rel_attn_bwd', 'mlt_gl_attn_fwd',
-               'mlt_gl_attn_bwd', 'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs'):
+               'mlt_gl_attn_bwd', 'mlt_build_dense_side_inputs', 'mlt_build_gl_side_inputs',
+               'mlt_dense_compact_from_explicit', 'mlt_gl_compact_from_explicit'):
     getattr(lib, name).restype = C.c_int
   lib.mlt_local_workspace_bytes.argtypes = [C.POINTER(LocalParams), C.c_int]
   lib.mlt_local_workspace_bytes.restype = C.c_size_t

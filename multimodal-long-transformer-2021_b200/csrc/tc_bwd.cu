@@ -223,6 +223,7 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
 
 __device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm, bool ex) {
   plan::PSeg s;
+  s.n_img = 0;   // the 2-D shortcut is a forward-kernel form
   s.expl_ok = ex;
   s.c_begin = r.kb;
   s.c_end = r.ke;
@@ -1181,6 +1182,7 @@ __device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRan
 
 __device__ __forceinline__ plan::PSeg make_kv_pseg(const TcQuerySource& src, const SrcRange& r, bool ex) {
   plan::PSeg s;
+  s.n_img = 0;   // the 2-D shortcut is a forward-kernel form
   s.expl_ok = ex;
   const Side& sd = src.q.side;
   s.c_begin = r.ib;

@@ -119,6 +119,8 @@ __device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange
   s.col_sent = (s.id_rule == IDR_CROSS_KSENT);
   s.c_sent = s.col_sent ? sg.side.sent : nullptr;
   s.c_sent_stride = sg.side.sent_len;
+  // compact 2-D layout served through the library's id plane (abi.cu with_ids_plane keeps npr)
+  s.n_img = (ex && sg.side.id_rule == IDR_EXPLICIT && sg.side.npr > 0) ? sg.side.npr * sg.side.npr : 0;
   return s;
 }
 
@@ -132,10 +134,12 @@ struct SegC {          // warp-uniform
   int D, R, pd;
   bool perm;
   int col_base;        // dropout counter offset of key 0
+  int n_img;           // see plan::PSeg::n_img
 };
 struct RowC {          // per thread and segment
   int q_e, q_sent;
   float relP, relN, relX, relX1;
+  float relM;          // 2-D layout: text row -> id of an image column, image row -> id of a text column
 };
 
 __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
@@ -151,6 +155,7 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
   sc.pd = pd;
   sc.perm = perm;
   sc.col_base = sg.col_base;
+  sc.n_img = (sg.side.id_rule == IDR_EXPLICIT && sg.side.npr > 0) ? sg.side.npr * sg.side.npr : 0;
   return sc;
 }
 
@@ -163,7 +168,7 @@ __device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i
 // `meta` = the id -> slot table of the tile (plan::rel_meta_init): one warp-broadcast LDS instead of the
 // branchy id -> slot rule in this once-per-tile (cold) code
 __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, const plan::RelMeta* meta,
-                                           int row) {
+                                           int row, int i) {
   auto rel_at = [&](int id) -> float {
     return (id >= 0 && id < sc.R) ? rel_s[meta[id].slot_off + row] : 0.f;
   };
@@ -172,6 +177,16 @@ __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float
   rc.relN = on ? rel_at(2 * sc.D) : 0.f;
   rc.relX = on ? rel_at(2 * sc.D + 1) : 0.f;
   rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
+  rc.relM = 0.f;
+  if (on && sc.n_img > 0) {   // rel_id_2d: image_part_id = n_img + 8 + 2 D + 1, text_part_id = image_part_id + 1
+    const int image_part_id = sc.n_img + 8 + 2 * sc.D + 1;
+    rc.relM = rel_at(i >= sc.n_img ? image_part_id : image_part_id + 1);
+  }
+}
+__device__ __forceinline__ float rel_const(int ccls, const RowC& rc) {
+  return ccls == plan::C_POS ? rc.relP
+                             : (ccls == plan::C_NEG ? rc.relN
+                                                    : (ccls == plan::C_CROSS ? rc.relX : (ccls == plan::C_MODAL ? rc.relM : 0.f)));
 }
 
 // Generic per-element score (any rule).  Dead pairs return -inf.
@@ -359,8 +374,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tc_fence_after_sync();
       plan::rel_table_build(tmem + T_REL + lane_sel, relmeta, rel_s, row, rpad, a.scale, [](int, const float (&)[16]) {});
     }
-    row_consts(rc0, sc0, rel_s, relmeta, row);   // a thread only reads its own column of rel_s: no barrier
-    row_consts(rc1, sc1, rel_s, relmeta, row);
+    row_consts(rc0, sc0, rel_s, relmeta, row, i);   // a thread only reads its own column of rel_s: no barrier
+    row_consts(rc1, sc1, rel_s, relmeta, row, i);
 
     if (tid == 0) TRACE(0, 2);
     const float scale2 = a.scale * LOG2E;
@@ -434,7 +449,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 return;
               }
               const int ccls = (int)((w0 >> 8) & 0xffu);
-              const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+              const float relc = rel_const(ccls, rc);
               const float gmul = masked ? 0.f : scale2;
               const float gsub = fmaf(relc + (masked ? a.neg : 0.f), LOG2E, -mb);
               const int gmode = (int)(w0 & 0xffu);
@@ -505,7 +520,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           if (lit && mode == plan::FAST && __any_sync(0xffffffffu, masked)) mode = plan::EDGE;
           const float mterm = masked ? a.neg : 0.f;
           const int ccls = (int)((w0 >> 8) & 0xffu);
-          const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+          const float relc = rel_const(ccls, rc);
           float gmul, gadd, gmax;
           if (mode == plan::FAST) {
             // every row of the warp masked here and already holding a real maximum: p == 0 exactly

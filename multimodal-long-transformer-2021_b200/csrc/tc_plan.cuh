@@ -30,7 +30,8 @@ namespace plan {
 
 enum Mode : int { DEAD = 0, FAST, EDGE, DIAG, QS, KS, GEN, EXPL };
 // constant relative classes of a group (which per-row constant applies)
-enum CCls : int { C_NONE = 0, C_POS = 1, C_NEG = 2, C_CROSS = 3 };
+// C_MODAL: 2-D image + text layout, text row x image column or image row x text column (one id per row kind)
+enum CCls : int { C_NONE = 0, C_POS = 1, C_NEG = 2, C_CROSS = 3, C_MODAL = 4 };
 
 constexpr uint32_t F_MASK_PE = 1u << 16;   // example-id mask changes inside the group
 
@@ -65,6 +66,9 @@ struct PSeg {
   int64_t c_eid_stride, c_sent_stride;
   bool col_sent;         // sentence ids live on the column side (KS form); else on the row side (QS)
   bool expl_ok;          // the kernel instantiation carries the EXPL form (else explicit tensors take GEN)
+  int n_img;             // > 0: the explicit ids are the library's own plane of the 2-D image + text layout
+                         // (first n_img positions = patches) and the kernel carries C_MODAL: only
+                         // image x image groups read the plane (reference src/feature_utils.py:114-184)
 };
 
 // Per-tile row-side sentence ranges (QS form): [rs_min[w], rs_max[w]] of quadrant w.
@@ -128,8 +132,22 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
     const bool dead = g0 >= s.c_end || (s.band && (o_min > s.radius || o_max < -s.radius));
     // explicit tensors (ids explicit or absent; the mask explicit, absent, or the example-id rule --
     // the latter with an explicit id plane is how compact 2-D ids are served)
-    const bool expl = s.expl_ok && (s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT) &&
-                      (s.id_rule == IDR_EXPLICIT || s.id_rule == IDR_NONE);
+    bool expl = s.expl_ok && (s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT) &&
+                (s.id_rule == IDR_EXPLICIT || s.id_rule == IDR_NONE);
+    int id_rule = s.id_rule;
+    if (expl && s.n_img > 0 && s.mask_rule == MR_EXAMPLE_ID && !s.rows_are_keys) {
+      // text x text pairs follow the 1-D rule, text x image / image x text pairs carry one id per row kind
+      const bool r_txt = a >= s.n_img, r_img = a + 31 < s.n_img;
+      const bool c_txt = g0 >= s.n_img, c_img = g0 + 31 < s.n_img;
+      if (r_txt && c_txt) {
+        id_rule = IDR_1D;
+        expl = false;
+      } else if ((r_txt && c_img) || (r_img && c_txt)) {
+        id_rule = IDR_NONE;
+        ccls = C_MODAL;
+        expl = false;
+      }
+    }
     if (dead) {
       mode = DEAD;
     } else if (expl) {
@@ -141,7 +159,7 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
       if (s.mask_rule == MR_EXPLICIT) gen = true;
       if (s.mask_rule == MR_EXAMPLE_ID && !(g ? uni1 : uni0)) flags |= F_MASK_PE;
       int rcls = 0;  // 0 const, 1 diag, 2 qs, 3 ks, 4 generic
-      switch (s.id_rule) {
+      switch (id_rule) {
         case IDR_NONE:
           break;
         case IDR_1D:

@@ -307,13 +307,19 @@ class RelativeTransformerLayers(nn.Module):
                hidden_dropout_prob: float = 0.1, attention_probs_dropout_prob: float = 0.1,
                initializer_range: float = 0.02, relative_vocab_size: Optional[int] = None,
                use_pre_activation_order: bool = False, use_one_hot_lookup: bool = False,
-               impl: str = 'auto'):
+               impl: str = 'auto', recognize_side_inputs: bool = True, id_layout_hint=None):
     super().__init__()
     if intermediate_size is None:
       intermediate_size = 4 * hidden_size
     if hidden_size % num_attention_heads != 0:
       raise ValueError('`hidden_size` must be a multiple of `num_attention_heads`.')
     self.use_pre_activation_order = use_pre_activation_order
+    # Explicit [B,S,S] side inputs (the reference's signature) are checked ONCE per call of the stack against
+    # the compact rules; when every element is reproduced, all layers run from the descriptors (same results,
+    # no O(S^2) int32 reads per layer).  `id_layout_hint` = (num_patch_per_row, num_core_layers,
+    # max_distance) names the 2-D layout to check against; None = the 1-D rule.
+    self.recognize_side_inputs = recognize_side_inputs
+    self.id_layout_hint = id_layout_hint
     self.attention_layers = nn.ModuleList([
         RelativeAttention(hidden_size, num_attention_heads, relative_vocab_size=relative_vocab_size,
                           att_dropout_prob=attention_probs_dropout_prob,
@@ -331,6 +337,12 @@ class RelativeTransformerLayers(nn.Module):
     tr = resolve_training(self, training)   # applies to this call only; the module mode is untouched
     drop = lambda t: F.dropout(t, self.hidden_dropout_prob, tr)
     x = inputs
+    if (compact is None and self.recognize_side_inputs and att_mask is not None and relative_att_ids is not None
+        and att_mask.is_cuda):
+      npr, core, dist = self.id_layout_hint or (0, 0, None)
+      compact = ops.compact_from_explicit_dense(att_mask, relative_att_ids, npr, core, dist)
+      if compact is not None:
+        att_mask = relative_att_ids = None
     for att, ffn, n1, n2 in zip(self.attention_layers, self.feed_forward_layers,
                                 self.attention_norms, self.feed_forward_norms):
       if self.use_pre_activation_order:
@@ -357,8 +369,10 @@ class GlobalLocalTransformerLayers(nn.Module):
                share_feed_forward_params: bool = True, share_kv_projections: bool = False,
                share_qkv_projections: bool = True, share_att_output_projection: bool = True,
                use_pre_activation_order: bool = False, use_one_hot_lookup: bool = False,
-               impl: str = 'auto'):
+               impl: str = 'auto', recognize_side_inputs: bool = True):
     super().__init__()
+    self.recognize_side_inputs = recognize_side_inputs   # see RelativeTransformerLayers
+    self.local_radius = local_radius
     li = 4 * long_hidden_size if long_intermediate_size is None else long_intermediate_size
     gi = 4 * global_hidden_size if global_intermediate_size is None else global_intermediate_size
     self.use_pre_activation_order = use_pre_activation_order
@@ -396,6 +410,12 @@ class GlobalLocalTransformerLayers(nn.Module):
     tr = resolve_training(self, training)   # applies to this call only; the module mode is untouched
     drop = lambda t: F.dropout(t, self.hidden_dropout_prob, tr)
     xl, xg = long_input, global_input
+    if compact_side_inputs is None and self.recognize_side_inputs and l2l_att_mask is not None and l2l_att_mask.is_cuda:
+      compact_side_inputs = ops.compact_from_explicit_gl(
+          dict(l2l_att_mask=l2l_att_mask, l2l_relative_att_ids=l2l_relative_att_ids, l2g_att_mask=l2g_att_mask,
+               l2g_relative_att_ids=l2g_relative_att_ids, g2g_att_mask=g2g_att_mask,
+               g2g_relative_att_ids=g2g_relative_att_ids, g2l_att_mask=g2l_att_mask,
+               g2l_relative_att_ids=g2l_relative_att_ids), self.local_radius)
     side = dict(l2l_att_mask=l2l_att_mask, g2g_att_mask=g2g_att_mask, l2g_att_mask=l2g_att_mask,
                 g2l_att_mask=g2l_att_mask, l2l_relative_att_ids=l2l_relative_att_ids,
                 g2g_relative_att_ids=g2g_relative_att_ids, l2g_relative_att_ids=l2g_relative_att_ids,

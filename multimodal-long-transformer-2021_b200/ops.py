@@ -586,3 +586,75 @@ def build_gl_side_inputs(compact: CompactSideInputs, local_radius: int):
                                             local_radius, compact.relative_pos_max_distance,
                                             C.byref(arr), _stream(le.device)), 'mlt_build_gl_side_inputs')
   return out
+
+
+def compact_from_explicit_dense(att_mask: torch.Tensor, relative_att_ids: torch.Tensor,
+                                num_patch_per_row: int = 0, num_core_layers: int = 0,
+                                max_distance: Optional[int] = None) -> Optional[DenseCompactSideInputs]:
+  """Recognition of generator-shaped explicit side inputs of the dense path (the reference's own call
+  signature, ``src/modeling/models/mmt_encoder.py:220-224``): returns the compact descriptors when they
+  reproduce EVERY element of ``att_mask [B,S,S]`` and ``relative_att_ids [B or 1,S,S]`` exactly, else ``None``.
+
+  Meant to be called once per batch (the tensors are shared by all layers); it reads one int32 flag back,
+  i.e. synchronises the stream once.  ``num_patch_per_row > 0`` checks the ids against that 2-D image + text
+  layout (``src/feature_utils.py:114-184``; ``max_distance`` required); otherwise the 1-D rule, with the
+  distance read from the ids when ``max_distance`` is None.
+  """
+  lib = _lib.load()
+  if att_mask is None or relative_att_ids is None or att_mask.dim() != 3 or att_mask.shape[1] != att_mask.shape[2]:
+    return None
+  b, s, _ = att_mask.shape
+  if s < 2 or relative_att_ids.dim() != 3 or tuple(relative_att_ids.shape[1:]) != (s, s) or \
+      relative_att_ids.shape[0] not in (1, b):
+    return None
+  if num_patch_per_row > 0 and max_distance is None:
+    raise ValueError('the 2-D layout needs `max_distance`.')
+  mask = _int32(att_mask, (b, s, s), 'att_mask')
+  ids = _int32(relative_att_ids.expand(b, s, s), (b, s, s), 'relative_att_ids')
+  dev = mask.device
+  qe = torch.empty((b, s), dtype=torch.int32, device=dev)
+  ke = torch.empty((b, s), dtype=torch.int32, device=dev)
+  res = torch.empty(4, dtype=torch.int32, device=dev)
+  hint = IdLayout(num_patch_per_row, num_core_layers, -1 if max_distance is None else max_distance)
+  with torch.cuda.device(dev):
+    _lib.check(lib.mlt_dense_compact_from_explicit(mask.data_ptr(), ids.data_ptr(), b, s, hint, qe.data_ptr(),
+                                                   ke.data_ptr(), res.data_ptr(), _stream(dev)),
+               'mlt_dense_compact_from_explicit')
+  ok, dist = res[:2].tolist()
+  if not ok:
+    return None
+  return DenseCompactSideInputs(qe, ke, dist, num_patch_per_row, num_core_layers)
+
+
+def compact_from_explicit_gl(side: dict, local_radius: int) -> Optional[CompactSideInputs]:
+  """Same for the eight tensors of ``FusedGlobalLocalAttention.call`` [UPSTREAM-RECALLED]: returns
+  ``CompactSideInputs`` when the compact rules reproduce every element of all eight, else ``None``."""
+  lib = _lib.load()
+  if any(side.get(k) is None for k in _GL_SIDE_KEYS):
+    return None
+  l2l, l2g = side['l2l_att_mask'], side['l2g_att_mask']
+  if l2l.dim() != 3 or l2g.dim() != 3 or l2l.shape[2] != 2 * local_radius + 1:
+    return None
+  b, l, w = l2l.shape
+  g = l2g.shape[2]
+  shapes = {'l2l': (b, l, w), 'l2g': (b, l, g), 'g2g': (b, g, g), 'g2l': (b, g, l)}
+  ts = []
+  for k in _GL_SIDE_KEYS:
+    t = side[k]
+    if t.dim() != 3 or tuple(t.shape[1:]) != shapes[k[:3]][1:] or t.shape[0] not in (1, b):
+      return None
+    ts.append(_int32(t.expand(*shapes[k[:3]]), shapes[k[:3]], k))
+  dev = ts[0].device
+  le = torch.empty((b, l), dtype=torch.int32, device=dev)
+  ge = torch.empty((b, g), dtype=torch.int32, device=dev)
+  sid = torch.empty((b, l), dtype=torch.int32, device=dev)
+  res = torch.empty(4, dtype=torch.int32, device=dev)
+  arr = (C.c_void_p * 8)(*[t.data_ptr() for t in ts])
+  with torch.cuda.device(dev):
+    _lib.check(lib.mlt_gl_compact_from_explicit(C.byref(arr), b, l, g, local_radius, le.data_ptr(), ge.data_ptr(),
+                                                sid.data_ptr(), res.data_ptr(), _stream(dev)),
+               'mlt_gl_compact_from_explicit')
+  ok, dist = res[:2].tolist()
+  if not ok:
+    return None
+  return CompactSideInputs(le, ge, sid, dist)

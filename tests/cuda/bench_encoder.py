@@ -23,7 +23,9 @@ lengths = torch.randint(S // 2, S + 1, (B,))
 eid = (torch.arange(S)[None, :] < lengths[:, None]).to(torch.int32).cuda()
 mask2d, ids2d = ops.build_dense_side_inputs(eid, D, num_patch_per_row=NPR, num_core_layers=2)
 cases = {
-    'explicit [B,S,S] mask + 2-D ids (reference call)': dict(att_mask=mask2d, relative_att_ids=ids2d),
+    'explicit [B,S,S] mask + 2-D ids (reference call), explicit kernels': dict(att_mask=mask2d, relative_att_ids=ids2d),
+    'explicit [B,S,S] mask + 2-D ids (reference call), recognised once per forward': dict(
+        att_mask=mask2d, relative_att_ids=ids2d),
     'compact 2-D descriptors': dict(compact=ops.DenseCompactSideInputs(eid, max_distance=D, num_patch_per_row=NPR,
                                                                        num_core_layers=2)),
     'compact 1-D descriptors': dict(compact=ops.DenseCompactSideInputs(eid, max_distance=D)),
@@ -36,6 +38,8 @@ def run(kw):
 
 
 for name, kw in cases.items():
+  enc.transformer_layers.recognize_side_inputs = 'recognised' in name
+  enc.transformer_layers.id_layout_hint = (NPR, 2, D)
   for _ in range(2):
     run(kw)
   torch.cuda.synchronize()

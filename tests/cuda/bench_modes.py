@@ -45,8 +45,16 @@ def gl(side):
   return f
 
 
+def gl_recognised():
+  side = ops.compact_from_explicit_gl(explicit, shape.local_radius)   # per call here; per batch in a stack
+  assert side is not None
+  gl(side)()
+
+
+t_rec = timeit(lambda: ops.compact_from_explicit_gl(explicit, shape.local_radius))
 print(f'global-local c3_4096 batch {batch}: compact {timeit(gl(compact)):.3f} ms, '
-      f'explicit {timeit(gl(explicit)):.3f} ms')
+      f'explicit {timeit(gl(explicit)):.3f} ms, explicit recognised per call {timeit(gl_recognised):.3f} ms '
+      f'(recognition alone {t_rec:.3f} ms, once per batch in a stack)')
 
 # dense, config-2 shape: S = 512 (196 patches + text), 2-D ids for the patch block
 B, S, H, D, R = 32, 512, 12, 64, 32

@@ -34,9 +34,13 @@ if phase in ('fwd', 'both'):
         lo, go = ops.global_local_attention(*dev_in, local_radius=shape.local_radius, side=side, impl=impl)
       torch.cuda.synchronize()
       outs[impl] = lo.float()
+      outs[impl + '_g'] = go.float()
     print('  long_out gl2 vs generic %.4g, vs simt %.4g, finite %s' % (
         (outs['tc'] - outs['tc_generic']).abs().max().item(), (outs['tc'] - outs['simt']).abs().max().item(),
         bool(torch.isfinite(outs['tc']).all())), flush=True)
+    print('  global_out gl2 vs generic %.4g, vs simt %.4g, finite %s' % (
+        (outs['tc_g'] - outs['tc_generic_g']).abs().max().item(), (outs['tc_g'] - outs['simt_g']).abs().max().item(),
+        bool(torch.isfinite(outs['tc_g']).all())), flush=True)
 if phase in ('bwd', 'both'):
   for dims in shapes:
     shape, x = inputs(dims)
