@@ -529,7 +529,10 @@ def run_extra(args):
             'example_ids': pin(eid)}
     if name == 'c2_encoder':
       units, cfg = B * S, dict(batch_per_gpu=B, seq_len=S, layers=12, side_inputs='explicit [B,S,S] mask + 2-D ids, '
-                               'built on the device per step from example ids (mlt_build_dense_side_inputs)')
+                               'built on the device per step from example ids (mlt_build_dense_side_inputs); the '
+                               'stack recognises them once per forward (mlt_dense_compact_from_explicit, every '
+                               'element verified) and runs its 12 layers from the descriptors')
+      model.encoder.transformer_layers.id_layout_hint = (NPR, 2, D)   # the layout the data pipeline used
 
       def run(d):
         mask, ids = ops.build_dense_side_inputs(d['example_ids'], D, num_patch_per_row=NPR, num_core_layers=2)
