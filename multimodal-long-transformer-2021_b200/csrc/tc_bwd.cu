@@ -313,7 +313,9 @@ constexpr int bq_threads() { return (4 * (SLIM ? 1 : 2) * SETS + 3) * 32; }
 
 // EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
 // instantiations stay free of its code and register pressure.
-template <int SETS, bool SLIM, bool EX = false, bool DROP = false>
+// ABSORB: the literal-`neg` mode is compiled out (|neg| > 1e5 guaranteed by the launcher): the instantiation the
+// reference's -1e9 runs on.  Carrying the mode as a run-time switch costs the hot kernels 3 - 7 %.
+template <int SETS, bool SLIM, bool EX = false, bool DROP = false, bool ABSORB = false>
 __global__ void __launch_bounds__(bq_threads<SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_v0,
@@ -576,7 +578,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // additive constant itself (per-row constant lpm below); |neg| <= 1e5 ("literal" mode) -> a masked
     // element evaluates like an unmasked one with neg * log2e added to its exponent, and FAST groups
     // with masked rows take the per-element EDGE form.
-    const bool lit = fabsf(a.neg) <= 1e5f;
+    const bool lit = ABSORB ? false : fabsf(a.neg) <= 1e5f;
     const bool skip_ok = a.neg < -200.f;
     const float negl2 = a.neg * LOG2E;
     const float real_thr2 = 0.5f * a.neg * LOG2E;
@@ -1247,7 +1249,7 @@ constexpr int bk_threads() { return (4 * NP * SETS + (SLIM ? 2 : 3)) * 32; }
 // per-query constants arrive exponent-ready in the row records the query-centric pass published
 // (TcBwdQParams::rec_ws), so the common element costs
 //     p = ex2(fma(x, scale*log2e, rec[i][4 + id])),  ds = p * (dp - rec[i][2]).
-template <int NP, int SETS, bool SLIM, bool EX = false, bool DROP = false>
+template <int NP, int SETS, bool SLIM, bool EX = false, bool DROP = false, bool ABSORB = false>
 __global__ void __launch_bounds__(bk_threads<NP, SETS, SLIM>(), SLIM ? 2 : 1)
 tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_do0,
@@ -1423,7 +1425,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     const float scale2 = p.scale * LOG2E;
     // `neg` honoured literally (see tc_fwd.cu / the query-centric pass): in literal mode a masked element
     // evaluates like an unmasked one with neg * log2e added to its exponent.
-    const bool lit = fabsf(p.neg) <= 1e5f;
+    const bool lit = ABSORB ? false : fabsf(p.neg) <= 1e5f;
     const float negl2 = p.neg * LOG2E;
     // One call per query source (inlined twice: no per-field selects inside the chunk loop).
     // Chunks [c_begin, c_end) belong to this source; this warp set handles those with c % SETS == set.
@@ -1749,12 +1751,16 @@ struct BqLaunch {
     tc_bwd_q_kernel<SETS, SLIM, EX, DROP><<<grid, bq_threads<SETS, SLIM>(), bq::Cfg<SLIM>::SM_ALLOC, st>>>(
         mq, mdo, mk0, mv0, mk1, mv1, me, p);
   }
+  static bool absorbed(const TcBwdQParams& p) { return !(fabsf(p.a.neg) <= 1e5f); }
   static void run(bool ex, bool dr, dim3 grid, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdo,
                   const CUtensorMap& mk0, const CUtensorMap& mv0, const CUtensorMap& mk1, const CUtensorMap& mv1,
                   const CUtensorMap& me, const TcBwdQParams& p) {
     if (ex && dr) go<true, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
     else if (ex) go<true, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
     else if (dr) go<false, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    else if (absorbed(p))
+      tc_bwd_q_kernel<SETS, SLIM, false, false, true><<<grid, bq_threads<SETS, SLIM>(), bq::Cfg<SLIM>::SM_ALLOC, st>>>(
+          mq, mdo, mk0, mv0, mk1, mv1, me, p);
     else go<false, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   }
   static cudaError_t attrs() {
@@ -1767,6 +1773,7 @@ struct BqLaunch {
     set(tc_bwd_q_kernel<SETS, SLIM, true, false>);
     set(tc_bwd_q_kernel<SETS, SLIM, false, true>);
     set(tc_bwd_q_kernel<SETS, SLIM, true, true>);
+    set(tc_bwd_q_kernel<SETS, SLIM, false, false, true>);
     return e;
   }
 };
@@ -1783,6 +1790,9 @@ struct BkLaunch {
     if (ex && dr) go<true, true>(grid, st, mk, mv, mq, mdo, p);
     else if (ex) go<true, false>(grid, st, mk, mv, mq, mdo, p);
     else if (dr) go<false, true>(grid, st, mk, mv, mq, mdo, p);
+    else if (!(fabsf(p.neg) <= 1e5f))
+      tc_bwd_kv_kernel<NP, SETS, SLIM, false, false, true>
+          <<<grid, bk_threads<NP, SETS, SLIM>(), bk::Cfg<SLIM>::SM_ALLOC, st>>>(mk, mv, mq[0], mdo[0], mq[1], mdo[1], p);
     else go<false, false>(grid, st, mk, mv, mq, mdo, p);
   }
   static cudaError_t attrs() {
@@ -1795,6 +1805,7 @@ struct BkLaunch {
     set(tc_bwd_kv_kernel<NP, SETS, SLIM, true, false>);
     set(tc_bwd_kv_kernel<NP, SETS, SLIM, false, true>);
     set(tc_bwd_kv_kernel<NP, SETS, SLIM, true, true>);
+    set(tc_bwd_kv_kernel<NP, SETS, SLIM, false, false, true>);
     return e;
   }
 };

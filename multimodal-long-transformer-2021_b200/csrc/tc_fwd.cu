@@ -222,7 +222,8 @@ __device__ __forceinline__ float score_generic(float x, const SegC& sc, const Ro
 
 // EX: the instantiation that carries the EXPL form (explicit int32 side inputs); the compact
 // instantiation stays free of its code and register pressure.
-template <bool EX, bool DROP>
+// ABSORB: literal-`neg` mode compiled out (see tc_bwd.cu)
+template <bool EX, bool DROP, bool ABSORB = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k0,
               const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_k1,
@@ -384,7 +385,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // |neg| <= 1e5 ("literal" mode): a masked score still carries x * scale + rel, so FAST groups with
     // masked rows take the per-element EDGE form.  Masked groups are skipped (p == 0 exactly) only when
     // neg is negative enough for exp(neg + 64) to flush to zero, against a real (unmasked) maximum.
-    const bool lit = fabsf(a.neg) <= 1e5f;
+    const bool lit = ABSORB ? false : fabsf(a.neg) <= 1e5f;
     const bool skip_ok = a.neg < -200.f;
     const float real_thr = 0.5f * a.neg;
     const uint32_t drow = DROP ? dropout_row_base(dropout_salt(a.drop, (uint32_t)(b * a.H + h)), i) : 0u;
@@ -834,6 +835,7 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
     set(tc_fwd_kernel<true, false>);
     set(tc_fwd_kernel<false, true>);
     set(tc_fwd_kernel<true, true>);
+    set(tc_fwd_kernel<false, false, true>);
     return (int)e;
   });
   if (ae) return ae;
@@ -862,6 +864,7 @@ int tc_launch_fwd(const FwdArgs& a, cudaStream_t st) {
   if (ex && dr) launch(tc_fwd_kernel<true, true>);
   else if (ex) launch(tc_fwd_kernel<true, false>);
   else if (dr) launch(tc_fwd_kernel<false, true>);
+  else if (!(fabsf(a.neg) <= 1e5f)) launch(tc_fwd_kernel<false, false, true>);
   else launch(tc_fwd_kernel<false, false>);
   return (int)cudaGetLastError();
 }
