@@ -496,22 +496,60 @@ __global__ void __launch_bounds__(NT) table_grad_partial_kernel(const TableGradA
   if (tid < R) a.partial_bias[pidx * R + tid] = bacc;
 }
 
-__global__ void table_grad_reduce_kernel(const TableGradArgs a) {
+// Stage 2 of the table gradients: d_emb[p, h, :] = scale * sum_k partial[k, h, p, :] (k over batch x row chunks),
+// d_bias likewise.  One block per (p, h): 64 lanes across d (one coalesced 256-byte row per k), 8 slices of k
+// with independent loads in flight, combined through shared memory in a fixed order (deterministic).
+// HBM-read-bound: the partials are read exactly once.
+constexpr int TGR_X = 64, TGR_Y = 8;
+__global__ void __launch_bounds__(TGR_X * TGR_Y) table_grad_reduce_kernel(const TableGradArgs a) {
+  __shared__ float red[TGR_Y][TGR_X];
+  __shared__ float redb[TGR_Y];
   const int D = a.d;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over R*H*D then R*H
-  const int n_emb = a.R * a.H * D;
+  const int h = blockIdx.x % a.H, p = blockIdx.x / a.H;   // output order [R][H]
+  const int x = threadIdx.x, y = threadIdx.y;
   const int np = a.B * a.nchunk;
-  if (idx < n_emb) {
-    const int c = idx % D, h = (idx / D) % a.H, p = idx / (D * a.H);
+  const int64_t kstride = (int64_t)a.H * a.R * D;
+  for (int c0 = 0; c0 < D; c0 += TGR_X) {
+    const int c = c0 + x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < D) {
+      const float* src = a.partial + ((int64_t)h * a.R + p) * D + c;
+      int k = y;
+      for (; k + 3 * TGR_Y < np; k += 4 * TGR_Y) {
+        s0 += __ldg(src + (int64_t)k * kstride);
+        s1 += __ldg(src + (int64_t)(k + TGR_Y) * kstride);
+        s2 += __ldg(src + (int64_t)(k + 2 * TGR_Y) * kstride);
+        s3 += __ldg(src + (int64_t)(k + 3 * TGR_Y) * kstride);
+      }
+      for (; k < np; k += TGR_Y) s0 += __ldg(src + (int64_t)k * kstride);
+    }
+    red[y][x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (y == 0 && c < D) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < TGR_Y; ++j) s += red[j][x];
+      a.d_emb[((int64_t)p * a.H + h) * D + c] = s * a.scale;
+    }
+    __syncthreads();
+  }
+  // bias: lane x of slice y takes k = y * 64 + x, y * 64 + x + 512, ...
+  {
     float s = 0.f;
-    for (int k = 0; k < np; ++k) s += a.partial[(((int64_t)k * a.H + h) * a.R + p) * D + c];
-    a.d_emb[idx] = s * a.scale;
-  } else if (idx < n_emb + a.R * a.H) {
-    const int e = idx - n_emb;
-    const int h = e % a.H, p = e / a.H;
-    float s = 0.f;
-    for (int k = 0; k < np; ++k) s += a.partial_bias[((int64_t)k * a.H + h) * a.R + p];
-    a.d_bias[e] = s * a.scale;
+    for (int k = y * TGR_X + x; k < np; k += TGR_X * TGR_Y) s += __ldg(a.partial_bias + ((int64_t)k * a.H + h) * a.R + p);
+    red[y][x] = s;
+    __syncthreads();
+    if (x == 0) {
+      float t = 0.f;
+      for (int j = 0; j < TGR_X; ++j) t += red[y][j];
+      redb[y] = t;
+    }
+    __syncthreads();
+    if (x == 0 && y == 0) {
+      float t = 0.f;
+      for (int j = 0; j < TGR_Y; ++j) t += redb[j];
+      a.d_bias[p * a.H + h] = t * a.scale;
+    }
   }
 }
 
@@ -558,8 +596,7 @@ cudaError_t launch_table_grad_t(const TableGradArgs& a, cudaStream_t st) {
   table_grad_partial_kernel<T, D><<<grid, NT, 0, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int total = a.R * a.H * a.d + a.R * a.H;
-  table_grad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  table_grad_reduce_kernel<<<a.R * a.H, dim3(TGR_X, TGR_Y), 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -592,8 +629,7 @@ cudaError_t simt_launch_bwd_kv(const BwdKVArgs& a, int dtype, int d, cudaStream_
   MLT_DISPATCH(launch_bwd_kv_t, a);
 }
 cudaError_t simt_launch_table_grad_reduce(const TableGradArgs& a, cudaStream_t st) {
-  const int total = a.R * a.H * a.d + a.R * a.H;
-  table_grad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  table_grad_reduce_kernel<<<a.R * a.H, dim3(TGR_X, TGR_Y), 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t simt_launch_table_grad(const TableGradArgs& a, int dtype, cudaStream_t st) {
