@@ -26,6 +26,7 @@
 // group's geometry calls for.  m only moves when the bound outgrows it by 2^8 (then O is rescaled in
 // TMEM).  Every valid row sees its own diagonal key (same example id), so a masked key has weight
 // exactly 0 (exp(-1e9 + ...) flushes): masked rows / groups are simply skipped.
+#include <atomic>
 #include "tc_api.cuh"
 
 #include "gl2_geom.cuh"
@@ -74,14 +75,34 @@ struct Params {
   T4 out;
   float* stats;               // [B, H, L, 2]
   int pairs_per_bh, total_pairs;
+  unsigned* sched;            // {next pair after the first gridDim.x, CTAs done}: both 0 at launch, reset by the last CTA
 };
+
+// Work distribution: pair number blockIdx.x first, then whatever pair is next when the CTA is ready for one
+// (one atomic per pair).  CTAs that start late -- the SM was still running another kernel's blocks, as with
+// the global-row kernel that is launched beside this one -- take fewer pairs instead of finishing late.
+// The producer thread fetches the pair and publishes it to the other roles through a small ring.
+constexpr int NSQ = 4;
+__device__ unsigned g_sched_fwd[256][2];
 
 struct Bars {
   uint64_t q_full[2], q_empty[2];
   uint64_t kv_full[NST], kv_empty[NST];
   uint64_t rel_full[2], s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t sched_full[NSQ], sched_empty[NSQ];
   uint32_t tmem_base;
+  int32_t sched_pair[NSQ];
 };
+// consumer side of the pair ring: a whole (converged) warp, one arrival -- or a single elected thread
+template <bool WARP>
+__device__ __forceinline__ int sched_take(Bars* bars, int it, bool lane0) {
+  const int sq = it % NSQ;
+  mbar_wait(&bars->sched_full[sq], (it / NSQ) & 1);
+  const int pair = *reinterpret_cast<volatile int32_t*>(&bars->sched_pair[sq]);
+  if (WARP) __syncwarp();   // every lane has read the entry
+  if (lane0) mbar_arrive(&bars->sched_empty[sq]);
+  return pair;
+}
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
 // Geometry of one pair of tiles, identical in every role.  The kernel is specialised for
@@ -148,6 +169,10 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&bars->kv_full[s], 1);
       mbar_init(&bars->kv_empty[s], 2);   // two consumers (tiles); the MMA thread arrives for an absent one
     }
+    for (int s = 0; s < NSQ; ++s) {
+      mbar_init(&bars->sched_full[s], 1);
+      mbar_init(&bars->sched_empty[s], NSW + 1);   // the softmax warps and the MMA thread
+    }
     fence_barrier_init();
   }
   if (warp == NSW + 1) tmem_alloc<512>(&bars->tmem_base);
@@ -165,11 +190,18 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       prefetch_tensormap(&map_gk);
       prefetch_tensormap(&map_gv);
       prefetch_tensormap(&map_e);
-      int it = 0, kvc = 0;
-      for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x, ++it) {
-        const Pair q = make_pair(p, pair);
+      int kvc = 0;
+      for (int it = 0;; ++it) {
         const int buf = it & 1;
-        mbar_wait(&bars->q_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&bars->q_empty[buf], ((it >> 1) & 1) ^ 1);   // taken as late as possible: no pair is held back
+        int pair = it == 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(p.sched, 1u));
+        if (pair >= p.total_pairs) pair = -1;
+        const int sq = it % NSQ;
+        mbar_wait(&bars->sched_empty[sq], ((it / NSQ) & 1) ^ 1);
+        bars->sched_pair[sq] = pair;
+        mbar_arrive(&bars->sched_full[sq]);
+        if (pair < 0) break;
+        const Pair q = make_pair(p, pair);
         mbar_arrive_expect_tx(&bars->q_full[buf], 2 * TM * 128 + 32 * 128);
         tma_load_4d(smem + SM_Q + (buf * 2 + 0) * TM * 128, &map_q, &bars->q_full[buf], 0, q.i0, q.h, q.b);
         tma_load_4d(smem + SM_Q + (buf * 2 + 1) * TM * 128, &map_q, &bars->q_full[buf], 0, q.i0 + TM, q.h, q.b);
@@ -210,7 +242,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       uint32_t s_cnt[2] = {0, 0};    // S MMAs issued per tile slot (parity of s_full is kept by the softmax side)
       uint32_t p_cnt[2] = {0, 0};    // P chunks consumed per tile slot
       uint32_t tile_cnt[2] = {0, 0}; // tiles started per slot
-      for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x, ++it) {
+      for (;; ++it) {
+        const int pair = sched_take<false>(bars, it, true);
+        if (pair < 0) break;
         const Pair q = make_pair(p, pair);
         const int buf = it & 1;
         const int npc = NBAND + q.nglob;
@@ -312,7 +346,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #else
 #define ST(code) do {} while (0)
 #endif
-    for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+    for (int sit = 0;; ++sit) {
+      const int pair = sched_take<true>(bars, sit, lane == 0);
+      if (pair < 0) break;
       const Pair q = make_pair(p, pair);
       if (!tile_exists(q, w)) continue;
       const int b = q.b, h = q.h;
@@ -637,6 +673,10 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   tc_fence_before_sync();
   __syncthreads();
   if (warp == NSW + 1) tmem_dealloc<512>(tmem);
+  if (tid == 0 && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {   // every CTA has taken its last pair
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+  }
 }
 
 }  // namespace gl2
@@ -669,11 +709,14 @@ bool gl2_fwd_long_supported(const FwdArgs& a, int dtype, int d) {
 int gl2_launch_fwd_long(const FwdArgs& a, cudaStream_t st) {
   static PerDeviceOnce once;
   static int sm_count[64];
+  static unsigned* sched_base[64];
+  static std::atomic<unsigned> sched_slot{0};
   const int ae = once.run([] {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaError_t e = cudaFuncSetAttribute(gl2::gl2_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          gl2::SM_ALLOC);
+    if (e == cudaSuccess) e = cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base[dev]), gl2::g_sched_fwd);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     return (int)e;
   });
@@ -693,6 +736,8 @@ int gl2_launch_fwd_long(const FwdArgs& a, cudaStream_t st) {
   p.stats = a.stats;
   p.pairs_per_bh = (p.L + 2 * gl2::TM - 1) / (2 * gl2::TM);
   p.total_pairs = p.pairs_per_bh * a.B * a.H;
+  // launches that may overlap in time use different counters (256 in rotation, each left at zero by its kernel)
+  p.sched = sched_base[dev] + 2 * (sched_slot.fetch_add(1, std::memory_order_relaxed) % 256);
   CUtensorMap mq, mk, mv, mgk, mgv, me;
   int e = 0;
   e |= make_qkv_tensor_map(&mq, a.rows.q.ptr, a.rows.q.sb, a.rows.q.sl, a.rows.q.sh, a.B, p.L, a.H, gl2::TM);

@@ -23,6 +23,15 @@ a.record()
 for _ in range(20): step()
 b.record(); torch.cuda.synchronize()
 print('step ms', a.elapsed_time(b) / 20)
+def fwd():
+  with torch.no_grad():
+    ops.global_local_attention(*leaves, local_radius=shape.local_radius, side=compact, impl=impl)
+for _ in range(3): fwd()
+torch.cuda.synchronize()
+a.record()
+for _ in range(20): fwd()
+b.record(); torch.cuda.synchronize()
+print('forward only ms', a.elapsed_time(b) / 20)
 _lib.profile_enable(True)
 for _ in range(3): step()
 torch.cuda.synchronize()
