@@ -17,6 +17,7 @@
 // TMEM (512 columns): S0 [128] S1 [128] dP / dS [128] dQ [64] allrel / dallrel 2 x [32]; the table-gradient
 // tile (M = 64) reuses S1 after the last chunk.  The MMA warp starts the next tile (allrel, S_0, dP_0) as
 // soon as this tile's last MMAs are issued, i.e. under the elementwise warps' epilogue.
+#include <atomic>
 #include "tc_api.cuh"
 
 #include "gl2_geom.cuh"
@@ -81,14 +82,28 @@ struct Params {
   float* tg_partial_bias;        // [...][R]
   int lp, rw;
   int tiles_per_bh, total_tiles;
+  unsigned* sched;   // {next tile after the first gridDim.x, CTAs done}: 0 at launch, reset by the last CTA (see gl2_fwd.cu)
 };
 
+constexpr int NSQ = 4;   // ring of tile numbers, producer thread -> the other roles (dynamic distribution, gl2_fwd.cu)
+__device__ unsigned g_sched_bq[256][2];
 struct Bars {
   uint64_t q_full[2], q_empty[2];
   uint64_t kv_full[NST], kv_empty[NST];
   uint64_t rel_full, s_full[2], dp_full, ds_full, dar_full, dq_full, tile_done;
+  uint64_t sched_full[NSQ], sched_empty[NSQ];
   uint32_t tmem_base;
+  int32_t sched_tile[NSQ];
 };
+template <bool WARP>
+__device__ __forceinline__ int sched_take(Bars* bars, int it, bool lane0) {
+  const int sq = it % NSQ;
+  mbar_wait(&bars->sched_full[sq], (it / NSQ) & 1);
+  const int t = *reinterpret_cast<volatile int32_t*>(&bars->sched_tile[sq]);
+  if (WARP) __syncwarp();   // every lane has read the entry
+  if (lane0) mbar_arrive(&bars->sched_empty[sq]);
+  return t;
+}
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
 struct Tile {
@@ -136,6 +151,10 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_init(&bars->kv_full[s], 1);
       mbar_init(&bars->kv_empty[s], 1);
     }
+    for (int s = 0; s < NSQ; ++s) {
+      mbar_init(&bars->sched_full[s], 1);
+      mbar_init(&bars->sched_empty[s], NEWARPS + 1);   // the elementwise warps and the MMA thread
+    }
     mbar_init(&bars->rel_full, 1);
     mbar_init(&bars->dp_full, 1);
     mbar_init(&bars->ds_full, NEW);
@@ -156,11 +175,18 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   if (warp == NEWARPS) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int it = 0, kvc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const Tile q = make_tile(p, t);
+      int kvc = 0;
+      for (int it = 0;; ++it) {
         const int buf = it & 1;
         mbar_wait(&bars->q_empty[buf], ((it >> 1) & 1) ^ 1);
+        int t = it == 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(p.sched, 1u));
+        if (t >= p.total_tiles) t = -1;
+        const int sq = it % NSQ;
+        mbar_wait(&bars->sched_empty[sq], ((it / NSQ) & 1) ^ 1);
+        bars->sched_tile[sq] = t;
+        mbar_arrive(&bars->sched_full[sq]);
+        if (t < 0) break;
+        const Tile q = make_tile(p, t);
         mbar_arrive_expect_tx(&bars->q_full[buf], 2 * TM * 128 + 32 * 128);
         uint8_t* qs = smem + SM_Q + buf * 2 * TM * 128;
         tma_load_4d(qs, &map_q, &bars->q_full[buf], 0, q.i0, q.h, q.b);
@@ -226,8 +252,9 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           umma_ss(tmem + T_DP, sdesc(do_addr).at(kk * 32), sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->dp_full);
       };
-      if ((int)blockIdx.x < p.total_tiles) start_tile(0, 0);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int t = sched_take<false>(bars, 0, true);
+      if (t >= 0) start_tile(0, 0);
+      for (; t >= 0; ++it) {
         const Tile q = make_tile(p, t);
         const int buf = it & 1;
         const int nc = 2 + q.nglob;
@@ -280,7 +307,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         kv_base += nc;
         // next tile's prologue under this tile's epilogue: allrel -> the other buffer, S_0 -> S0 (free since the
         // last even chunk), dP_0 -> dP (its dS was consumed by the dQ MMAs above: MMAs execute in issue order)
-        if (t + (int)gridDim.x < p.total_tiles) start_tile(it + 1, kv_base);
+        t = sched_take<false>(bars, it + 1, true);
+        if (t >= 0) start_tile(it + 1, kv_base);
       }
     }
   } else {
@@ -299,7 +327,9 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int D = p.D, R = p.R;
     const bool d12 = (D == 12);
     uint32_t it = 0, s_par[2] = {0, 0}, dp_par = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (;; ++it) {
+      const int t = sched_take<true>(bars, (int)it, lane == 0);
+      if (t < 0) break;
       const Tile q = make_tile(p, t);
       const int b = q.b, h = q.h;
       const int i = q.i0 + row;
@@ -659,6 +689,10 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   if (warp == NEWARPS + 1) tmem_dealloc<512>(tmem);
+  if (tid == 0 && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {   // every CTA has taken its last tile
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+  }
 }
 
 }  // namespace bq
@@ -689,11 +723,14 @@ int gl2_launch_bwd_q_long(const BwdQArgs& a, const float4* rowstat, float* rec_w
   using namespace gl2;
   static PerDeviceOnce once;
   static int sm_count[64];
+  static unsigned* sched_base[64];
+  static std::atomic<unsigned> sched_slot{0};
   const int ae = once.run([] {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaError_t e = cudaFuncSetAttribute(bq::gl2_bwd_q_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          bq::SM_ALLOC);
+    if (e == cudaSuccess) e = cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base[dev]), bq::g_sched_bq);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     return (int)e;
   });
@@ -717,6 +754,7 @@ int gl2_launch_bwd_q_long(const BwdQArgs& a, const float4* rowstat, float* rec_w
   p.rw = rw;
   p.tiles_per_bh = (p.L + TM - 1) / TM;
   p.total_tiles = p.tiles_per_bh * a.B * a.H;
+  p.sched = sched_base[dev] + 2 * (sched_slot.fetch_add(1, std::memory_order_relaxed) % 256);
   CUtensorMap mq, mdo, mk, mv, mgk, mgv, me;
   int e = 0;
   e |= make_qkv_tensor_map(&mq, a.rows.q.ptr, a.rows.q.sb, a.rows.q.sl, a.rows.q.sh, a.B, p.L, a.H, TM);
