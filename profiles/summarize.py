@@ -104,7 +104,7 @@ def main():
     names = {'fwd': ('tc_fwd_global_rows', 'tc_fwd_long_rows'),
              'bwd_q': ('tc_bwd_q_global_rows', 'tc_bwd_q_long_rows'),
              'bwd_kv': ('tc_bwd_kv_global_keys', 'tc_bwd_kv_long_keys')}[kind]
-    if len(lst) > 1:
+    if len(lst) > 1 and small[0] != large[0]:
       out[names[0]] = {'grid': small[0], 'dram_bytes_per_launch': small[1]}
       out[names[1]] = {'grid': large[0], 'dram_bytes_per_launch': large[1]}
     else:                            # only the global-row launch of this family is left on the general kernels
