@@ -246,6 +246,38 @@ class MltGlAttnGradOp : public tf::OpKernel {
 }  // namespace
 
 // ---- op registrations ------------------------------------------------------------------------------
+// Recognition of generator-shaped explicit side inputs, once per batch: the eight int32 tensors of
+// make_global_local_transformer_side_inputs -> compact descriptors + result int32[4] (result[0] = 1 iff the
+// descriptors reproduce every element of all eight; result[1] = max_distance).  Feed MltGlAttnCompact under
+// tf.cond(result[0] == 1, ...) and MltGlAttn otherwise.
+class MltGlSideInputsToCompactOp : public tf::OpKernel {
+ public:
+  explicit MltGlSideInputsToCompactOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("local_radius", &radius_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& l2l = ctx->input(0);
+    const tf::Tensor& l2g = ctx->input(2);
+    OP_REQUIRES(ctx, l2l.dims() == 3 && l2g.dims() == 3, tf::errors::InvalidArgument("side inputs must be [B, rows, cols]"));
+    const int64_t B = l2l.dim_size(0), L = l2l.dim_size(1), G = l2g.dim_size(2);
+    const int32_t* in[8];
+    for (int i = 0; i < 8; ++i) in[i] = Ids(ctx->input(i));
+    tf::Tensor *le, *ge, *sid, *res;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, L}), &le));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, G}), &ge));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({B, L}), &sid));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({4}), &res));
+    MLT_OP_CALL(ctx,
+                mlt_gl_compact_from_explicit(in, static_cast<int32_t>(B), static_cast<int32_t>(L), static_cast<int32_t>(G),
+                                             radius_, le->flat<tf::int32>().data(), ge->flat<tf::int32>().data(),
+                                             sid->flat<tf::int32>().data(), res->flat<tf::int32>().data(),
+                                             ctx->eigen_gpu_device().stream()),
+                "mlt_gl_compact_from_explicit");
+  }
+ private:
+  int radius_;
+};
+
 #define MLT_QKV_TABLES                                                                                  \
   .Input("long_q: T").Input("long_k: T").Input("long_v: T")                                             \
   .Input("global_q: T").Input("global_k: T").Input("global_v: T")                                       \
@@ -298,6 +330,11 @@ REGISTER_OP("MltGlAttnCompact") MLT_QKV_TABLES MLT_COMPACT_SIDE .Input("seed: in
     .Attr("max_distance: int").SetShapeFn(GlFwdShape);
 REGISTER_OP("MltGlAttnCompactGrad") MLT_QKV_TABLES MLT_COMPACT_SIDE .Input("seed: int64") MLT_GL_GRAD_TAIL MLT_GL_ATTRS
     .Attr("max_distance: int").SetShapeFn(GradShape10);
+
+REGISTER_OP("MltGlSideInputsToCompact") MLT_EXPLICIT_SIDE
+    .Output("long_example_ids: int32").Output("global_example_ids: int32").Output("sentence_ids: int32")
+    .Output("result: int32").Attr("local_radius: int");
+REGISTER_KERNEL_BUILDER(Name("MltGlSideInputsToCompact").Device(tf::DEVICE_GPU), MltGlSideInputsToCompactOp);
 
 #define MLT_REGISTER(NAME, ...)                                                                          \
   REGISTER_KERNEL_BUILDER(Name(NAME).Device(tf::DEVICE_GPU).TypeConstraint<float>("T").HostMemory("seed"), \

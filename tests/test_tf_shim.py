@@ -46,8 +46,11 @@ def _snake(name):
 def test_python_binding_matches_op_registrations():
   ops, kernels = _registered_ops()
   assert set(ops) == {'MltDenseRelAttn', 'MltDenseRelAttnGrad', 'MltGlAttn', 'MltGlAttnGrad', 'MltGlAttnCompact',
-                      'MltGlAttnCompactGrad'}
-  assert kernels == set(ops)                                     # every op has GPU kernels for float and bfloat16
+                      'MltGlAttnCompactGrad', 'MltGlSideInputsToCompact'}
+  # every attention op has GPU kernels for float and bfloat16; the side-input op is integer-only
+  assert kernels == set(ops) - {'MltGlSideInputsToCompact'}
+  assert ops['MltGlSideInputsToCompact']['inputs'] == ops['MltGlAttn']['inputs'][10:18]
+  assert ops['MltGlSideInputsToCompact']['outputs'][:3] == ops['MltGlAttnCompact']['inputs'][10:13]
   # forward / gradient pairs line up: grad inputs = forward inputs + forward outputs + output gradients
   for fwd, n_dout in (('MltDenseRelAttn', 1), ('MltGlAttn', 2), ('MltGlAttnCompact', 2)):
     f, g = ops[fwd], ops[fwd + 'Grad']
