@@ -90,6 +90,25 @@ def test_validation_codes_without_gpu(lib):
   assert lib.mlt_gl_workspace_bytes(C.byref(p), 1) > lib.mlt_gl_workspace_bytes(C.byref(p), 0)
 
 
+def test_recognition_entry_points_validate_before_touching_the_device(lib):
+  hint = _lib.IdLayout(0, 0, -1)
+  one = C.c_void_p(16)   # never dereferenced: every call below fails validation first
+  assert lib.mlt_dense_compact_from_explicit(None, one, 1, 8, hint, one, one, one, None) == -1   # MLT_ERR_NULL
+  assert lib.mlt_dense_compact_from_explicit(one, one, 1, 8, hint, one, one, None, None) == -1
+  assert lib.mlt_dense_compact_from_explicit(one, one, 0, 8, hint, one, one, one, None) == -2    # MLT_ERR_SHAPE
+  assert lib.mlt_dense_compact_from_explicit(one, one, 1, 1, hint, one, one, one, None) == -2    # S < 2: no offset -1
+  # a 2-D layout needs its core size and distance, and must fit the sequence
+  assert lib.mlt_dense_compact_from_explicit(one, one, 1, 8, _lib.IdLayout(2, 0, 3), one, one, one, None) == -2
+  assert lib.mlt_dense_compact_from_explicit(one, one, 1, 8, _lib.IdLayout(2, 1, -1), one, one, one, None) == -2
+  assert lib.mlt_dense_compact_from_explicit(one, one, 1, 8, _lib.IdLayout(3, 1, 3), one, one, one, None) == -2
+  arr = (C.c_void_p * 8)(*([16] * 8))
+  assert lib.mlt_gl_compact_from_explicit(None, 1, 8, 2, 2, one, one, one, one, None) == -1
+  assert lib.mlt_gl_compact_from_explicit(C.byref(arr), 1, 8, 2, 2, one, one, one, None, None) == -1
+  assert lib.mlt_gl_compact_from_explicit(C.byref(arr), 1, 8, 2, 0, one, one, one, one, None) == -2   # radius < 1
+  arr[5] = None                                                                                      # all eight required
+  assert lib.mlt_gl_compact_from_explicit(C.byref(arr), 1, 8, 2, 2, one, one, one, one, None) == -1
+
+
 def test_ops_refuse_cpu_tensors():
   import torch
   from mlt_b200 import ops
