@@ -327,23 +327,37 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int D = p.D, R = p.R;
     const bool d12 = (D == 12);
     uint32_t it = 0, s_par[2] = {0, 0}, dp_par = 0;
-    for (;; ++it) {
-      const int t = sched_take<true>(bars, (int)it, lane == 0);
-      if (t < 0) break;
+    // row scalars of a tile (example id, sentence, forward statistics): loaded one tile ahead, under the
+    // epilogue of the previous tile
+    struct RowPre { int q_e, q_sent; float4 rs4; };
+    auto row_pre = [&](int t_) {
+      RowPre r;
+      r.q_e = -2; r.q_sent = -1; r.rs4 = make_float4(0.f, 1.f, 0.f, 0.f);
+      if (t_ >= 0) {
+        const Tile q_ = make_tile(p, t_);
+        const int i_ = q_.i0 + row;
+        if (i_ < p.L) {
+          r.q_e = __ldg(p.long_eid + (int64_t)q_.b * p.L + i_);
+          r.q_sent = __ldg(p.sent + (int64_t)q_.b * p.L + i_);
+          r.rs4 = __ldg(p.rowstat + (int64_t)(q_.b * p.H + q_.h) * p.lp + i_);
+        }
+      }
+      return r;
+    };
+    int t = sched_take<true>(bars, 0, lane == 0);
+    RowPre pre = row_pre(t);
+    for (; t >= 0; ++it) {
       const Tile q = make_tile(p, t);
       const int b = q.b, h = q.h;
       const int i = q.i0 + row;
       const bool row_ok = i < p.L;
       const int a_lo = q.i0 + quad * 32;
       if (tid == 0) GTRACE(0, 0);
-      int q_e = -2, q_sent = -1;
+      const int q_e = pre.q_e, q_sent = pre.q_sent;
       float nm2l = -INFINITY, delta = 0.f;
       if (row_ok) {
-        q_e = __ldg(p.long_eid + (int64_t)b * p.L + i);
-        q_sent = __ldg(p.sent + (int64_t)b * p.L + i);
-        const float4 rs4 = __ldg(p.rowstat + (int64_t)(b * p.H + h) * p.lp + i);
-        nm2l = __log2f(rs4.y) - rs4.x;     // -(m*log2e + log2 l)
-        delta = rs4.z;
+        nm2l = __log2f(pre.rs4.y) - pre.rs4.x;     // -(m*log2e + log2 l)
+        delta = pre.rs4.z;
       }
       // zero the bins; bias * scale * log2e of this head
       for (int x = 4 * tid; x < 32 * TM; x += 4 * NEW) *reinterpret_cast<float4*>(bins + x) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -609,6 +623,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       named_bar_sync(1, NEW);   // bins complete
       if (tid == 0) GTRACE(0, 40);
+      const int t_next = sched_take<true>(bars, (int)it + 1, lane == 0);
+      const RowPre pre_next = row_pre(t_next);
       {
         // each of the four column groups packs 8 ids: bf16 A operand (TMEM) for dQ += dallrel.E, the
         // dallrel^T tile for the table-gradient MMA, and the bias partial sums of the warp's 32 rows
@@ -627,15 +643,26 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                      : "memory");
         *reinterpret_cast<uint4*>(a_tile + row * 128 + (((c0 >> 3) ^ (row & 7)) << 4)) =
             make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+        {
+          // bias partial sums of the warp's 32 rows, 8 ids: halving exchange (8 -> 4 -> 2 -> 1 values per lane over
+          // lane bits 16, 8, 4), then two plain steps: 9 shuffles instead of 40, fixed order
+          const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+          float a4[4], a2[2];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          float r = w16[x];
-          r += __shfl_xor_sync(0xffffffffu, r, 16);
-          r += __shfl_xor_sync(0xffffffffu, r, 8);
-          r += __shfl_xor_sync(0xffffffffu, r, 4);
+          for (int x = 0; x < 4; ++x) {
+            const float keep = b16 ? w16[x + 4] : w16[x], give = b16 ? w16[x] : w16[x + 4];
+            a4[x] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+          }
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const float keep = b8 ? a4[x + 2] : a4[x], give = b8 ? a4[x] : a4[x + 2];
+            a2[x] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+          }
+          const float keep = b4 ? a2[1] : a2[0], give = b4 ? a2[0] : a2[1];
+          float r = keep + __shfl_xor_sync(0xffffffffu, give, 4);
           r += __shfl_xor_sync(0xffffffffu, r, 2);
           r += __shfl_xor_sync(0xffffffffu, r, 1);
-          if (lane == 0) bs[quad * 32 + c0 + x] = r;
+          if ((lane & 3) == 0) bs[quad * 32 + c0 + (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0)] = r;
         }
         tmem_wait_st();
         fence_proxy_async_smem();
@@ -647,13 +674,16 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       if (tid == 0) GTRACE(0, 42);
       tc_fence_after_sync();
       const int64_t pidx = ((int64_t)(b * p.tiles_per_bh + q.tile) * p.H + h);
+      uint32_t vq[16];
       {
         // table-gradient tile: M = 64 accumulator rows live in lanes {0-15, 32-47, 64-79, 96-111}; each column
         // group stores 16 of the 64 columns
         const int pid = quad * 16 + lane;
         uint32_t v[16];
         tmem_ld16(t_base + T_DE + hf * 16, v);
+        tmem_ld16(t_base + T_DQ + 16 * hf, vq);   // both read-outs in flight together
         tmem_wait_ld();
+        if (tid == 0) GTRACE(0, 44);
         if (lane < 16 && pid < R) {
           float4* dst = reinterpret_cast<float4*>(p.tg_partial + (pidx * R + pid) * 64 + hf * 16);
 #pragma unroll
@@ -662,12 +692,13 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                                  __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]));
         }
       }
+      if (tid == 0) GTRACE(0, 45);
       named_bar_sync(1, NEW);   // bias sums of all four quadrants are in shared memory
+      if (tid == 0) GTRACE(0, 46);
       if (tid < R) p.tg_partial_bias[pidx * R + tid] = (bs[tid] + bs[32 + tid]) + (bs[64 + tid] + bs[96 + tid]);
       {
-        uint32_t v[16];
-        tmem_ld16(t_base + T_DQ + 16 * hf, v);
-        tmem_wait_ld();
+        const uint32_t (&v)[16] = vq;
+        if (tid == 0) GTRACE(0, 47);
         if (row_ok) {
           __nv_bfloat16* dst = row_ptr_mut<__nv_bfloat16>(p.d_q, b, i, h) + 16 * hf;
 #pragma unroll
@@ -684,6 +715,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tc_fence_before_sync();
       mbar_arrive(&bars->tile_done);
       if (tid == 0) GTRACE(0, 43);
+      t = t_next;
+      pre = pre_next;
     }
   }
   tc_fence_before_sync();
