@@ -102,6 +102,22 @@ def test_batch16_slices_bit_identical():
       assert torch.equal(full[b:b + 1], single), (n, b)
 
 
+def test_tc_repeat_runs_are_bit_identical_including_table_gradients():
+  """The persistent kernels hand their tiles out dynamically (whichever CTA is free takes the next one): no
+  result may depend on that.  Two runs of the benchmarked shape (batch 4) agree bit for bit in every output
+  and gradient, the table gradients (summed over batch and tiles in a fixed order) included."""
+  seed_off, shape = synthetic.CONFIGS['c3_4096']
+  shape = dataclasses.replace(shape, batch=4)
+  x = synthetic.make_inputs(shape, seed=1234 + seed_off, dtype=torch.bfloat16)
+  side = compact_of(x, shape)
+  a = run_cuda_gl(x, shape, side, impl='tc')
+  for _ in range(2):
+    b = run_cuda_gl(x, shape, side, impl='tc')
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for n, ga, gb in zip(NAMES, a[2], b[2]):
+      assert torch.equal(ga, gb), n
+
+
 # ------------------------------------------------------------------------------------------
 # 2. The ABI's `neg` is honoured by both kernel families
 
