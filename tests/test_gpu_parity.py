@@ -252,10 +252,10 @@ TC_SHAPES = [
     (1, 50, 4, 2, 64, 32, 12),       # L < r
     (2, 300, 70, 2, 20, 20, 3),      # small radius, R not a multiple of 16, G > 64
     (1, 1024, 64, 2, 100, 64, 30),   # radius > chunk, R = 64: one-warp-set backward configurations
-    (1, 1100, 40, 2, 64, 32, 12),    # >= 16 chunks per global tile: two-warp-set backward configurations
+    (1, 1100, 40, 2, 64, 32, 12),    # >= 16 chunks per global tile: the two-warp-set query-centric backward
 ]
 # (Between them the shapes above select every launch configuration of the tcgen05 backward -- slim /
-# two CTAs per SM for the long rows and keys, two warp sets for tiles with many chunks, one warp set
+# two CTAs per SM for the long rows and keys, two warp sets for query tiles with many chunks, one warp set
 # for relative vocabularies > 32 -- through the library's own shape rules; no debug knobs.)
 
 
