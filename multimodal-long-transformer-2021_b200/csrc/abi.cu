@@ -668,12 +668,14 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
                        qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st,
                        p->impl != MLT_IMPL_TC_GENERIC));
   }
-  // Main stream: the long-key kernel (longest).  Side stream: global-key kernel, then the small
-  // table-gradient kernels, which only need the bins of the query-centric pass and are light
-  // enough (24 KB smem, 128 threads) to co-reside with the key-centric CTAs.
+  // Main stream: the long-key kernel (longest).  Side stream: the global-key kernel, then the small
+  // table-gradient kernels (they only need the bins of the query-centric pass).
   ForkScope fk2(st);
   cudaStream_t s2 = fk2.side();
   if (profile_enabled()) s2 = st;
+  // the few long-running tiles of the global keys go first, the many short tiles of the long keys fill in
+  MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
+                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), s2));
   MLT_TRY(launch_bwd_kv(kl, tc, ws_lg, p->dtype, p->d, "bwd_kv_long_keys", bh * 4 * dd * (p_l2l + p_lg),
                         qkv_bytes(bh, 6.0 * p->L + 2.0 * p->G, p->d, p->dtype, 1), st));
   if (p->R > 0) {
@@ -694,8 +696,6 @@ int mlt_gl_attn_bwd(const mlt_gl_params* p, const mlt_gl_grads* g, void* cuda_st
       else MLT_CUDA(simt_launch_table_grad(tg, p->dtype, s2));
     }
   }
-  MLT_TRY(launch_bwd_kv(kg, tc, ws_lg, p->dtype, p->d, "bwd_kv_global_keys", bh * 4 * dd * (p_lg + p_gg),
-                        qkv_bytes(bh, 2.0 * p->L + 6.0 * p->G, p->d, p->dtype, 1), s2));
   return MLT_OK;
 }
 
