@@ -199,11 +199,18 @@ struct SegC {          // warp-uniform
   int D, R, pd;
   bool perm;
   int col_base;        // dropout counter offset of key 0
+  int n_img;           // see plan::PSeg::n_img
 };
 struct RowC {          // per thread and segment
   int q_e, q_sent;
   float relP, relN, relX, relX1;
+  float relM;          // 2-D layout: the row's cross-modality constant (plan::C_MODAL)
 };
+__device__ __forceinline__ float rel_const(int ccls, const RowC& rc) {
+  return ccls == plan::C_POS ? rc.relP
+                             : (ccls == plan::C_NEG ? rc.relN
+                                                    : (ccls == plan::C_CROSS ? rc.relX : (ccls == plan::C_MODAL ? rc.relM : 0.f)));
+}
 
 __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm) {
   SegC sc;
@@ -218,12 +225,14 @@ __device__ __forceinline__ SegC make_segc(const KeySeg& sg, const SegRange& r, i
   sc.pd = pd;
   sc.perm = perm;
   sc.col_base = sg.col_base;
+  sc.n_img = (sg.side.id_rule == IDR_EXPLICIT && sg.side.npr > 0) ? sg.side.npr * sg.side.npr : 0;
   return sc;
 }
 
 __device__ __forceinline__ plan::PSeg make_pseg(const KeySeg& sg, const SegRange& r, int R, int pd, bool perm, bool ex) {
   plan::PSeg s;
-  s.n_img = 0;   // the 2-D shortcut is a forward-kernel form
+  // compact 2-D layout served through the library's id plane (abi.cu with_ids_plane keeps npr)
+  s.n_img = (ex && sg.side.id_rule == IDR_EXPLICIT && sg.side.npr > 0) ? sg.side.npr * sg.side.npr : 0;
   s.expl_ok = ex;
   s.c_begin = r.kb;
   s.c_end = r.ke;
@@ -253,7 +262,7 @@ __device__ __forceinline__ void row_loads(RowC& rc, const SegC& sc, int b, int i
 // `meta` = the id -> slot table of the tile (plan::rel_meta_init): one warp-broadcast LDS instead of the
 // branchy id -> slot rule in this once-per-tile (cold) code
 __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float* rel_s, const plan::RelMeta* meta,
-                                           int row) {
+                                           int row, int i) {
   auto rel_at = [&](int id) -> float {
     return (id >= 0 && id < sc.R) ? rel_s[meta[id].slot_off + row] : 0.f;
   };
@@ -262,6 +271,7 @@ __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float
   rc.relN = on ? rel_at(2 * sc.D) : 0.f;
   rc.relX = on ? rel_at(2 * sc.D + 1) : 0.f;
   rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
+  rc.relM = (on && sc.n_img > 0) ? rel_at(plan::modal_id(i, sc.n_img, sc.D)) : 0.f;
 }
 
 // Generic per-element evaluation (any rule): relative term (already * scale), mask and liveness.
@@ -641,10 +651,10 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (tid == 0) TRACE(1, 3);
     named_bar_sync(1, NALL);  // rel_s (written by set 0 / part 0) visible to all; bins zeroed
     if (tid == 0) TRACE(1, 4);
-    row_consts(rc0, sc0, rel_s, relmeta, row);
-    row_consts(rc1, sc1, rel_s, relmeta, row);
+    row_consts(rc0, sc0, rel_s, relmeta, row, i);
+    row_consts(rc1, sc1, rel_s, relmeta, row, i);
     // per-row accumulators of the constant relative classes (flushed into the bins at the end)
-    float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f;
+    float accP = 0.f, accN = 0.f, accX = 0.f, accX1 = 0.f, accM = 0.f;
     const float scale2 = a.scale * LOG2E;
 
     // One call per key segment (inlined twice: no per-field selects inside the chunk loop).
@@ -682,7 +692,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const bool mask_pe = (w0 & plan::F_MASK_PE) != 0;
         const bool masked = mre && !mask_pe && (rc.q_e != ce0);
         const int ccls = (int)((w0 >> 8) & 0xffu);
-        const float relc = ccls == plan::C_POS ? rc.relP : (ccls == plan::C_NEG ? rc.relN : (ccls == plan::C_CROSS ? rc.relX : 0.f));
+        const float relc = rel_const(ccls, rc);
         const int dcol = sc.col_base + g0;   // dropout counter of the group's first key
         uint32_t ds_pk[W / 2];
         bool zero = (mode == plan::DEAD);
@@ -721,6 +731,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (ccls == plan::C_POS) accP += tot;
           else if (ccls == plan::C_NEG) accN += tot;
           else if (ccls == plan::C_CROSS) accX += tot;
+          else if (EX && ccls == plan::C_MODAL) accM += tot;
         } else {
           float ds[W];
           if (mode == plan::GEN) {
@@ -871,6 +882,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if (ccls == plan::C_POS) accP += tot;
               else if (ccls == plan::C_NEG) accN += tot;
               else if (ccls == plan::C_CROSS) accX += tot;
+              else if (EX && ccls == plan::C_MODAL) accM += tot;
             } else if (mode == plan::DIAG) {
               // slot = clamp(d0 + x, 0, 2D).  The clamped ends are the constant classes (offset <= -D,
               // offset >= D): register accumulators.  Every interior slot belongs to exactly one key
@@ -954,6 +966,7 @@ tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       flush(2 * dd, accN);
       flush(2 * dd + 1, accX);
       flush(2 * dd + 2, accX1);
+      if (EX && sc0.n_img > 0) flush(plan::modal_id(i, sc0.n_img, dd), accM);
     }
     // ---- epilogue: dallrel (summed over parts) -> global + bf16 A-operand for dQ += dallrel.E ----
     if (tid == 0) TRACE(1, 5);
@@ -1161,6 +1174,7 @@ struct SrcC {            // warp-uniform, one per query source
   int mask_rule, id_rule;
   int col_base;          // dropout: position of this key set on the source rows' key axis
   Dropout drop;          // dropout descriptor of the source's row set
+  int n_img;             // see plan::PSeg::n_img
 };
 struct KeyC {            // per thread and source
   int k_e, k_sent;
@@ -1173,6 +1187,7 @@ __device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRan
   sc.R = src.q.rows.R;
   sc.D = src.q.side.max_distance;
   sc.rw = src.rw + 4;   // record stride (floats)
+  sc.n_img = (src.q.side.id_rule == IDR_EXPLICIT && src.q.side.npr > 0) ? src.q.side.npr * src.q.side.npr : 0;
   sc.band = src.q.band != 0;
   sc.radius = src.q.radius;
   sc.mask_rule = src.q.side.mask_rule;
@@ -1184,9 +1199,9 @@ __device__ __forceinline__ SrcC make_srcc(const TcQuerySource& src, const SrcRan
 
 __device__ __forceinline__ plan::PSeg make_kv_pseg(const TcQuerySource& src, const SrcRange& r, bool ex) {
   plan::PSeg s;
-  s.n_img = 0;   // the 2-D shortcut is a forward-kernel form
   s.expl_ok = ex;
   const Side& sd = src.q.side;
+  s.n_img = (ex && sd.id_rule == IDR_EXPLICIT && sd.npr > 0) ? sd.npr * sd.npr : 0;
   s.c_begin = r.ib;
   s.c_end = r.ie;
   s.c_len = src.q.rows.len;
@@ -1462,7 +1477,11 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         if (lit && mode == plan::FAST && __any_sync(0xffffffffu, masked)) mode = plan::EDGE;
         const int ccls = (int)((w0 >> 8) & 0xffu);
         // record field of the group's constant class
-        const int coff = ccls == plan::C_POS ? 4 + sc.D : (ccls == plan::C_NEG ? 4 + 2 * sc.D : (ccls == plan::C_CROSS ? 5 + 2 * sc.D : 0));
+        int coff = ccls == plan::C_POS ? 4 + sc.D : (ccls == plan::C_NEG ? 4 + 2 * sc.D : (ccls == plan::C_CROSS ? 5 + 2 * sc.D : 0));
+        if (EX && ccls == plan::C_MODAL) {   // the group's queries are all text or all image
+          const int idm = plan::modal_id(g0w, sc.n_img, sc.D);
+          coff = idm < sc.R ? 4 + idm : 0;
+        }
         // the thread's W columns are processed in sub-slices of WS (SLIM: 16, to stay within the
         // register budget of two CTAs per SM); packed results of sub-slice hh land in the first half
         // of the columns already consumed
@@ -1755,9 +1774,13 @@ struct BqLaunch {
   static void run(bool ex, bool dr, dim3 grid, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdo,
                   const CUtensorMap& mk0, const CUtensorMap& mv0, const CUtensorMap& mk1, const CUtensorMap& mv1,
                   const CUtensorMap& me, const TcBwdQParams& p) {
-    if (ex && dr) go<true, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
-    else if (ex) go<true, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
-    else if (dr) go<false, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    // the two-warp-set configuration does not carry the EXPL form (19 warps: 96 registers per thread, the form
+    // spilled 1.9 KB there); the launcher sends explicit side inputs to the one-warp-set configuration
+    if constexpr (SETS == 1) {
+      if (ex && dr) return go<true, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+      if (ex) return go<true, false>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
+    }
+    if (dr) go<false, true>(grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
     else if (absorbed(p))
       tc_bwd_q_kernel<SETS, SLIM, false, false, true><<<grid, bq_threads<SETS, SLIM>(), bq::Cfg<SLIM>::SM_ALLOC, st>>>(
           mq, mdo, mk0, mv0, mk1, mv1, me, p);
@@ -1770,9 +1793,11 @@ struct BqLaunch {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::Cfg<SLIM>::SM_ALLOC);
     };
     set(tc_bwd_q_kernel<SETS, SLIM, false, false>);
-    set(tc_bwd_q_kernel<SETS, SLIM, true, false>);
     set(tc_bwd_q_kernel<SETS, SLIM, false, true>);
-    set(tc_bwd_q_kernel<SETS, SLIM, true, true>);
+    if constexpr (SETS == 1) {
+      set(tc_bwd_q_kernel<SETS, SLIM, true, false>);
+      set(tc_bwd_q_kernel<SETS, SLIM, true, true>);
+    }
     set(tc_bwd_q_kernel<SETS, SLIM, false, false, true>);
     return e;
   }
@@ -1871,6 +1896,7 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st, bool allow_gl2
   // explicit int32 side inputs: the instantiations that carry the EXPL form
   const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
   const bool dr = a.drop.thr != 0;
+  if (ex && cfg == 2) cfg = 1;   // measured equal (explicit global-local step 3.06 vs 3.08 ms), and free of spills
   if (cfg == 3) BqLaunch<1, true>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2) BqLaunch<2, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else BqLaunch<1, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);

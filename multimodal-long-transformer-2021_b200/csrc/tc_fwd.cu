@@ -178,10 +178,7 @@ __device__ __forceinline__ void row_consts(RowC& rc, const SegC& sc, const float
   rc.relX = on ? rel_at(2 * sc.D + 1) : 0.f;
   rc.relX1 = on ? rel_at(2 * sc.D + 2) : 0.f;
   rc.relM = 0.f;
-  if (on && sc.n_img > 0) {   // rel_id_2d: image_part_id = n_img + 8 + 2 D + 1, text_part_id = image_part_id + 1
-    const int image_part_id = sc.n_img + 8 + 2 * sc.D + 1;
-    rc.relM = rel_at(i >= sc.n_img ? image_part_id : image_part_id + 1);
-  }
+  if (on && sc.n_img > 0) rc.relM = rel_at(plan::modal_id(i, sc.n_img, sc.D));
 }
 __device__ __forceinline__ float rel_const(int ccls, const RowC& rc) {
   return ccls == plan::C_POS ? rc.relP

@@ -70,6 +70,10 @@ struct PSeg {
                          // (first n_img positions = patches) and the kernel carries C_MODAL: only
                          // image x image groups read the plane (reference src/feature_utils.py:114-184)
 };
+// id of a cross-modality pair by the query's kind (rel_id_2d: image_part_id = n_img + 8 + 2 D + 1)
+__host__ __device__ __forceinline__ int modal_id(int query_pos, int n_img, int D) {
+  return n_img + 8 + 2 * D + 1 + (query_pos >= n_img ? 0 : 1);
+}
 
 // Per-tile row-side sentence ranges (QS form): [rs_min[w], rs_max[w]] of quadrant w.
 struct RowSent {
@@ -135,8 +139,9 @@ __device__ __forceinline__ void plan_chunk(const PSeg& s, const ColLanes& cl, in
     bool expl = s.expl_ok && (s.mask_rule == MR_EXPLICIT || s.id_rule == IDR_EXPLICIT) &&
                 (s.id_rule == IDR_EXPLICIT || s.id_rule == IDR_NONE);
     int id_rule = s.id_rule;
-    if (expl && s.n_img > 0 && s.mask_rule == MR_EXAMPLE_ID && !s.rows_are_keys) {
-      // text x text pairs follow the 1-D rule, text x image / image x text pairs carry one id per row kind
+    if (expl && s.n_img > 0 && s.mask_rule == MR_EXAMPLE_ID) {
+      // text x text pairs follow the 1-D rule, text x image / image x text pairs carry one id per QUERY kind
+      // (query text -> image_part_id, query image -> text_part_id); the test is symmetric in rows and columns
       const bool r_txt = a >= s.n_img, r_img = a + 31 < s.n_img;
       const bool c_txt = g0 >= s.n_img, c_img = g0 + 31 < s.n_img;
       if (r_txt && c_txt) {

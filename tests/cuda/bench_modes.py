@@ -77,3 +77,27 @@ def dense(**kw):
 
 print(f'dense B {B} S {S}: explicit 1-D ids {timeit(dense(att_mask=mask, relative_att_ids=ids)):.3f} ms, '
       f'compact {timeit(dense(compact=ops.DenseCompactSideInputs(eid, max_distance=12))):.3f} ms')
+
+# dense, 2-D image + text layout (14 x 14 patches), forward + backward: compact descriptors and the reference's
+# explicit tensors (recognised per call here), relative vocabulary 32 and the shipped 49
+for R2 in (32, 49):
+  emb2 = (0.02 * torch.randn(R2, H, D, generator=g)).to(torch.bfloat16).cuda().requires_grad_()
+  bias2 = (0.02 * torch.randn(R2, H, generator=g)).to(torch.bfloat16).cuda().requires_grad_()
+  mask2, ids2 = ops.build_dense_side_inputs(eid, 12, num_patch_per_row=14, num_core_layers=2)
+  c2d = ops.DenseCompactSideInputs(eid, max_distance=12, num_patch_per_row=14, num_core_layers=2)
+
+  def dense2(**kw):
+    def f():
+      o = ops.dense_relative_attention(q, k, v, emb2, bias2, **kw)
+      o.backward(do)
+    return f
+
+  def fwd2(**kw):
+    def f():
+      with torch.no_grad():
+        ops.dense_relative_attention(q, k, v, emb2, bias2, **kw)
+    return f
+
+  print(f'dense 2-D ids, R {R2}: compact fwd+bwd {timeit(dense2(compact=c2d)):.3f} ms (fwd {timeit(fwd2(compact=c2d)):.3f}), '
+        f'explicit fwd+bwd {timeit(dense2(att_mask=mask2, relative_att_ids=ids2)):.3f} ms, '
+        f'1-D compact fwd+bwd {timeit(dense2(compact=ops.DenseCompactSideInputs(eid, max_distance=12))):.3f} ms')

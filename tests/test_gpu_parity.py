@@ -459,6 +459,38 @@ def test_tc_dense_2d_compact_backward_matches_simt_and_explicit():
       assert abs_err(got, want) < 2 * BF16_ABS * scale, name
 
 
+def test_tc_dense_2d_cross_modality_ids_inside_the_vocabulary():
+  """A 2-D layout small enough (6 x 6 patches, distance 3) for image_part_id = 51 / text_part_id = 52 to lie
+  inside a relative vocabulary of 64: the cross-modality groups then carry a real per-row constant and a real
+  table gradient (at 14 x 14 patches those ids fall outside the vocabulary and contribute nothing).
+  tcgen05 path (planner forms: 1-D for text x text, one id per query kind for text x image, the id plane for
+  image x image) against the SIMT kernels (closed rule) and the fp64 oracle, fwd + bwd."""
+  b, s, h, d, rv, npr, core, dist = 2, 300, 2, 64, 64, 6, 1, 3
+  gen = torch.Generator().manual_seed(23)
+  q, k, v, do = (torch.randn(b, s, h, d, generator=gen).bfloat16() for _ in range(4))
+  emb = (torch.randn(rv, h, d, generator=gen) * 0.2).bfloat16()
+  bias = (torch.randn(rv, h, generator=gen) * 0.5).bfloat16()
+  e = (torch.arange(s)[None] < torch.tensor([[300], [217]])).int()
+  compact = ops.DenseCompactSideInputs(e.cuda(), max_distance=dist, num_patch_per_row=npr, num_core_layers=core)
+  ids_host = torch.tensor(fo.MmtRelativePositionOracle(npr, core, dist).make_relative_att_ids(s))
+  assert int(ids_host.max()) == npr * npr + 8 + 2 * dist + 2 < rv        # text_part_id is a real table row
+  results = []
+  for impl in ('tc', 'simt'):
+    dev = [t.cuda().requires_grad_() for t in (q, k, v, emb, bias)]
+    out = ops.dense_relative_attention(*dev, impl=impl, compact=compact)
+    (out.float() * do.cuda().float()).sum().backward()
+    results.append([out.detach()] + [t.grad for t in dev])
+  ref = [t.double().requires_grad_() for t in (q, k, v, emb, bias)]
+  mask = torch.tensor(fo.make_segmented_att_mask(e.numpy()))
+  ro = ao.qkv_relative_attention(ref[0], ref[1], ref[2], mask, ids_host[None].expand(b, s, s), ref[3], ref[4])
+  (ro * do.double()).sum().backward()
+  want_all = [ro.detach()] + [t.grad for t in ref]
+  for name, got, simt, want in zip('out q k v emb bias'.split(), results[0], results[1], want_all):
+    scale = max(1.0, want.abs().max().item())
+    assert abs_err(got, want) < 2 * BF16_ABS * scale, name
+    assert abs_err(got, simt.double().cpu()) < 2 * BF16_ABS * scale, name
+
+
 @pytest.mark.parametrize('seed', range(6))
 def test_tc_random_shapes_explicit_match_simt(seed):
   """Property test of the EXPL form over (B, L, G, H, radius, R, D): explicit int32 side inputs built by the
