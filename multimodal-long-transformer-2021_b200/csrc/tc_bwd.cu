@@ -1896,7 +1896,10 @@ int tc_launch_bwd_q(const BwdQArgs& a, void* ws, cudaStream_t st, bool allow_gl2
   // explicit int32 side inputs: the instantiations that carry the EXPL form
   const bool ex = side_is_explicit(a.seg[0].side) || (a.nseg > 1 && side_is_explicit(a.seg[1].side));
   const bool dr = a.drop.thr != 0;
-  if (ex && cfg == 2) cfg = 1;   // measured equal (explicit global-local step 3.06 vs 3.08 ms), and free of spills
+  // explicit side inputs (and the 2-D id plane): the one-warp-set configuration.  Against two warp sets it
+  // measures equal (explicit global-local step 3.06 vs 3.08 ms) and is free of their 1.9 KB of spills; against
+  // the slim configuration it is faster from 8 chunks on (dense S 512 with the 2-D plane, fwd + bwd 1.06 -> 0.93 ms)
+  if (ex && est_chunks >= 8) cfg = 1;
   if (cfg == 3) BqLaunch<1, true>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else if (cfg == 2) BqLaunch<2, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
   else BqLaunch<1, false>::run(ex, dr, grid, st, mq, mdo, mk0, mv0, mk1, mv1, me, p);
@@ -1943,8 +1946,9 @@ int tc_launch_bwd_kv(const BwdKVArgs& a, void* const ws[2], cudaStream_t st) {
   // (0.214 vs 0.226 ms on c3_4096, the same ratio at L = 2048 and 8192), and it is the one configuration
   // that holds relative vocabularies > 32.
   const bool slim_ok = p.src[0].rw <= 32 && p.src[1].rw <= 32;
-  const int cfg = est_chunks >= 16 ? 1 : (slim_ok ? 3 : 1);
   const bool ex = side_is_explicit(a.src[0].side) || (a.nsrc > 1 && side_is_explicit(a.src[1].side));
+  // (explicit side inputs: the slim configuration only below 8 chunks, as in the query-centric pass)
+  const int cfg = est_chunks >= (ex ? 8 : 16) ? 1 : (slim_ok ? 3 : 1);
   const bool dr = a.src[0].drop.thr != 0;
   if (cfg == 3) BkLaunch<2, 1, true>::run(ex, dr, grid, st, mk, mv, mq, mdo, p);
   else BkLaunch<4, 1, false>::run(ex, dr, grid, st, mk, mv, mq, mdo, p);
