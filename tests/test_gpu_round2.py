@@ -118,6 +118,40 @@ def test_tc_repeat_runs_are_bit_identical_including_table_gradients():
       assert torch.equal(ga, gb), n
 
 
+def test_concurrent_callers_on_their_own_streams():
+  """Two host threads, each on its own CUDA stream, run forward + backward at the same time (TF's inter-op pool
+  does this): the library's per-device state -- side-stream pool, tensor-map cache, the tile counters of the
+  persistent kernels -- must not let the calls disturb one another.  Every result equals the serial one."""
+  import threading
+  seed_off, shape = synthetic.CONFIGS['c3_4096']
+  shape = dataclasses.replace(shape, batch=2)
+  cases = []
+  for k in range(2):
+    x = synthetic.make_inputs(shape, seed=77 + k, dtype=torch.bfloat16)
+    cases.append((x, compact_of(x, shape), run_cuda_gl(x, shape, compact_of(x, shape), impl='tc')))
+  errors = []
+
+  def worker(k):
+    try:
+      x, side, want = cases[k]
+      stream = torch.cuda.Stream()
+      with torch.cuda.stream(stream):
+        for _ in range(6):
+          got = run_cuda_gl(x, shape, side, impl='tc')
+          assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+          for n, ga, gb in zip(NAMES, got[2], want[2]):
+            assert torch.equal(ga, gb), n
+    except BaseException as e:   # noqa: BLE001  (reported in the main thread)
+      errors.append((k, repr(e)))
+
+  threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  assert not errors, errors
+
+
 # ------------------------------------------------------------------------------------------
 # 2. The ABI's `neg` is honoured by both kernel families
 
