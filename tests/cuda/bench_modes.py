@@ -101,3 +101,13 @@ for R2 in (32, 49):
   print(f'dense 2-D ids, R {R2}: compact fwd+bwd {timeit(dense2(compact=c2d)):.3f} ms (fwd {timeit(fwd2(compact=c2d)):.3f}), '
         f'explicit fwd+bwd {timeit(dense2(att_mask=mask2, relative_att_ids=ids2)):.3f} ms, '
         f'1-D compact fwd+bwd {timeit(dense2(compact=ops.DenseCompactSideInputs(eid, max_distance=12))):.3f} ms')
+
+# attention-probability dropout 0.1 (the reference's training default), dense S 512
+for label, kw in (('1-D compact', dict(compact=ops.DenseCompactSideInputs(eid, max_distance=12))),
+                  ('2-D compact', dict(compact=c2d))):
+  def drop_step(p):
+    def f():
+      o = ops.dense_relative_attention(q, k, v, emb2, bias2, dropout_p=p, dropout_seed=5, **kw)
+      o.backward(do)
+    return f
+  print(f'dense {label}, R {R2}: fwd+bwd without dropout {timeit(drop_step(0.0)):.3f} ms, with dropout 0.1 {timeit(drop_step(0.1)):.3f} ms')
