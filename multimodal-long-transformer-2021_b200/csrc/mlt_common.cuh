@@ -59,8 +59,9 @@ struct KeySeg {
 // keep(i, col) is a pure function of (seed, batch, head, row set, query row i, column col), where
 // col indexes the row's concatenated key axis (segment 0 first).  Forward, both backward passes, the
 // SIMT and the tcgen05 kernels and the numpy restatement in tests/ all evaluate the same function, so
-// the mask is never stored.  The hash is the 32-bit finaliser "lowbias32" (two multiplies, three
-// xor-shifts) over a per-(batch, head, row set) salted linear counter; keep iff hash >= thr with
+// the mask is never stored.  The per-(batch, head, row set) salt comes from the 32-bit finaliser "lowbias32"
+// (mix32: two multiplies, three xor-shifts); the per-element hash over the salted linear counter is the lighter
+// mix_elem (it runs once per score element in three kernels); keep iff hash >= thr with
 // thr = floor(p * 2^32): the rate is exact to 2^-32.
 struct Dropout {
   uint32_t thr;        // 0: dropout off
@@ -77,6 +78,14 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
+// per-element hash: two multiplies, one xor-shift (the counter is already salted by a full mix32; the
+// comparison with the threshold reads the high bits, which the final multiply mixes best)
+__host__ __device__ __forceinline__ uint32_t mix_elem(uint32_t x) {
+  x *= 0x9e3779b1U;
+  x ^= x >> 15;
+  x *= 0x85ebca77U;
+  return x;
+}
 // salt of one (batch * H + head, row set) unit
 __host__ __device__ __forceinline__ uint32_t dropout_salt(const Dropout& d, uint32_t bh) {
   return mix32(d.seed_lo ^ mix32(d.seed_hi + 0x9e3779b9U * (2u * bh + d.rowset + 1u)));
@@ -86,7 +95,7 @@ __host__ __device__ __forceinline__ uint32_t dropout_row_base(uint32_t salt, int
   return salt + (uint32_t)i * 0x00010001U;
 }
 __host__ __device__ __forceinline__ bool dropout_keep(uint32_t row_base, int col, uint32_t thr) {
-  return mix32(row_base + (uint32_t)col) >= thr;
+  return mix_elem(row_base + (uint32_t)col) >= thr;
 }
 
 struct RowSet {  // query rows + the tables of their attention core

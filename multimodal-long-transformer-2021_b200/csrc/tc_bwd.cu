@@ -1451,7 +1451,7 @@ tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       const uint32_t dthr = sc.drop.thr;
       const float dinv = sc.drop.inv_keep;
       const uint32_t dkey = DROP ? dropout_salt(sc.drop, (uint32_t)(b * p.H + h)) + (uint32_t)(sc.col_base + j) : 0u;
-      auto keep_at = [&](int i) -> bool { return mix32(dkey + (uint32_t)i * 0x00010001U) >= dthr; };
+      auto keep_at = [&](int i) -> bool { return mix_elem(dkey + (uint32_t)i * 0x00010001U) >= dthr; };
 #pragma unroll 1
       for (; c < c_end; c += SETS) {
         const int st = c % NST;

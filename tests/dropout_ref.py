@@ -19,6 +19,14 @@ def mix32(x):
   return x
 
 
+def mix_elem(x):
+  x = np.asarray(x, dtype=np.uint64) & _M
+  x = (x * np.uint64(0x9e3779b1)) & _M
+  x ^= x >> np.uint64(15)
+  x = (x * np.uint64(0x85ebca77)) & _M
+  return x
+
+
 def keep_mask(seed, p, batch, heads, rows, cols, rowset):
   """bool [B, rows, cols, H]: keep(b, h, i, col) for one row set (0 = dense / long rows, 1 = global
   rows); ``cols`` indexes the row's concatenated key axis (segment 0 first)."""
@@ -30,4 +38,4 @@ def keep_mask(seed, p, batch, heads, rows, cols, rowset):
   i = np.arange(rows, dtype=np.uint64)[None, :, None, None]
   c = np.arange(cols, dtype=np.uint64)[None, None, :, None]
   x = (salt[:, None, None, :] + i * np.uint64(0x00010001) + c) & _M
-  return mix32(x) >= thr
+  return mix_elem(x) >= thr
