@@ -51,7 +51,8 @@ class MmtEncoder(nn.Module):
                relative_pos_max_distance: int = 12, initializer_range: float = 0.02,
                use_pre_activation_order: bool = False, use_one_hot_lookup: bool = True,
                use_pooler_layer: bool = False, patch_embedding_size: int = 768,
-               local_radius: Optional[int] = None, num_global_tokens: int = 0, impl: str = 'auto'):
+               local_radius: Optional[int] = None, num_global_tokens: int = 0, impl: str = 'auto',
+               recognize_side_inputs: bool = True, id_layout_hint=None):
     super().__init__()
     # reference mmt_encoder.py:69-80
     if relative_vocab_size is None:
@@ -82,11 +83,17 @@ class MmtEncoder(nn.Module):
                   attention_probs_dropout_prob=attention_probs_dropout_prob,
                   initializer_range=initializer_range, relative_vocab_size=relative_vocab_size,
                   use_pre_activation_order=use_pre_activation_order,
-                  use_one_hot_lookup=use_one_hot_lookup, impl=impl)
+                  use_one_hot_lookup=use_one_hot_lookup, impl=impl,
+                  recognize_side_inputs=recognize_side_inputs)
+    # Additive fields (not in the reference): explicit [B,S,S] side inputs are checked once per call against the
+    # compact rules and, when reproduced exactly, replaced by descriptors for all layers (layers.py);
+    # `id_layout_hint` = (num_patch_per_row, num_core_layers, max_distance) names the 2-D layout of the data
+    # pipeline (reference src/feature_utils.py:29-255) to check the ids against.
     if local_radius is None:
       self.transformer_layers = layers.RelativeTransformerLayers(
           hidden_size=hidden_size, num_hidden_layers=num_hidden_layers,
-          num_attention_heads=num_attention_heads, intermediate_size=intermediate_size, **common)
+          num_attention_heads=num_attention_heads, intermediate_size=intermediate_size,
+          id_layout_hint=id_layout_hint, **common)
     else:
       if num_global_tokens < 1:
         raise ValueError('`num_global_tokens` must be positive when `local_radius` is set.')

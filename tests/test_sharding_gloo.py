@@ -31,7 +31,7 @@ def test_two_rank_partition_and_timing_reduction(tmp_path):
   script = tmp_path / 'worker.py'
   script.write_text(WORKER)
   env = dict(os.environ, MLT_ROOT=ROOT)
-  for attempt in range(2):      # the probed port can be taken between the probe and the rendezvous: one retry
+  for attempt in range(3):      # the probed port can be taken between the probe and the rendezvous: retried
     with socket.socket() as s:
       s.bind(('127.0.0.1', 0))
       port = s.getsockname()[1]

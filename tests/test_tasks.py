@@ -116,7 +116,7 @@ dist.destroy_process_group()
 def test_gradient_allreduce_keeps_replicas_identical(tmp_path):
   script = tmp_path / 'worker.py'
   script.write_text(WORKER)
-  for attempt in range(2):      # the probed port can be taken between the probe and the rendezvous: one retry
+  for attempt in range(3):      # the probed port can be taken between the probe and the rendezvous: retried
     with socket.socket() as s:
       s.bind(('127.0.0.1', 0))
       port = s.getsockname()[1]
