@@ -46,7 +46,8 @@ constexpr int SM_CMB = SM_A + TM * 128;               // class sums of column gr
 constexpr int SM_BS = SM_CMB + 3 * 4 * TM * 4;        // bias partial sums [4 quadrants][32]
 constexpr int SM_BIAS = SM_BS + 4 * 32 * 4;           // [32] bias * scale * log2e
 constexpr int SM_BAR = SM_BIAS + 32 * 4;
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_SCHED = SM_BAR + 256;                // ring of tile descriptors {t, b, h, tile} (16 B each)
+constexpr int SM_TOTAL = SM_SCHED + 64;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;
 static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
 
@@ -93,16 +94,17 @@ struct Bars {
   uint64_t rel_full, s_full[2], dp_full, ds_full, dar_full, dq_full, tile_done;
   uint64_t sched_full[NSQ], sched_empty[NSQ];
   uint32_t tmem_base;
-  int32_t sched_tile[NSQ];
 };
+// The producer thread decodes the tile number once (two integer divisions) and publishes {t, b, h, tile};
+// t < 0 ends the loop.
 template <bool WARP>
-__device__ __forceinline__ int sched_take(Bars* bars, int it, bool lane0) {
+__device__ __forceinline__ int4 sched_take(Bars* bars, const int4* ring, int it, bool lane0) {
   const int sq = it % NSQ;
   mbar_wait(&bars->sched_full[sq], (it / NSQ) & 1);
-  const int t = *reinterpret_cast<volatile int32_t*>(&bars->sched_tile[sq]);
+  const int4 e = ring[sq];
   if (WARP) __syncwarp();   // every lane has read the entry
   if (lane0) mbar_arrive(&bars->sched_empty[sq]);
-  return t;
+  return e;
 }
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -117,6 +119,15 @@ __device__ __forceinline__ Tile make_tile(const Params& p, int t) {
   q.h = bh - q.b * p.H;
   q.tile = t - bh * p.tiles_per_bh;
   q.i0 = q.tile * TM;
+  q.nglob = (p.G + TK - 1) / TK;
+  return q;
+}
+__device__ __forceinline__ Tile tile_of(const Params& p, const int4& e) {   // from a published descriptor
+  Tile q;
+  q.b = e.y;
+  q.h = e.z;
+  q.tile = e.w;
+  q.i0 = e.w * TM;
   q.nglob = (p.G + TK - 1) / TK;
   return q;
 }
@@ -140,6 +151,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int4* ring = reinterpret_cast<int4*>(smem + SM_SCHED);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -183,10 +195,11 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         if (t >= p.total_tiles) t = -1;
         const int sq = it % NSQ;
         mbar_wait(&bars->sched_empty[sq], ((it / NSQ) & 1) ^ 1);
-        bars->sched_tile[sq] = t;
+        Tile q{};
+        if (t >= 0) q = make_tile(p, t);
+        ring[sq] = make_int4(t, q.b, q.h, q.tile);
         mbar_arrive(&bars->sched_full[sq]);
         if (t < 0) break;
-        const Tile q = make_tile(p, t);
         mbar_arrive_expect_tx(&bars->q_full[buf], 2 * TM * 128 + 32 * 128);
         uint8_t* qs = smem + SM_Q + buf * 2 * TM * 128;
         tma_load_4d(qs, &map_q, &bars->q_full[buf], 0, q.i0, q.h, q.b);
@@ -252,10 +265,10 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           umma_ss(tmem + T_DP, sdesc(do_addr).at(kk * 32), sdesc(v_addr).at(kk * 32), idesc_s, kk > 0);
         umma_commit(&bars->dp_full);
       };
-      int t = sched_take<false>(bars, 0, true);
-      if (t >= 0) start_tile(0, 0);
-      for (; t >= 0; ++it) {
-        const Tile q = make_tile(p, t);
+      int4 te = sched_take<false>(bars, ring, 0, true);
+      if (te.x >= 0) start_tile(0, 0);
+      for (; te.x >= 0; ++it) {
+        const Tile q = tile_of(p, te);
         const int buf = it & 1;
         const int nc = 2 + q.nglob;
         const uint32_t q_addr = smem_u32(smem + SM_Q + buf * 2 * TM * 128), do_addr = q_addr + TM * 128;
@@ -307,8 +320,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         kv_base += nc;
         // next tile's prologue under this tile's epilogue: allrel -> the other buffer, S_0 -> S0 (free since the
         // last even chunk), dP_0 -> dP (its dS was consumed by the dQ MMAs above: MMAs execute in issue order)
-        t = sched_take<false>(bars, it + 1, true);
-        if (t >= 0) start_tile(it + 1, kv_base);
+        te = sched_take<false>(bars, ring, it + 1, true);
+        if (te.x >= 0) start_tile(it + 1, kv_base);
       }
     }
   } else {
@@ -330,11 +343,11 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // row scalars of a tile (example id, sentence, forward statistics): loaded one tile ahead, under the
     // epilogue of the previous tile
     struct RowPre { int q_e, q_sent; float4 rs4; };
-    auto row_pre = [&](int t_) {
+    auto row_pre = [&](const int4& te_) {
       RowPre r;
       r.q_e = -2; r.q_sent = -1; r.rs4 = make_float4(0.f, 1.f, 0.f, 0.f);
-      if (t_ >= 0) {
-        const Tile q_ = make_tile(p, t_);
+      if (te_.x >= 0) {
+        const Tile q_ = tile_of(p, te_);
         const int i_ = q_.i0 + row;
         if (i_ < p.L) {
           r.q_e = __ldg(p.long_eid + (int64_t)q_.b * p.L + i_);
@@ -344,10 +357,10 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       return r;
     };
-    int t = sched_take<true>(bars, 0, lane == 0);
-    RowPre pre = row_pre(t);
-    for (; t >= 0; ++it) {
-      const Tile q = make_tile(p, t);
+    int4 te = sched_take<true>(bars, ring, 0, lane == 0);
+    RowPre pre = row_pre(te);
+    for (; te.x >= 0; ++it) {
+      const Tile q = tile_of(p, te);
       const int b = q.b, h = q.h;
       const int i = q.i0 + row;
       const bool row_ok = i < p.L;
@@ -623,8 +636,8 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       named_bar_sync(1, NEW);   // bins complete
       if (tid == 0) GTRACE(0, 40);
-      const int t_next = sched_take<true>(bars, (int)it + 1, lane == 0);
-      const RowPre pre_next = row_pre(t_next);
+      const int4 te_next = sched_take<true>(bars, ring, (int)it + 1, lane == 0);
+      const RowPre pre_next = row_pre(te_next);
       {
         // each of the four column groups packs 8 ids: bf16 A operand (TMEM) for dQ += dallrel.E, the
         // dallrel^T tile for the table-gradient MMA, and the bias partial sums of the warp's 32 rows
@@ -715,7 +728,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tc_fence_before_sync();
       mbar_arrive(&bars->tile_done);
       if (tid == 0) GTRACE(0, 43);
-      t = t_next;
+      te = te_next;
       pre = pre_next;
     }
   }

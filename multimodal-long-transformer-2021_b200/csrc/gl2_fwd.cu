@@ -50,7 +50,8 @@ constexpr int SM_REL = SM_KV + NST * 2 * TK * 128;    // [2 tiles][32 slots][128
 constexpr int SM_BIAS = SM_REL + 2 * 32 * TM * 4;     // [2 tiles][32] f32
 constexpr int SM_XCH = SM_BIAS + 2 * 32 * 4;          // [2 parities][2 tiles][2 halves][128 rows] f32: pair exchange
 constexpr int SM_BAR = SM_XCH + 2 * 2 * 2 * TM * 4;
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_SCHED = SM_BAR + 256;                // ring of pair descriptors {pair, b, h, i0} (16 B each)
+constexpr int SM_TOTAL = SM_SCHED + 64;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;
 
 constexpr uint32_t T_WG = 224;   // TMEM columns per warpgroup
@@ -91,17 +92,17 @@ struct Bars {
   uint64_t rel_full[2], s_full[2], p_full[2], o_full[2], o_empty[2];
   uint64_t sched_full[NSQ], sched_empty[NSQ];
   uint32_t tmem_base;
-  int32_t sched_pair[NSQ];
 };
-// consumer side of the pair ring: a whole (converged) warp, one arrival -- or a single elected thread
+// consumer side of the pair ring: a whole (converged) warp, one arrival -- or a single elected thread.  The
+// producer thread decodes the pair number once (two integer divisions) and publishes {pair, b, h, i0}.
 template <bool WARP>
-__device__ __forceinline__ int sched_take(Bars* bars, int it, bool lane0) {
+__device__ __forceinline__ int4 sched_take(Bars* bars, const int4* ring, int it, bool lane0) {
   const int sq = it % NSQ;
   mbar_wait(&bars->sched_full[sq], (it / NSQ) & 1);
-  const int pair = *reinterpret_cast<volatile int32_t*>(&bars->sched_pair[sq]);
+  const int4 e = ring[sq];
   if (WARP) __syncwarp();   // every lane has read the entry
   if (lane0) mbar_arrive(&bars->sched_empty[sq]);
-  return pair;
+  return e;
 }
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -123,6 +124,16 @@ __device__ __forceinline__ Pair make_pair(const Params& p, int pair) {
   q.b = bh / p.H;
   q.h = bh - q.b * p.H;
   q.i0 = (pair - bh * p.pairs_per_bh) * (2 * TM);
+  q.nglob = (p.G + TK - 1) / TK;
+  q.has[0] = true;
+  q.has[1] = q.i0 + TM < p.L;
+  return q;
+}
+__device__ __forceinline__ Pair pair_of(const Params& p, const int4& e) {   // from a published descriptor
+  Pair q;
+  q.b = e.y;
+  q.h = e.z;
+  q.i0 = e.w;
   q.nglob = (p.G + TK - 1) / TK;
   q.has[0] = true;
   q.has[1] = q.i0 + TM < p.L;
@@ -154,6 +165,7 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int4* ring = reinterpret_cast<int4*>(smem + SM_SCHED);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -198,10 +210,11 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if (pair >= p.total_pairs) pair = -1;
         const int sq = it % NSQ;
         mbar_wait(&bars->sched_empty[sq], ((it / NSQ) & 1) ^ 1);
-        bars->sched_pair[sq] = pair;
+        Pair q{};
+        if (pair >= 0) q = make_pair(p, pair);
+        ring[sq] = make_int4(pair, q.b, q.h, q.i0);
         mbar_arrive(&bars->sched_full[sq]);
         if (pair < 0) break;
-        const Pair q = make_pair(p, pair);
         mbar_arrive_expect_tx(&bars->q_full[buf], 2 * TM * 128 + 32 * 128);
         tma_load_4d(smem + SM_Q + (buf * 2 + 0) * TM * 128, &map_q, &bars->q_full[buf], 0, q.i0, q.h, q.b);
         tma_load_4d(smem + SM_Q + (buf * 2 + 1) * TM * 128, &map_q, &bars->q_full[buf], 0, q.i0 + TM, q.h, q.b);
@@ -243,9 +256,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       uint32_t p_cnt[2] = {0, 0};    // P chunks consumed per tile slot
       uint32_t tile_cnt[2] = {0, 0}; // tiles started per slot
       for (;; ++it) {
-        const int pair = sched_take<false>(bars, it, true);
-        if (pair < 0) break;
-        const Pair q = make_pair(p, pair);
+        const int4 pe = sched_take<false>(bars, ring, it, true);
+        if (pe.x < 0) break;
+        const Pair q = pair_of(p, pe);
         const int buf = it & 1;
         const int npc = NBAND + q.nglob;
         mbar_wait(&bars->q_full[buf], (it >> 1) & 1);
@@ -347,9 +360,9 @@ gl2_fwd_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #define ST(code) do {} while (0)
 #endif
     for (int sit = 0;; ++sit) {
-      const int pair = sched_take<true>(bars, sit, lane == 0);
-      if (pair < 0) break;
-      const Pair q = make_pair(p, pair);
+      const int4 pe = sched_take<true>(bars, ring, sit, lane == 0);
+      if (pe.x < 0) break;
+      const Pair q = pair_of(p, pe);
       if (!tile_exists(q, w)) continue;
       const int b = q.b, h = q.h;
       const int ti0 = q.i0 + w * TM;         // first row of this tile
