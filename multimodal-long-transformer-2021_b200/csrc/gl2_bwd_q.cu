@@ -298,13 +298,18 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_wait(&bars->ds_full, ds_cnt & 1);
           ++ds_cnt;
           tc_fence_after_sync();
+          // dS_c sits in the chunk's own S buffer (its scores are spent), so the dP columns are free once dS_c has
+          // arrived: dP_{c+1} goes first and runs under the dQ MMAs.  (Issuing it as soon as dP_c has been READ
+          // would need two-deep dS / dP hand-over barriers: a warp whose group is dead could otherwise arrive
+          // twice in one phase.  Tried, deadlocked, not pursued: the remaining dP wait is ~4 % of the samples.)
+          if (c + 1 < nc) issue_dp(c + 1);
           const uint32_t k_addr = kv_addr(c);
+          const uint32_t t_ds = tmem + ((c & 1) ? T_S1 : T_S0);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // dQ += dS_c . K_c  (dS packed per 32-key group at columns [32g, 32g + 16))
-            umma_ts(tmem + T_DQ, tmem + T_DP + (kk >> 1) * 32 + (kk & 1) * 8, sdesc(k_addr).at(kk * 2048), idesc_dq,
+            umma_ts(tmem + T_DQ, t_ds + (kk >> 1) * 32 + (kk & 1) * 8, sdesc(k_addr).at(kk * 2048), idesc_dq,
                     (c > 0 || kk > 0));
           umma_commit(&bars->kv_empty[(kv_base + c) % NST]);
-          if (c + 1 < nc) issue_dp(c + 1);
         }
         // dQ += dallrel . E ; table-gradient partial dE[64 ids x 64] = dallrel^T . Q (M = 64, K = the tile's rows)
         mbar_wait(&bars->dar_full, it & 1);
@@ -461,7 +466,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           if (fm == 0) {
 #pragma unroll
             for (int x = 0; x < 16; ++x) pk[x] = 0u;
-            if (!dp_ready) {   // the dS columns may only be written once dP of the chunk has landed
+            if (!dp_ready) {   // keeps this warp inside the chunk: it must not reach the next hand-over early
               mbar_wait_warp(&bars->dp_full, dp_par);
               tc_fence_after_sync();
               dp_ready = true;
@@ -607,7 +612,7 @@ gl2_bwd_q_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             }
           }
           __syncwarp();   // the per-lane bin stores may leave the warp diverged
-          tmem_st16(t_dp + 32 * g, pk);
+          tmem_st16(t_s + 32 * g, pk);   // dS over the group's own (spent) scores
         }
         dp_par ^= 1;
         tmem_wait_st();
