@@ -223,15 +223,21 @@ class _GlobalLocalAttnFn(torch.autograd.Function):
      gr.d_global_v) = map(_t4, grads)
     tab = [None] * 4
     if r_vocab > 0:
-      f32 = dict(dtype=torch.float32, device=lq.device)
-      tab = [torch.empty((r_vocab, h, d), **f32), torch.empty((r_vocab, h), **f32),
-             torch.empty((r_vocab, h, d), **f32), torch.empty((r_vocab, h), **f32)]
+      # one flat fp32 buffer, four views: a single conversion launch hands them back in the tables' dtype
+      sizes = [r_vocab * h * d, r_vocab * h, r_vocab * h * d, r_vocab * h]
+      shapes = [(r_vocab, h, d), (r_vocab, h), (r_vocab, h, d), (r_vocab, h)]
+      flat = torch.empty(sum(sizes), dtype=torch.float32, device=lq.device)
+      tab = [v.view(sh) for v, sh in zip(flat.split(sizes), shapes)]
       gr.d_long_emb, gr.d_long_bias, gr.d_global_emb, gr.d_global_bias = (
           t.data_ptr() for t in tab)
     with torch.cuda.device(lq.device):
       _lib.check(lib.mlt_gl_attn_bwd(C.byref(p), C.byref(gr), _stream(lq.device)), 'mlt_gl_attn_bwd')
     if r_vocab > 0:   # table gradients are accumulated in fp32; hand them back in the tables' own dtype
-      tab = [t.to(dt) for t, dt in zip(tab, ctx.table_dtypes)]
+      if len(set(ctx.table_dtypes)) == 1:
+        if ctx.table_dtypes[0] != torch.float32:
+          tab = [v.view(sh) for v, sh in zip(flat.to(ctx.table_dtypes[0]).split(sizes), shapes)]
+      else:
+        tab = [t.to(dt) for t, dt in zip(tab, ctx.table_dtypes)]
     return (*grads, *tab, None)
 
 
