@@ -64,8 +64,8 @@ __global__ void recog_finish_kernel(int32_t* res) { res[0] = res[2] == 0 ? 1 : 0
 // (a label no other token carries).  `through` (optional) maps the index to the label of that column's token.
 // hit[b, i] (optional) = first column whose ids entry equals res[1] * 2 + 2, else -1.  One warp per row.
 // band (optional, [B, rows, 2 * radius + 1]): a row without any hit in `mask` takes the label of the first
-// row it sees through the band instead (long tokens of an example that owns no global token, e.g. a short
-// padding tail: they still see one another).
+// token of its block instead, found by walking the band towards earlier tokens (long tokens of an example
+// that owns no global token, e.g. a padding tail: they still see one another).
 __global__ void first_hit_rows_kernel(const int32_t* mask, const int32_t* ids, int B, int rows, int cols,
                                       const int32_t* through, int through_len, int unique_offset,
                                       int32_t* label, int32_t* hit, const int32_t* res,
@@ -90,15 +90,23 @@ __global__ void first_hit_rows_kernel(const int32_t* mask, const int32_t* ids, i
     }
     int peer = i;
     if (first < 0 && band) {
+      // walk towards the start of the block: the first token this one sees, the first token THAT one sees, ...
+      // (a block longer than the window needs more than one step; warp-uniform loop, bounded by the row length)
       const int bw = 2 * radius + 1;
-      for (int c0 = 0; c0 < bw; c0 += 32) {
-        const int c = c0 + lane;
-        const bool m = c < bw && __ldg(band + r * bw + c) != 0;
-        const unsigned bm = __ballot_sync(0xffffffffu, m);
-        if (bm) {
-          peer = i + c0 + __ffs(bm) - 1 - radius;
-          break;
+      for (int step = 0; step < rows; ++step) {
+        int nxt = peer;
+        const int64_t pr = (int64_t)b * rows + peer;
+        for (int c0 = 0; c0 < bw; c0 += 32) {
+          const int c = c0 + lane;
+          const bool m = c < bw && __ldg(band + pr * bw + c) != 0;
+          const unsigned bm = __ballot_sync(0xffffffffu, m);
+          if (bm) {
+            nxt = peer + c0 + __ffs(bm) - 1 - radius;
+            break;
+          }
         }
+        if (nxt >= peer || nxt < 0) break;   // sees nothing earlier (or a malformed mask): this is the block's first token
+        peer = nxt;
       }
     }
     if (lane == 0) {

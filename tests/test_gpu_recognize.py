@@ -164,3 +164,37 @@ def test_stacks_give_the_same_results_from_explicit_tensors():
     c = dense(x, att_mask=mask, relative_att_ids=ids)
   assert torch.equal(a, b)
   assert (a.float() - c.float()).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_gl_recognition_random_packings(seed):
+  """Random packings: 1-4 examples per row of random lengths, each owning a random number of global tokens,
+  random padding tail, random radius / distance.  Generator-shaped inputs are always recognised and the
+  descriptors always rebuild the very same eight tensors."""
+  g = torch.Generator().manual_seed(1000 + seed)
+  ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+  batch, long_len, global_len = ri(1, 3), 32 * ri(3, 12), ri(4, 24)
+  radius, dist = ri(1, 40), ri(1, 9)
+  le = torch.zeros(batch, long_len, dtype=torch.int32)
+  ge = torch.zeros(batch, global_len, dtype=torch.int32)
+  sid = torch.full((batch, long_len), -1, dtype=torch.int32)
+  for b in range(batch):
+    n_ex = ri(1, min(4, global_len))
+    lcuts = sorted(torch.randperm(long_len - 1, generator=g)[:n_ex].add(1).tolist()) + [long_len]
+    gcuts = sorted(torch.randperm(global_len - 1, generator=g)[:n_ex - 1].add(1).tolist()) + [global_len]
+    lo = go = 0
+    for e in range(n_ex):                     # example e: long tokens [lo, lcuts[e]), global tokens [go, gcuts[e])
+      le[b, lo:lcuts[e]] = 11 + 3 * e
+      ge[b, go:gcuts[e]] = 11 + 3 * e
+      span, ng = lcuts[e] - lo, gcuts[e] - go
+      for t in range(span):                   # sentences of the example: its long tokens spread over its global tokens
+        sid[b, lo + t] = go + min(ng - 1, t * ng // max(span, 1))
+      lo, go = lcuts[e], gcuts[e]
+  compact = fu.CompactSideInputs(le.to(DEV), ge.to(DEV), sid.to(DEV), dist)
+  explicit = ops.build_gl_side_inputs(compact, radius)
+  got = ops.compact_from_explicit_gl(explicit, radius)
+  assert got is not None, (batch, long_len, global_len, radius, dist)
+  assert got.relative_pos_max_distance == dist
+  again = ops.build_gl_side_inputs(got, radius)
+  for k, v in explicit.items():
+    assert torch.equal(v, again[k]), k
