@@ -198,3 +198,35 @@ def test_gl_recognition_random_packings(seed):
   again = ops.build_gl_side_inputs(got, radius)
   for k, v in explicit.items():
     assert torch.equal(v, again[k]), k
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_dense_recognition_random_segments(seed):
+  """Random segmentations of the sequence (1-5 segments + optional padding), 1-D rule with a random distance and
+  the 2-D layout with a random patch grid: recognised, and the descriptors rebuild the very same tensors."""
+  g = torch.Generator().manual_seed(2000 + seed)
+  ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+  batch, seq = ri(1, 4), ri(40, 300)
+  eid = torch.zeros(batch, seq, dtype=torch.int32)
+  for b in range(batch):
+    cuts = sorted(torch.randperm(seq - 1, generator=g)[:ri(1, 5)].add(1).tolist()) + [seq]
+    lo = 0
+    for e, hi in enumerate(cuts[:-1] if ri(0, 1) else cuts):      # sometimes the last piece stays padding (id 0)
+      eid[b, lo:hi] = 5 + 2 * e
+      lo = hi
+  eid = eid.to(DEV)
+  dist = ri(1, 15)
+  mask, ids = ops.build_dense_side_inputs(eid, dist)
+  got = ops.compact_from_explicit_dense(mask, ids)
+  assert got is not None and got.max_distance == dist
+  m2, i2 = ops.build_dense_side_inputs(got.q_example_ids, dist)
+  assert torch.equal(m2, mask) and torch.equal(i2, ids)
+  npr = ri(2, 6)
+  if npr * npr <= seq:
+    core = ri(1, 3)
+    mask, ids = ops.build_dense_side_inputs(eid, dist, num_patch_per_row=npr, num_core_layers=core)
+    got = ops.compact_from_explicit_dense(mask, ids, npr, core, dist)
+    assert got is not None
+    m2, i2 = ops.build_dense_side_inputs(got.q_example_ids, dist, npr, core)
+    assert torch.equal(m2, mask) and torch.equal(i2, ids)
+    assert ops.compact_from_explicit_dense(mask, ids, npr, core, dist + 1) is None
